@@ -1,0 +1,63 @@
+// Shared device/host helpers for the conan_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/conan_b200.h"
+
+namespace conan {
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define CONAN_CUDA_OK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      conan::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+
+#define CONAN_CHECK_LAUNCH()                                                         \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      conan::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + \
+                       " at " + __FILE__ + ":" + std::to_string(__LINE__));          \
+      return 1;                                                                      \
+    }                                                                                \
+    conan::count_launch();                                                           \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_GELU = 3, ACT_TANH = 4 };
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_LRELU: return v > 0.f ? v : v * slope;
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact-erf GELU (nn.GELU default)
+    case ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// launchers implemented in the .cu files
+int launch_conv_gemm_ffma(const conan_conv_params_t& p, cudaStream_t st);
+int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st);
+bool conv_gemm_tc_eligible(const conan_conv_params_t& p);
+
+}  // namespace conan

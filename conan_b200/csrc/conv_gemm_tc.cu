@@ -1,0 +1,419 @@
+// Implicit-GEMM causal Conv1d on the 5th-generation tensor cores (sm_100a: tcgen05 + TMEM + TMA).
+//
+//   D[m, n] = sum_kk A[m, kk] * W[n, kk],  M = n_streams * L, N = cout, K = k * cin (tap-major)
+//   A[m, j*cin + c] = X[slot(m), row0 + t(m) + j*dil, c]
+//
+// The vocoder keeps the input of every causal conv in a per-slot fp16 context buffer
+// [slot, H + L, cin] (H history rows + the L rows of this chunk), so for one tap j and one
+// 64-channel slice the 128 A rows of a tile are contiguous row ranges of that buffer: the
+// producer warp fetches them with TMA boxes {BK channels, TT rows, 1 slot} (TT = largest
+// power of two <= 128 dividing L, 128/TT boxes per tile, each box with its own slot from the
+// ready list) straight into the 128B-swizzled K-major layout tcgen05.mma reads.  No im2col
+// buffer exists anywhere; dilation is a row offset of the box.  Weights are pre-packed
+// [cout, k*cin] fp16 and fetched as {BK, BN} boxes.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (one TMEM lane quarter each).  The fp32 accumulator tile
+// 128 x BN lives in TMEM; the epilogue reads it with tcgen05.ld 32x32b and applies the fused
+// chain of the path: bias, scale, activation, residual add (fp32 stream), row mask, MRF
+// 1/3 scale + accumulate, then writes the fp32 stream and/or the LeakyReLU'd fp16 copy that is
+// the next conv's context buffer (pixel shuffle is folded into the weight row order, so an
+// upsampling conv is just this kernel with a wider output row).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace conan {
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_SUB = 32;
+
+struct TcEpi {
+  const float* bias; float scale; int act; float slope;
+  const float* res; long long res_slot_stride; int res_row_stride;
+  const float* rowmask; int mask_slot_stride; float out_scale;
+  float* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
+  __half* y2; long long y2_slot_stride; int y2_row_stride, y2_row0; int act2; float slope2;
+};
+
+struct TcArgs {
+  int n_streams, L, TT, cin, k, dil, cout, row0;
+  int kblocks;               // k * cin / BK
+  int n_tiles;               // cout / BN
+  const int* slot_ids;
+  TcEpi e;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (= 1 for swizzled K-major), [32,46) SBO >> 4
+//   (8 rows * swizzle span), [46,48) version = 1, [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2 : 4;
+  constexpr uint64_t sbo = (8 * SWIZZLE_BYTES) >> 4;
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | (sbo << 32) | ((uint64_t)1 << 46) | (layout << 61);
+}
+
+// instruction descriptor for kind::f16: fp16 A/B (K-major), fp32 accumulate, M = 128, N = BN
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+template <int BN, int BK, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = TILE_M * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/;
+};
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
+  using SL = SmemLayout<BN, BK, STAGES>;
+  constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SL::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  __shared__ int s_slot[MAX_SUB], s_t0[MAX_SUB], s_valid[MAX_SUB];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % a.n_tiles, mt = blockIdx.x / a.n_tiles;
+  const int NSUB = TILE_M / a.TT, TPS = a.L / a.TT;
+
+  if (threadIdx.x < NSUB) {
+    int g = mt * NSUB + threadIdx.x;
+    int i = g / TPS;
+    int ok = i < a.n_streams;
+    int ic = ok ? i : a.n_streams - 1;
+    s_slot[threadIdx.x] = a.slot_ids ? a.slot_ids[ic] : ic;
+    s_t0[threadIdx.x] = (g % TPS) * a.TT;
+    s_valid[threadIdx.x] = ok;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      const int kb_per_tap = a.cin / BK;
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * SL::STAGE_BYTES;
+        uint8_t* sb = sa + SL::A_BYTES;
+        mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
+        const int j = kb / kb_per_tap, c0 = (kb - j * kb_per_tap) * BK;
+        for (int q = 0; q < NSUB; ++q)
+          tma_load_3d(sa + q * a.TT * SWZ, &tmA, &full_bar[s], c0, a.row0 + s_t0[q] + j * a.dil, s_slot[q]);
+        tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+        const uint32_t sb = sa + SL::A_BYTES;
+        const uint64_t adesc = make_smem_desc<SWZ>(sa), bdesc = make_smem_desc<SWZ>(sb);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          // advance 16 halfs = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);            // frees the smem stage when these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);              // accumulator complete
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;       // tile row == TMEM lane
+    const int q = r / a.TT, tt = r - q * a.TT;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool valid = s_valid[q] != 0;
+    const int slot = s_slot[q];
+    const int t = s_t0[q] + tt;
+    const TcEpi& e = a.e;
+    const float rm = (e.rowmask && valid) ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
+    const int nbase = nt * BN;
+    const float* resp = e.res ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
+    float* yp = e.y ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
+    __half* y2p = e.y2 ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t acc[32];
+      tc_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+        if (e.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + c0 + i));
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i] * e.scale, e.act, e.slope);
+        if (resp) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 rr = *reinterpret_cast<const float4*>(resp + c0 + i);
+            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+          }
+        }
+        const float f = rm * e.out_scale;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= f;
+        if (yp) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4* dst = reinterpret_cast<float4*>(yp + c0 + i);
+            if (e.accumulate) { float4 o = *dst; v[i] += o.x; v[i + 1] += o.y; v[i + 2] += o.z; v[i + 3] += o.w; }
+            *dst = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        if (y2p) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __half2 h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              h[u] = __floats2half2_rn(apply_act(v[i + 2 * u], e.act2, e.slope2), apply_act(v[i + 2 * u + 1], e.act2, e.slope2));
+            *reinterpret_cast<uint4*>(y2p + c0 + i) = *reinterpret_cast<uint4*>(h);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; unsigned long long d0, d1, d2, s1, s2; unsigned b0, b1, b2, swz;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b0 == o.b0 && b1 == o.b1 &&
+           b2 == o.b2 && swz == o.swz;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    for (unsigned long long v : {k.d0, k.d1, k.d2, k.s1, k.s2, (unsigned long long)k.b0, (unsigned long long)k.b1,
+                                 (unsigned long long)k.b2, (unsigned long long)k.swz})
+      h = h * 1000003ull ^ (size_t)v;
+    return h;
+  }
+};
+
+int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                   unsigned long long s1_bytes, unsigned long long s2_bytes, unsigned b0, unsigned b1, unsigned b2, int swz_bytes) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, d0, d1, d2, s1_bytes, s2_bytes, b0, b1, b2, (unsigned)swz_bytes};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return 1; }
+  cache.emplace(key, m);
+  *out = m;
+  return 0;
+}
+
+int pick_tt(int L) {
+  for (int tt = 128; tt >= 4; tt >>= 1)
+    if (L % tt == 0) return tt;
+  return 0;
+}
+int pick_bn(int cout) {
+  if (cout % 128 == 0) return 128;
+  if (cout % 64 == 0) return 64;
+  if (cout % 32 == 0) return 32;
+  return 0;
+}
+
+template <int BN, int BK, int STAGES>
+int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcArgs& a, long long m_tiles, cudaStream_t st) {
+  using SL = SmemLayout<BN, BK, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  conv_gemm_tc_kernel<BN, BK, STAGES><<<(unsigned)(m_tiles * a.n_tiles), NUM_THREADS, SL::TOTAL, st>>>(tmA, tmW, a);
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
+  if (!p.x_is_half) return false;
+  if (p.y2 && !p.y2_is_half) return false;
+  if (p.cin % 32 != 0 || p.x_row_stride != p.cin) return false;
+  if (pick_bn(p.cout) == 0 || pick_tt(p.L) == 0) return false;
+  if (p.row0 < 0) return false;
+  if (p.y && (p.y_slot_stride % 4 || p.y_row_stride % 4)) return false;
+  if (p.res && (p.res_slot_stride % 4 || p.res_row_stride % 4)) return false;
+  if (p.y2 && (p.y2_slot_stride % 8 || p.y2_row_stride % 8)) return false;
+  if (((uintptr_t)p.x) % 128 || ((uintptr_t)p.w) % 128) return false;
+  return true;
+}
+
+int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
+  if (!conv_gemm_tc_eligible(p)) { set_error("conv_gemm_tc: not eligible"); return 1; }
+  if (p.n_streams <= 0) return 0;
+  const int BK = (p.cin % 64 == 0) ? 64 : 32;
+  const int BN = pick_bn(p.cout);
+  const int TT = pick_tt(p.L);
+  const int Ktot = p.k * p.cin;
+  CUtensorMap tmA, tmW;
+  if (get_tensor_map(&tmA, p.x, 3, (unsigned long long)p.cin, (unsigned long long)p.x_rows, (unsigned long long)p.n_slots,
+                     (unsigned long long)p.x_row_stride * 2, (unsigned long long)p.x_slot_stride * 2, BK, TT, 1, BK * 2))
+    return 1;
+  if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, BN, 1,
+                     BK * 2))
+    return 1;
+  TcArgs a;
+  a.n_streams = p.n_streams; a.L = p.L; a.TT = TT; a.cin = p.cin; a.k = p.k; a.dil = p.dil; a.cout = p.cout; a.row0 = p.row0;
+  a.kblocks = Ktot / BK; a.n_tiles = p.cout / BN; a.slot_ids = p.slot_ids;
+  a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
+              p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
+              p.y2_row_stride, p.y2_row0, p.act2, p.slope2};
+  const long long M = (long long)p.n_streams * p.L;
+  const long long m_tiles = (M + TILE_M - 1) / TILE_M;
+  if (BK == 64) {
+    if (BN == 128) return launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
+    if (BN == 64) return launch_variant<64, 64, 4>(tmA, tmW, a, m_tiles, st);
+    return launch_variant<32, 64, 4>(tmA, tmW, a, m_tiles, st);
+  }
+  if (BN == 128) return launch_variant<128, 32, 4>(tmA, tmW, a, m_tiles, st);
+  if (BN == 64) return launch_variant<64, 32, 4>(tmA, tmW, a, m_tiles, st);
+  return launch_variant<32, 32, 4>(tmA, tmW, a, m_tiles, st);
+}
+
+}  // namespace conan

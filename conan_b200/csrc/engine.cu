@@ -1,0 +1,851 @@
+// The resident-state engine behind the C ABI (include/conan_b200.h).
+//
+// State lives in HBM as a slab of per-slot buffers (struct-of-arrays: one allocation per
+// logical tensor, `max_slots` slots each):
+//   * Emformer: K|V ring per layer [slot, ring_rows, 2D] + past_len[slot]
+//   * Conan   : causal "context buffers" [slot, H + L, C] in front of every causal conv
+//               (H = (k-1)*dil zero-initialised history rows, L = rows produced per chunk),
+//               per-session style vector and aligner K/V cache
+//   * vocoder : the same context buffers, fp16 (tensor-core operand type) or fp32
+// A chunk step runs every layer over the n ready streams named by slot_ids (one launch per
+// layer, the slot indirection is resolved inside the kernels), then one ring-shift kernel per
+// sub-model moves the last H rows of every context buffer to its front.
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <cmath>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace conan {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+struct Ctx {                 // context buffer [slot, H + L + R, C]
+  void* p = nullptr;
+  int H = 0, L = 0, R = 0, C = 0, is_half = 0;
+  int rows() const { return H + L + R; }
+  long long slot_stride() const { return (long long)rows() * C; }
+  size_t elem() const { return is_half ? 2 : 4; }
+  RowView new_rows() const { return RowView{p, slot_stride(), C, H, is_half}; }
+  void* at_row(int r) const { return (char*)p + (size_t)r * C * elem(); }
+};
+
+struct WeightSlot { std::string name; size_t numel; int dtype; const void* ptr; };
+
+}  // namespace conan
+
+using namespace conan;
+
+struct conan_engine {
+  conan_config_t cfg;
+  std::vector<WeightSlot> weights;
+  std::unordered_map<std::string, int> windex;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  size_t state_bytes = 0;
+  int S = 0, tp_max = 0;
+  // ---- Emformer
+  int ring_rows = 0;
+  float *eX = nullptr, *eXN = nullptr, *eQKV = nullptr, *eATT = nullptr, *eR1 = nullptr, *eFN = nullptr, *eHF = nullptr,
+        *eR2 = nullptr, *eLOG = nullptr;
+  std::vector<float*> eRing;
+  int* ePast = nullptr;
+  int* TOK = nullptr;
+  // ---- Conan chunk path
+  Ctx cC, cUV[5], cD[8][2], cP;
+  float *dX0 = nullptr, *dQ = nullptr, *dATT = nullptr, *dT1 = nullptr, *dO1 = nullptr, *dHF = nullptr, *dT2 = nullptr,
+        *dPROS[2] = {nullptr, nullptr}, *dPINP = nullptr, *dUVH = nullptr, *dDECX = nullptr, *dDECH = nullptr, *dPOST = nullptr,
+        *dMEL = nullptr, *dUVP = nullptr, *dMASK0 = nullptr, *dMASKB = nullptr;
+  float *sSTYLE = nullptr, *sKV = nullptr, *sKPM = nullptr;
+  int* sNKEYS = nullptr;
+  // ---- vocoder
+  Ctx vPRE, vUP[8], vXA[8], vC1[8][4][4], vC2[8][4][4], vPOST;
+  float *vXS = nullptr, *vXR[2] = {nullptr, nullptr}, *vSUM = nullptr;
+  int vL[9], vC[9];     // rows / channels entering scale i (vL[0] = segment, vC[0] = initial channel)
+  // ---- ring tables
+  RingDesc* ringsConan = nullptr; int nRingsConan = 0, maxHistConan = 0;
+  RingDesc* ringsVoc = nullptr; int nRingsVoc = 0, maxHistVoc = 0;
+  ZeroDesc* zeroEmf = nullptr; int nZeroEmf = 0;
+  ZeroDesc* zeroConan = nullptr; int nZeroConan = 0;
+  ZeroDesc* zeroVoc = nullptr; int nZeroVoc = 0;
+  // ---- session scratch (compact index)
+  int SB = 0;
+  float *qMA = nullptr, *qMF = nullptr, *qXG = nullptr, *qC31 = nullptr, *qHG = nullptr, *qC3G = nullptr, *qPG = nullptr,
+        *qXW = nullptr, *qCW = nullptr, *qAW = nullptr, *qACT = nullptr, *qRS = nullptr, *qSKIP = nullptr, *qGRP = nullptr,
+        *qMP = nullptr, *qMPB = nullptr, *qXP = nullptr, *qC5 = nullptr, *qHP = nullptr, *qC3P = nullptr, *qPZ = nullptr,
+        *qXE = nullptr, *qZC = nullptr, *qPE = nullptr, *qKVs = nullptr, *qMGB = nullptr;
+  int* qVQ = nullptr;
+  int* qSlots = nullptr;
+  // ---- host-call staging
+  int* hIds = nullptr; float* hChunk = nullptr; float* hWav = nullptr; float* hMel = nullptr; int* hTok = nullptr; int* hIdsSmall = nullptr;
+
+  const WeightSlot* W(const std::string& name) const {
+    auto it = windex.find(name);
+    return it == windex.end() ? nullptr : &weights[it->second];
+  }
+  const float* F(const std::string& name) const { auto* w = W(name); return w ? (const float*)w->ptr : nullptr; }
+  const void* P(const std::string& name) const { auto* w = W(name); return w ? w->ptr : nullptr; }
+};
+
+namespace {
+
+void need(conan_engine* e, const std::string& name, size_t numel, int dtype = CONAN_DTYPE_F32) {
+  e->windex[name] = (int)e->weights.size();
+  e->weights.push_back(WeightSlot{name, numel, dtype, nullptr});
+}
+
+void declare_weights(conan_engine* e) {
+  const conan_config_t& c = e->cfg;
+  const int D = c.emformer_dim, F = c.emformer_ffn, H = c.hidden_size;
+  for (int l = 0; l < c.emformer_layers; ++l) {
+    std::string p = "emf." + std::to_string(l) + ".";
+    need(e, p + "ln_in.g", D); need(e, p + "ln_in.b", D);
+    need(e, p + "qkv.w", (size_t)3 * D * D); need(e, p + "qkv.b", 3 * D);
+    need(e, p + "out.w", (size_t)D * D); need(e, p + "out.b", D);
+    need(e, p + "ffn_ln.g", D); need(e, p + "ffn_ln.b", D);
+    need(e, p + "ffn1.w", (size_t)F * D); need(e, p + "ffn1.b", F);
+    need(e, p + "ffn2.w", (size_t)D * F); need(e, p + "ffn2.b", D);
+    need(e, p + "ln_out.g", D); need(e, p + "ln_out.b", D);
+  }
+  need(e, "emf.proj.w", (size_t)c.emformer_output_dim * D); need(e, "emf.proj.b", c.emformer_output_dim);
+
+  need(e, "conan.content_embedding", (size_t)102 * H);
+  need(e, "conan.content_proj.w", (size_t)H * c.content_kernel * H); need(e, "conan.content_proj.b", H);
+  for (int l = 0; l < 2; ++l) {
+    std::string p = "conan.align." + std::to_string(l) + ".";
+    need(e, p + "q.w", (size_t)H * H); need(e, p + "q.b", H);
+    need(e, p + "kv.w", (size_t)2 * H * H); need(e, p + "kv.b", 2 * H);
+    need(e, p + "out.w", (size_t)H * H); need(e, p + "out.b", H);
+    need(e, p + "norm1.g", H); need(e, p + "norm1.b", H);
+    need(e, p + "ffn1.w", (size_t)2048 * H); need(e, p + "ffn1.b", 2048);
+    need(e, p + "ffn2.w", (size_t)H * 2048); need(e, p + "ffn2.b", H);
+    need(e, p + "norm2.g", H); need(e, p + "norm2.b", H);
+  }
+  for (int i = 0; i < 5; ++i) {
+    std::string p = "conan.uv." + std::to_string(i) + ".";
+    need(e, p + "w", (size_t)128 * c.predictor_kernel * (i == 0 ? H : 128)); need(e, p + "b", 128);
+  }
+  need(e, "conan.uv.ln.g", 128); need(e, "conan.uv.ln.b", 128);
+  need(e, "conan.uv.lin.w", 256); need(e, "conan.uv.lin.b", 2);
+  need(e, "conan.pitch_embed", (size_t)300 * H);
+  for (int b = 0; b < c.dec_blocks; ++b)
+    for (int s = 0; s < 2; ++s) {
+      std::string p = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
+      need(e, p + "ln.g", H); need(e, p + "ln.b", H);
+      need(e, p + "conv.w", (size_t)2 * H * c.dec_kernel * H); need(e, p + "conv.b", 2 * H);
+      need(e, p + "pw.w", (size_t)H * 2 * H); need(e, p + "pw.b", H);
+    }
+  need(e, "conan.dec.last_norm.g", H); need(e, "conan.dec.last_norm.b", H);
+  need(e, "conan.dec.post.w", (size_t)H * c.dec_post_kernel * H); need(e, "conan.dec.post.b", H);
+  need(e, "conan.mel_out.w", (size_t)c.n_mels * H); need(e, "conan.mel_out.b", c.n_mels);
+  // session-setup branch
+  need(e, "conan.global_in.w", (size_t)H * c.n_mels); need(e, "conan.global_in.b", H);
+  for (int b = 0; b < 5; ++b)
+    for (int s = 0; s < 2; ++s) {
+      std::string p = "conan.genc." + std::to_string(b) + "." + std::to_string(s) + ".";
+      need(e, p + "ln.g", H); need(e, p + "ln.b", H);
+      need(e, p + "conv.w", (size_t)2 * H * 31 * H); need(e, p + "conv.b", 2 * H);
+      need(e, p + "pw.w", (size_t)H * 2 * H); need(e, p + "pw.b", H);
+      std::string q = "conan.penc." + std::to_string(b) + "." + std::to_string(s) + ".";
+      need(e, q + "ln.g", 80); need(e, q + "ln.b", 80);
+      need(e, q + "conv.w", (size_t)160 * 5 * 80); need(e, q + "conv.b", 160);
+      need(e, q + "pw.w", (size_t)80 * 160); need(e, q + "pw.b", 80);
+    }
+  need(e, "conan.genc.last_norm.g", H); need(e, "conan.genc.last_norm.b", H);
+  need(e, "conan.genc.post.w", (size_t)H * 3 * H); need(e, "conan.genc.post.b", H);
+  need(e, "conan.penc.last_norm.g", 80); need(e, "conan.penc.last_norm.b", 80);
+  need(e, "conan.penc.post.w", (size_t)H * 3 * 80); need(e, "conan.penc.post.b", H);
+  for (int i = 0; i < 4; ++i) {
+    std::string p = "conan.wn." + std::to_string(i) + ".";
+    int co = i < 3 ? 160 : 80;
+    need(e, p + "in.w", (size_t)160 * 3 * 80); need(e, p + "in.b", 160);
+    need(e, p + "rs.w", (size_t)co * 80); need(e, p + "rs.b", co);
+  }
+  need(e, "conan.vq.embedding", (size_t)c.n_vq * H); need(e, "conan.vq.e2", c.n_vq);
+  need(e, "conan.pos_table", (size_t)(e->tp_max + 1) * H);
+  need(e, "conan.l1.w", (size_t)H * 2 * H); need(e, "conan.l1.b", H);
+  // vocoder
+  const int wdt = c.voc_precision ? CONAN_DTYPE_F16 : CONAN_DTYPE_F32;
+  int ch = c.voc_initial_channel;
+  need(e, "voc.pre.w", (size_t)ch * 7 * c.n_mels, wdt); need(e, "voc.pre.b", ch);
+  for (int i = 0; i < c.voc_n_ups; ++i) {
+    int co = ch / 2;
+    std::string p = "voc.up." + std::to_string(i) + ".";
+    need(e, p + "w", (size_t)co * c.voc_rates[i] * c.voc_up_kernels[i] * ch, wdt); need(e, p + "b", (size_t)co * c.voc_rates[i]);
+    for (int r = 0; r < c.voc_n_res; ++r)
+      for (int j = 0; j < c.voc_n_dil; ++j) {
+        std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
+        need(e, q + "c1." + std::to_string(j) + ".w", (size_t)co * c.voc_res_kernels[r] * co, wdt);
+        need(e, q + "c1." + std::to_string(j) + ".b", co);
+        need(e, q + "c2." + std::to_string(j) + ".w", (size_t)co * c.voc_res_kernels[r] * co, wdt);
+        need(e, q + "c2." + std::to_string(j) + ".b", co);
+      }
+    ch = co;
+  }
+  need(e, "voc.post.w", (size_t)7 * ch); need(e, "voc.post.b", 1);
+}
+
+template <typename T>
+int dalloc(conan_engine* e, T** out, size_t count) {
+  void* p = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  bytes = (bytes + 255) & ~(size_t)255;
+  CONAN_CUDA_OK(cudaMalloc(&p, bytes));
+  CONAN_CUDA_OK(cudaMemset(p, 0, bytes));
+  e->allocs.push_back(p);
+  e->state_bytes += bytes;
+  *out = (T*)p;
+  return 0;
+}
+
+int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half) {
+  c->H = H; c->L = L; c->R = R; c->C = C; c->is_half = is_half;
+  size_t count = (size_t)e->S * c->rows() * C;
+  if (is_half) { __half* p; if (dalloc(e, &p, count)) return 1; c->p = p; }
+  else { float* p; if (dalloc(e, &p, count)) return 1; c->p = p; }
+  return 0;
+}
+
+// ---- conv parameter builders ---------------------------------------------------------------
+conan_conv_params_t conv_on_ctx(const conan_engine* e, const Ctx& in, int k, int dil, const void* w, const float* bias,
+                                int cout, int n, const int* ids, bool causal = true) {
+  conan_conv_params_t p;
+  memset(&p, 0, sizeof(p));
+  p.x = in.p; p.x_slot_stride = in.slot_stride(); p.x_row_stride = in.C; p.x_rows = in.rows(); p.x_is_half = in.is_half;
+  p.row0 = causal ? in.H - (k - 1) * dil : in.H - ((k - 1) * dil) / 2;
+  p.L = in.L; p.cin = in.C; p.k = k; p.dil = dil; p.cout = cout; p.w = w; p.bias = bias;
+  p.n_streams = n; p.slot_ids = ids; p.n_slots = e->S;
+  p.scale = 1.f; p.out_scale = 1.f;
+  return p;
+}
+conan_conv_params_t conv_on_rows(const conan_engine* e, const float* x, int rows_per_slot, int row0, int L, int C,
+                                 const void* w, const float* bias, int cout, int n, const int* ids) {
+  conan_conv_params_t p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.x_slot_stride = (long long)rows_per_slot * C; p.x_row_stride = C; p.x_rows = rows_per_slot; p.x_is_half = 0;
+  p.row0 = row0; p.L = L; p.cin = C; p.k = 1; p.dil = 1; p.cout = cout; p.w = w; p.bias = bias;
+  p.n_streams = n; p.slot_ids = ids; p.n_slots = e->S;
+  p.scale = 1.f; p.out_scale = 1.f;
+  return p;
+}
+void out_rows(conan_conv_params_t& p, float* y, int L, int C) { p.y = y; p.y_slot_stride = (long long)L * C; p.y_row_stride = C; p.y_row0 = 0; }
+void out_ctx(conan_conv_params_t& p, const Ctx& c) {     // fp32 context buffer as the primary output
+  p.y = (float*)c.p; p.y_slot_stride = c.slot_stride(); p.y_row_stride = c.C; p.y_row0 = c.H;
+}
+void out2_ctx(conan_conv_params_t& p, const Ctx& c, int act2, float slope2) {
+  p.y2 = c.p; p.y2_slot_stride = c.slot_stride(); p.y2_row_stride = c.C; p.y2_row0 = c.H; p.y2_is_half = c.is_half;
+  p.act2 = act2; p.slope2 = slope2;
+}
+void res_rows(conan_conv_params_t& p, const float* r, int L, int C) { p.res = r; p.res_slot_stride = (long long)L * C; p.res_row_stride = C; }
+
+int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t st, bool allow_tc = false) {
+  if (allow_tc && e->cfg.voc_use_tensor_cores && conv_gemm_tc_eligible(p)) return launch_conv_gemm_tc(p, st);
+  return launch_conv_gemm_ffma(p, st);
+}
+
+int ln_rows(const float* in, int in_rows, int in_row0, RowView out, const float* g, const float* b, int C, int L, int n,
+            const int* ids, cudaStream_t st, const float* premask = nullptr, const float* postmask = nullptr, int mask_stride = 0,
+            float* write_mask = nullptr, float* write_mask2 = nullptr) {
+  LnArgs a;
+  a.in = RowView{(void*)in, (long long)in_rows * C, C, in_row0, 0};
+  a.out = out; a.gamma = g; a.beta = b; a.eps = 1e-5f; a.C = C; a.L = L; a.n = n; a.slot_ids = ids;
+  a.premask = premask; a.premask_slot_stride = mask_stride;
+  a.postmask = postmask; a.postmask_slot_stride = mask_stride;
+  a.write_mask = write_mask; a.write_mask_slot_stride = mask_stride; a.write_mask2 = write_mask2;
+  return launch_layernorm(a, st);
+}
+
+#define TRY(x) do { if ((x) != 0) return 1; } while (0)
+
+// ============================================================================ allocation
+int allocate_state(conan_engine* e) {
+  const conan_config_t& c = e->cfg;
+  const int S = e->S, D = c.emformer_dim, H = c.hidden_size, seg = c.segment, rows = c.segment + c.right_context;
+  // ---- Emformer
+  e->ring_rows = ((c.left_context + seg + seg - 1) / seg) * seg;      // >= lc + seg, multiple of seg
+  TRY(dalloc(e, &e->eX, (size_t)S * rows * D)); TRY(dalloc(e, &e->eXN, (size_t)S * rows * D));
+  TRY(dalloc(e, &e->eQKV, (size_t)S * rows * 3 * D)); TRY(dalloc(e, &e->eATT, (size_t)S * rows * D));
+  TRY(dalloc(e, &e->eR1, (size_t)S * rows * D)); TRY(dalloc(e, &e->eFN, (size_t)S * rows * D));
+  TRY(dalloc(e, &e->eHF, (size_t)S * rows * c.emformer_ffn)); TRY(dalloc(e, &e->eR2, (size_t)S * rows * D));
+  TRY(dalloc(e, &e->eLOG, (size_t)S * seg * c.emformer_output_dim));
+  e->eRing.resize(c.emformer_layers);
+  for (int l = 0; l < c.emformer_layers; ++l) TRY(dalloc(e, &e->eRing[l], (size_t)S * e->ring_rows * 2 * D));
+  TRY(dalloc(e, &e->ePast, (size_t)S)); TRY(dalloc(e, &e->TOK, (size_t)S * seg));
+  // ---- Conan chunk path
+  TRY(alloc_ctx(e, &e->cC, c.content_kernel - 1, seg, 0, H, 0));
+  for (int i = 0; i < 5; ++i) TRY(alloc_ctx(e, &e->cUV[i], c.predictor_kernel - 1, seg, 0, i == 0 ? H : 128, 0));
+  for (int b = 0; b < c.dec_blocks; ++b)
+    for (int s = 0; s < 2; ++s) TRY(alloc_ctx(e, &e->cD[b][s], c.dec_kernel - 1, seg, 0, H, 0));
+  TRY(alloc_ctx(e, &e->cP, c.dec_post_kernel - 1, seg, 0, H, 0));
+  TRY(dalloc(e, &e->dX0, (size_t)S * seg * H)); TRY(dalloc(e, &e->dQ, (size_t)S * seg * H));
+  TRY(dalloc(e, &e->dATT, (size_t)S * seg * H)); TRY(dalloc(e, &e->dT1, (size_t)S * seg * H));
+  TRY(dalloc(e, &e->dO1, (size_t)S * seg * H)); TRY(dalloc(e, &e->dHF, (size_t)S * seg * 2048));
+  TRY(dalloc(e, &e->dT2, (size_t)S * seg * H));
+  TRY(dalloc(e, &e->dPROS[0], (size_t)S * seg * H)); TRY(dalloc(e, &e->dPROS[1], (size_t)S * seg * H));
+  TRY(dalloc(e, &e->dPINP, (size_t)S * seg * H)); TRY(dalloc(e, &e->dUVH, (size_t)S * seg * 128));
+  TRY(dalloc(e, &e->dDECX, (size_t)S * seg * H)); TRY(dalloc(e, &e->dDECH, (size_t)S * seg * 2 * H));
+  TRY(dalloc(e, &e->dPOST, (size_t)S * seg * H)); TRY(dalloc(e, &e->dMEL, (size_t)S * seg * c.n_mels));
+  TRY(dalloc(e, &e->dUVP, (size_t)S * seg * 4)); TRY(dalloc(e, &e->dMASK0, (size_t)S * seg));
+  TRY(dalloc(e, &e->dMASKB, (size_t)S * seg));
+  TRY(dalloc(e, &e->sSTYLE, (size_t)S * H)); TRY(dalloc(e, &e->sKV, (size_t)S * 2 * e->tp_max * 2 * H));
+  TRY(dalloc(e, &e->sKPM, (size_t)S * e->tp_max)); TRY(dalloc(e, &e->sNKEYS, (size_t)S));
+  // ---- vocoder
+  const int hf = c.voc_precision ? 1 : 0;
+  e->vL[0] = seg; e->vC[0] = c.voc_initial_channel;
+  for (int i = 0; i < c.voc_n_ups; ++i) { e->vL[i + 1] = e->vL[i] * c.voc_rates[i]; e->vC[i + 1] = e->vC[i] / 2; }
+  TRY(alloc_ctx(e, &e->vPRE, 6, seg, 0, c.n_mels, hf));
+  size_t maxLC = 0;
+  for (int i = 0; i < c.voc_n_ups; ++i) {
+    TRY(alloc_ctx(e, &e->vUP[i], c.voc_up_kernels[i] - 1, e->vL[i], 0, e->vC[i], hf));
+    int L = e->vL[i + 1], C = e->vC[i + 1];
+    int hmax = 0;
+    for (int r = 0; r < c.voc_n_res; ++r) hmax = std::max(hmax, (c.voc_res_kernels[r] - 1) * c.voc_res_dilations[0]);
+    TRY(alloc_ctx(e, &e->vXA[i], hmax, L, 0, C, hf));
+    for (int r = 0; r < c.voc_n_res; ++r)
+      for (int j = 0; j < c.voc_n_dil; ++j) {
+        if (j > 0) TRY(alloc_ctx(e, &e->vC1[i][r][j], (c.voc_res_kernels[r] - 1) * c.voc_res_dilations[j], L, 0, C, hf));
+        TRY(alloc_ctx(e, &e->vC2[i][r][j], c.voc_res_kernels[r] - 1, L, 0, C, hf));
+      }
+    maxLC = std::max(maxLC, (size_t)L * C);
+  }
+  TRY(alloc_ctx(e, &e->vPOST, 6, e->vL[c.voc_n_ups], 0, e->vC[c.voc_n_ups], hf));
+  TRY(dalloc(e, &e->vXS, (size_t)S * maxLC)); TRY(dalloc(e, &e->vXR[0], (size_t)S * maxLC));
+  TRY(dalloc(e, &e->vXR[1], (size_t)S * maxLC)); TRY(dalloc(e, &e->vSUM, (size_t)S * maxLC));
+
+  // ---- ring / zero tables
+  auto build_tables = [&](std::vector<const Ctx*> ctxs, RingDesc** rings, int* nrings, int* maxhist, ZeroDesc** zeros, int* nzeros,
+                          std::vector<ZeroDesc> extra_zero) -> int {
+    std::vector<RingDesc> r; std::vector<ZeroDesc> z = extra_zero;
+    int mh = 0;
+    for (const Ctx* cx : ctxs) {
+      size_t rowb = (size_t)cx->C * cx->elem();
+      if (cx->H > 0) {
+        RingDesc d{cx->p, (long long)(cx->slot_stride() * cx->elem()), (int)(cx->H * rowb), (int)(cx->L * rowb)};
+        if (d.hist_bytes % 16 || d.new_bytes % 16 || d.slot_stride_bytes % 16) { set_error("ring sizes must be multiples of 16 bytes"); return 1; }
+        r.push_back(d); mh = std::max(mh, d.hist_bytes);
+      }
+      z.push_back(ZeroDesc{cx->p, (long long)(cx->slot_stride() * cx->elem()), (long long)(cx->slot_stride() * cx->elem())});
+    }
+    *nrings = (int)r.size(); *maxhist = mh; *nzeros = (int)z.size();
+    if (!r.empty()) {
+      TRY(dalloc(e, rings, r.size()));
+      CONAN_CUDA_OK(cudaMemcpy(*rings, r.data(), r.size() * sizeof(RingDesc), cudaMemcpyHostToDevice));
+    }
+    if (!z.empty()) {
+      TRY(dalloc(e, zeros, z.size()));
+      CONAN_CUDA_OK(cudaMemcpy(*zeros, z.data(), z.size() * sizeof(ZeroDesc), cudaMemcpyHostToDevice));
+    }
+    return 0;
+  };
+  {
+    std::vector<ZeroDesc> ez;
+    for (int l = 0; l < c.emformer_layers; ++l)
+      ez.push_back(ZeroDesc{e->eRing[l], (long long)e->ring_rows * 2 * D * 4, (long long)e->ring_rows * 2 * D * 4});
+    ez.push_back(ZeroDesc{e->ePast, 4, 4});
+    RingDesc* dummy = nullptr; int nd = 0, mh = 0;
+    TRY(build_tables({}, &dummy, &nd, &mh, &e->zeroEmf, &e->nZeroEmf, ez));
+  }
+  {
+    std::vector<const Ctx*> cs{&e->cC, &e->cP};
+    for (int i = 0; i < 5; ++i) cs.push_back(&e->cUV[i]);
+    for (int b = 0; b < c.dec_blocks; ++b) for (int s = 0; s < 2; ++s) cs.push_back(&e->cD[b][s]);
+    TRY(build_tables(cs, &e->ringsConan, &e->nRingsConan, &e->maxHistConan, &e->zeroConan, &e->nZeroConan, {}));
+  }
+  {
+    std::vector<const Ctx*> cs{&e->vPRE, &e->vPOST};
+    for (int i = 0; i < c.voc_n_ups; ++i) {
+      cs.push_back(&e->vUP[i]); cs.push_back(&e->vXA[i]);
+      for (int r = 0; r < c.voc_n_res; ++r)
+        for (int j = 0; j < c.voc_n_dil; ++j) { if (j > 0) cs.push_back(&e->vC1[i][r][j]); cs.push_back(&e->vC2[i][r][j]); }
+    }
+    TRY(build_tables(cs, &e->ringsVoc, &e->nRingsVoc, &e->maxHistVoc, &e->zeroVoc, &e->nZeroVoc, {}));
+  }
+  // ---- session scratch
+  e->SB = std::min(S, 32);
+  const int SB = e->SB, T = c.max_ref_frames, Tp = e->tp_max;
+  TRY(dalloc(e, &e->qMA, (size_t)SB * T)); TRY(dalloc(e, &e->qMF, (size_t)SB * T)); TRY(dalloc(e, &e->qMGB, (size_t)SB * T));
+  TRY(dalloc(e, &e->qXG, (size_t)SB * T * H)); TRY(dalloc(e, &e->qC31, (size_t)SB * (T + 30) * H));
+  TRY(dalloc(e, &e->qHG, (size_t)SB * T * 2 * H)); TRY(dalloc(e, &e->qC3G, (size_t)SB * (T + 2) * H));
+  TRY(dalloc(e, &e->qPG, (size_t)SB * T * H));
+  TRY(dalloc(e, &e->qXW, (size_t)SB * T * 80)); TRY(dalloc(e, &e->qCW, (size_t)SB * (T + 2) * 80));
+  TRY(dalloc(e, &e->qAW, (size_t)SB * T * 160)); TRY(dalloc(e, &e->qACT, (size_t)SB * T * 80));
+  TRY(dalloc(e, &e->qRS, (size_t)SB * T * 160)); TRY(dalloc(e, &e->qSKIP, (size_t)SB * T * 80));
+  TRY(dalloc(e, &e->qGRP, (size_t)SB * Tp * 80)); TRY(dalloc(e, &e->qMP, (size_t)SB * Tp)); TRY(dalloc(e, &e->qMPB, (size_t)SB * Tp));
+  TRY(dalloc(e, &e->qXP, (size_t)SB * Tp * 80)); TRY(dalloc(e, &e->qC5, (size_t)SB * (Tp + 4) * 80));
+  TRY(dalloc(e, &e->qHP, (size_t)SB * Tp * 160)); TRY(dalloc(e, &e->qC3P, (size_t)SB * (Tp + 2) * 80));
+  TRY(dalloc(e, &e->qPZ, (size_t)SB * Tp * H)); TRY(dalloc(e, &e->qXE, (size_t)SB * Tp * c.n_vq));
+  TRY(dalloc(e, &e->qZC, (size_t)SB * Tp * 2 * H)); TRY(dalloc(e, &e->qPE, (size_t)SB * Tp * H));
+  TRY(dalloc(e, &e->qKVs, (size_t)SB * Tp * 2 * H)); TRY(dalloc(e, &e->qVQ, (size_t)SB * Tp));
+  TRY(dalloc(e, &e->qSlots, (size_t)SB));
+  // ---- host-call staging
+  TRY(dalloc(e, &e->hIds, (size_t)S)); TRY(dalloc(e, &e->hIdsSmall, (size_t)S));
+  TRY(dalloc(e, &e->hChunk, (size_t)S * rows * D));
+  TRY(dalloc(e, &e->hWav, (size_t)S * e->vL[c.voc_n_ups])); TRY(dalloc(e, &e->hMel, (size_t)S * seg * c.n_mels));
+  TRY(dalloc(e, &e->hTok, (size_t)S * seg));
+  return 0;
+}
+
+// ============================================================================ Emformer step
+int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, float* enc_out, float* logits_out,
+                  int* tokens_out, cudaStream_t st) {
+  const conan_config_t& c = e->cfg;
+  const int D = c.emformer_dim, seg = c.segment, rc = c.right_context, rows = seg + rc, F = c.emformer_ffn;
+  TRY(launch_emformer_assemble(chunk, e->eX, n, ids, seg, rc, D, st));
+  for (int l = 0; l < c.emformer_layers; ++l) {
+    std::string p = "emf." + std::to_string(l) + ".";
+    TRY(ln_rows(e->eX, rows, 0, view_f32(e->eXN, (long long)rows * D, D), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, ids, st));
+    auto q = conv_on_rows(e, e->eXN, rows, 0, rows, D, e->P(p + "qkv.w"), e->F(p + "qkv.b"), 3 * D, n, ids);
+    out_rows(q, e->eQKV, rows, 3 * D);
+    TRY(run_conv(e, q, st));
+    TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT, n, ids, seg, rc, c.left_context, e->ring_rows, D,
+                                  c.emformer_heads, st));
+    auto o = conv_on_rows(e, e->eATT, rows, 0, rows, D, e->P(p + "out.w"), e->F(p + "out.b"), D, n, ids);
+    out_rows(o, e->eR1, rows, D); res_rows(o, e->eX, rows, D);
+    TRY(run_conv(e, o, st));
+    TRY(ln_rows(e->eR1, rows, 0, view_f32(e->eFN, (long long)rows * D, D), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, ids, st));
+    auto f1 = conv_on_rows(e, e->eFN, rows, 0, rows, D, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n, ids);
+    out_rows(f1, e->eHF, rows, F); f1.act = ACT_RELU;
+    TRY(run_conv(e, f1, st));
+    auto f2 = conv_on_rows(e, e->eHF, rows, 0, rows, F, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), D, n, ids);
+    out_rows(f2, e->eR2, rows, D); res_rows(f2, e->eR1, rows, D);
+    TRY(run_conv(e, f2, st));
+    TRY(ln_rows(e->eR2, rows, 0, view_f32(e->eX, (long long)rows * D, D), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, ids, st));
+  }
+  TRY(launch_advance_past_len(e->ePast, n, ids, seg, st));
+  auto pj = conv_on_rows(e, e->eX, rows, rc, seg, D, e->P("emf.proj.w"), e->F("emf.proj.b"), c.emformer_output_dim, n, ids);
+  out_rows(pj, e->eLOG, seg, c.emformer_output_dim);
+  TRY(run_conv(e, pj, st));
+  TRY(launch_argmax_rows(e->eLOG, e->TOK, tokens_out, n, ids, seg, c.emformer_output_dim, st));
+  if (enc_out) TRY(launch_copy_rows_out(e->eX, (long long)rows * D, D, rc, enc_out, n, ids, seg, D, st));
+  if (logits_out) TRY(launch_copy_rows_out(e->eLOG, (long long)seg * c.emformer_output_dim, c.emformer_output_dim, 0, logits_out, n, ids, seg, c.emformer_output_dim, st));
+  return 0;
+}
+
+// ============================================================================ Conan chunk step
+int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, float* mel_out, cudaStream_t st) {
+  const conan_config_t& c = e->cfg;
+  const int H = c.hidden_size, seg = c.segment;
+  if (tokens_ext) TRY(launch_copy_rows_in(tokens_ext, 1, e->TOK, seg, n, ids, seg, st));
+  TRY(launch_embedding_rows(e->TOK, e->F("conan.content_embedding"), 102, e->cC.new_rows(), n, ids, seg, H, st));
+  {
+    auto p = conv_on_ctx(e, e->cC, c.content_kernel, 1, e->P("conan.content_proj.w"), e->F("conan.content_proj.b"), H, n, ids);
+    out_rows(p, e->dX0, seg, H); p.act = ACT_LRELU; p.slope = 0.01f;
+    p.res = e->sSTYLE; p.res_slot_stride = H; p.res_row_stride = 0;                  // + style_embed (Conan.py:162)
+    TRY(run_conv(e, p, st));
+  }
+  const float* cur = e->dX0;
+  for (int l = 0; l < 2; ++l) {
+    std::string a = "conan.align." + std::to_string(l) + ".";
+    auto q = conv_on_rows(e, cur, seg, 0, seg, H, e->P(a + "q.w"), e->F(a + "q.b"), H, n, ids);
+    out_rows(q, e->dQ, seg, H);
+    TRY(run_conv(e, q, st));
+    TRY(launch_cross_attention(e->dQ, e->sKV, e->sKPM, e->sNKEYS, e->dATT, n, ids, seg, H, 2, l, 2, e->tp_max, st));
+    auto o = conv_on_rows(e, e->dATT, seg, 0, seg, H, e->P(a + "out.w"), e->F(a + "out.b"), H, n, ids);
+    out_rows(o, e->dT1, seg, H); res_rows(o, cur, seg, H);
+    TRY(run_conv(e, o, st));
+    TRY(ln_rows(e->dT1, seg, 0, view_f32(e->dO1, (long long)seg * H, H), e->F(a + "norm1.g"), e->F(a + "norm1.b"), H, seg, n, ids, st));
+    auto f1 = conv_on_rows(e, e->dO1, seg, 0, seg, H, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, n, ids);
+    out_rows(f1, e->dHF, seg, 2048); f1.act = ACT_RELU;
+    TRY(run_conv(e, f1, st));
+    auto f2 = conv_on_rows(e, e->dHF, seg, 0, seg, 2048, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n, ids);
+    out_rows(f2, e->dT2, seg, H); res_rows(f2, e->dO1, seg, H);
+    TRY(run_conv(e, f2, st));
+    TRY(ln_rows(e->dT2, seg, 0, view_f32(e->dPROS[l], (long long)seg * H, H), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, ids, st));
+    cur = e->dPROS[l];
+  }
+  TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, ids, seg, H, st));      // Conan.py:168
+  for (int i = 0; i < 5; ++i) {                                                                // uv_predictor convs
+    std::string u = "conan.uv." + std::to_string(i) + ".";
+    auto p = conv_on_ctx(e, e->cUV[i], c.predictor_kernel, 1, e->P(u + "w"), e->F(u + "b"), 128, n, ids);
+    p.act = ACT_RELU;
+    if (i < 4) out_ctx(p, e->cUV[i + 1]); else out_rows(p, e->dUVH, seg, 128);
+    TRY(run_conv(e, p, st));
+  }
+  TRY(launch_pitch(e->dUVH, e->F("conan.uv.ln.g"), e->F("conan.uv.ln.b"), e->F("conan.uv.lin.w"), e->F("conan.uv.lin.b"), e->TOK,
+                   c.silent_token, e->F("conan.pitch_embed"), e->dPINP, e->dDECX, e->dUVP, n, ids, seg, 128, H, st));
+  for (int b = 0; b < c.dec_blocks; ++b)
+    for (int s = 0; s < 2; ++s) {
+      std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
+      TRY(ln_rows(e->dDECX, seg, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, ids, st, nullptr, nullptr, seg,
+                  s == 0 ? e->dMASKB : nullptr, (b == 0 && s == 0) ? e->dMASK0 : nullptr));
+      auto p = conv_on_ctx(e, e->cD[b][s], c.dec_kernel, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, n, ids);
+      out_rows(p, e->dDECH, seg, 2 * H); p.scale = 1.0f / sqrtf((float)c.dec_kernel); p.act = ACT_GELU;
+      TRY(run_conv(e, p, st));
+      auto w = conv_on_rows(e, e->dDECH, seg, 0, seg, 2 * H, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n, ids);
+      out_rows(w, e->dDECX, seg, H); res_rows(w, e->dDECX, seg, H); w.rowmask = e->dMASKB; w.mask_slot_stride = seg;
+      TRY(run_conv(e, w, st));
+    }
+  TRY(ln_rows(e->dDECX, seg, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, ids, st,
+              e->dMASK0, e->dMASK0, seg));
+  {
+    auto p = conv_on_ctx(e, e->cP, c.dec_post_kernel, 1, e->P("conan.dec.post.w"), e->F("conan.dec.post.b"), H, n, ids);
+    out_rows(p, e->dPOST, seg, H); p.rowmask = e->dMASK0; p.mask_slot_stride = seg;
+    TRY(run_conv(e, p, st));
+    auto m = conv_on_rows(e, e->dPOST, seg, 0, seg, H, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), c.n_mels, n, ids);
+    out_rows(m, e->dMEL, seg, c.n_mels);
+    out2_ctx(m, e->vPRE, ACT_NONE, 0.f);                                                       // feeds conv_pre of the vocoder
+    TRY(run_conv(e, m, st));
+  }
+  TRY(launch_ring_shift(e->ringsConan, e->nRingsConan, e->maxHistConan, n, ids, st));
+  if (mel_out) TRY(launch_copy_rows_out(e->dMEL, (long long)seg * c.n_mels, c.n_mels, 0, mel_out, n, ids, seg, c.n_mels, st));
+  return 0;
+}
+
+// ============================================================================ vocoder step
+int vocoder_pass(conan_engine* e, int n, const int* ids, float* wav_out, cudaStream_t st) {
+  const conan_config_t& c = e->cfg;
+  const float sl = 0.1f;
+  {
+    auto p = conv_on_ctx(e, e->vPRE, 7, 1, e->P("voc.pre.w"), e->F("voc.pre.b"), e->vC[0], n, ids);
+    out2_ctx(p, e->vUP[0], ACT_LRELU, sl);
+    TRY(run_conv(e, p, st, true));
+  }
+  for (int i = 0; i < c.voc_n_ups; ++i) {
+    const int r_up = c.voc_rates[i], L = e->vL[i + 1], C = e->vC[i + 1];
+    std::string u = "voc.up." + std::to_string(i) + ".";
+    {
+      // conv -> pixel shuffle folded into the weight row order: output row t holds r_up consecutive
+      // output frames, i.e. [slot, L_in, r*C] viewed as [slot, L_in*r, C]  (hifigan_causal.py:186-188)
+      auto p = conv_on_ctx(e, e->vUP[i], c.voc_up_kernels[i], 1, e->P(u + "w"), e->F(u + "b"), r_up * C, n, ids);
+      p.y = e->vXS; p.y_slot_stride = (long long)L * C; p.y_row_stride = r_up * C; p.y_row0 = 0;
+      p.y2 = e->vXA[i].at_row(e->vXA[i].H); p.y2_slot_stride = e->vXA[i].slot_stride(); p.y2_row_stride = r_up * C; p.y2_row0 = 0;
+      p.y2_is_half = e->vXA[i].is_half; p.act2 = ACT_LRELU; p.slope2 = sl;
+      TRY(run_conv(e, p, st, true));
+    }
+    const bool last_scale = (i == c.voc_n_ups - 1);
+    const Ctx& next = last_scale ? e->vPOST : e->vUP[i + 1];
+    for (int r = 0; r < c.voc_n_res; ++r) {
+      const int k = c.voc_res_kernels[r];
+      std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
+      const float* xj = e->vXS;
+      for (int j = 0; j < c.voc_n_dil; ++j) {
+        const Ctx& in1 = (j == 0) ? e->vXA[i] : e->vC1[i][r][j];
+        auto p1 = conv_on_ctx(e, in1, k, c.voc_res_dilations[j], e->P(q + "c1." + std::to_string(j) + ".w"),
+                              e->F(q + "c1." + std::to_string(j) + ".b"), C, n, ids);
+        out2_ctx(p1, e->vC2[i][r][j], ACT_LRELU, sl);
+        TRY(run_conv(e, p1, st, true));
+        auto p2 = conv_on_ctx(e, e->vC2[i][r][j], k, 1, e->P(q + "c2." + std::to_string(j) + ".w"),
+                              e->F(q + "c2." + std::to_string(j) + ".b"), C, n, ids);
+        res_rows(p2, xj, L, C);
+        if (j + 1 < c.voc_n_dil) {
+          float* xn = e->vXR[j & 1];
+          out_rows(p2, xn, L, C);
+          out2_ctx(p2, e->vC1[i][r][j + 1], ACT_LRELU, sl);
+          xj = xn;
+        } else {
+          out_rows(p2, e->vSUM, L, C);
+          p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)
+          if (r == c.voc_n_res - 1) out2_ctx(p2, next, ACT_LRELU, sl);
+        }
+        TRY(run_conv(e, p2, st, true));
+      }
+    }
+  }
+  const int Lw = e->vL[c.voc_n_ups];
+  TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
+                            e->F("voc.post.w"), e->F("voc.post.b"), wav_out, n, ids, st));
+  TRY(launch_ring_shift(e->ringsVoc, e->nRingsVoc, e->maxHistVoc, n, ids, st));
+  return 0;
+}
+
+int vocoder_step(conan_engine* e, int n, const int* ids, const float* mel_ext, float* wav_out, cudaStream_t st) {
+  const conan_config_t& c = e->cfg;
+  if (mel_ext) {
+    TRY(launch_copy_rows_in(mel_ext, 0, e->dMEL, (long long)c.segment * c.n_mels, n, ids, c.segment * c.n_mels, st));
+    TRY(launch_rows_to_view(e->dMEL, e->vPRE.new_rows(), n, ids, c.segment, c.n_mels, st));
+  }
+  const int G = c.voc_group > 0 ? c.voc_group : n;
+  const int Lw = e->vL[c.voc_n_ups];
+  for (int g = 0; g < n; g += G) TRY(vocoder_pass(e, std::min(G, n - g), ids + g, wav_out + (size_t)g * Lw, st));
+  return 0;
+}
+
+// ============================================================================ session setup
+// ConvBlocks.forward on compact [n, T, C] rows (modules/commons/conv.py:84-125 / prosody_util.py:299-336)
+int conv_blocks_noncausal(conan_engine* e, const std::string& pre, float* X, int C, int k, float* ctxk, float* Hbuf, float* ctx3,
+                          float* OUT, int outC, const float* nonpad, float* maskb, int n, int T, cudaStream_t st) {
+  const int pad = (k - 1) / 2;
+  Ctx ck; ck.p = ctxk; ck.H = pad; ck.L = T; ck.R = pad; ck.C = C; ck.is_half = 0;
+  Ctx c3; c3.p = ctx3; c3.H = 1; c3.L = T; c3.R = 1; c3.C = C; c3.is_half = 0;
+  CONAN_CUDA_OK(cudaMemsetAsync(ctxk, 0, (size_t)n * ck.rows() * C * 4, st));
+  CONAN_CUDA_OK(cudaMemsetAsync(ctx3, 0, (size_t)n * c3.rows() * C * 4, st));
+  for (int b = 0; b < 5; ++b)
+    for (int s = 0; s < 2; ++s) {
+      std::string d = pre + "." + std::to_string(b) + "." + std::to_string(s) + ".";
+      TRY(ln_rows(X, T, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, nullptr, st, nullptr, nullptr, T,
+                  s == 0 ? maskb : nullptr, nullptr));
+      auto p = conv_on_ctx(e, ck, k, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * C, n, nullptr, false);
+      p.n_slots = n; out_rows(p, Hbuf, T, 2 * C); p.scale = 1.0f / sqrtf((float)k); p.act = ACT_GELU;
+      TRY(run_conv(e, p, st));
+      auto w = conv_on_rows(e, Hbuf, T, 0, T, 2 * C, e->P(d + "pw.w"), e->F(d + "pw.b"), C, n, nullptr);
+      w.n_slots = n; out_rows(w, X, T, C); res_rows(w, X, T, C); w.rowmask = maskb; w.mask_slot_stride = T;
+      TRY(run_conv(e, w, st));
+    }
+  TRY(ln_rows(X, T, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, nullptr, st, nonpad, nonpad, T));
+  auto p = conv_on_ctx(e, c3, 3, 1, e->P(pre + ".post.w"), e->F(pre + ".post.b"), outC, n, nullptr, false);
+  p.n_slots = n; out_rows(p, OUT, T, outC); p.rowmask = nonpad; p.mask_slot_stride = T;
+  TRY(run_conv(e, p, st));
+  return 0;
+}
+
+int session_open_batch(conan_engine* e, int n, const int* slots_host, const float* ref, int T, cudaStream_t st) {
+  const conan_config_t& c = e->cfg;
+  const int H = c.hidden_size, M = c.n_mels;
+  const int Tp = (T - 1) / 4 + 1;
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->qSlots, slots_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  TRY(launch_row_masks(ref, e->qMA, e->qMF, n, T, M, st));
+  // ---- global style encoder (Conan.py:200-219)
+  {
+    auto p = conv_on_rows(e, ref, T, 0, T, M, e->P("conan.global_in.w"), e->F("conan.global_in.b"), H, n, nullptr);
+    p.n_slots = n; out_rows(p, e->qXG, T, H); p.rowmask = e->qMA; p.mask_slot_stride = T;
+    TRY(run_conv(e, p, st));
+    TRY(conv_blocks_noncausal(e, "conan.genc", e->qXG, H, 31, e->qC31, e->qHG, e->qC3G, e->qPG, H, e->qMA, e->qMGB, n, T, st));
+    TRY(launch_masked_time_mean(e->qPG, e->qMA, e->sSTYLE, e->qSlots, n, T, H, st));
+  }
+  // ---- LocalStyleAdaptor: WN (wavenet.py:55-88)
+  {
+    Ctx cw; cw.p = e->qCW; cw.H = 1; cw.L = T; cw.R = 1; cw.C = M; cw.is_half = 0;
+    CONAN_CUDA_OK(cudaMemsetAsync(e->qCW, 0, (size_t)n * cw.rows() * M * 4, st));
+    CONAN_CUDA_OK(cudaMemsetAsync(e->qSKIP, 0, (size_t)n * T * M * 4, st));
+    CONAN_CUDA_OK(cudaMemcpyAsync(e->qXW, ref, (size_t)n * T * M * 4, cudaMemcpyDeviceToDevice, st));
+    CONAN_CUDA_OK(cudaMemcpy2DAsync((float*)cw.p + M, (size_t)cw.rows() * M * 4, ref, (size_t)T * M * 4, (size_t)T * M * 4, n,
+                                    cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < 4; ++i) {
+      std::string w = "conan.wn." + std::to_string(i) + ".";
+      auto p = conv_on_ctx(e, cw, 3, 1, e->P(w + "in.w"), e->F(w + "in.b"), 2 * M, n, nullptr, false);
+      p.n_slots = n; out_rows(p, e->qAW, T, 2 * M);
+      TRY(run_conv(e, p, st));
+      TRY(launch_gated_tanh_sigmoid(e->qAW, e->qACT, (long long)n * T, M, st));
+      int co = i < 3 ? 2 * M : M;
+      auto r = conv_on_rows(e, e->qACT, T, 0, T, M, e->P(w + "rs.w"), e->F(w + "rs.b"), co, n, nullptr);
+      r.n_slots = n; out_rows(r, e->qRS, T, co);
+      TRY(run_conv(e, r, st));
+      TRY(launch_wn_update(e->qRS, e->qXW, cw.new_rows(), e->qSKIP, e->qMF, (long long)n * T, T, M, i == 3, st));
+    }
+    TRY(launch_group_mean4(e->qSKIP, e->qMF, e->qGRP, n, T, Tp, M, st));
+  }
+  // ---- prosody encoder ConvBlocks(80 -> H, k5) + VQ + positions + l1 + aligner K/V
+  {
+    TRY(launch_row_masks(e->qGRP, e->qMP, e->qMPB, n, Tp, M, st));      // qMPB is overwritten by the block masks below
+    CONAN_CUDA_OK(cudaMemcpyAsync(e->qXP, e->qGRP, (size_t)n * Tp * M * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(conv_blocks_noncausal(e, "conan.penc", e->qXP, M, 5, e->qC5, e->qHP, e->qC3P, e->qPZ, H, e->qMP, e->qMPB, n, Tp, st));
+    auto d = conv_on_rows(e, e->qPZ, Tp, 0, Tp, H, e->P("conan.vq.embedding"), nullptr, c.n_vq, n, nullptr);
+    d.n_slots = n; out_rows(d, e->qXE, Tp, c.n_vq);
+    TRY(run_conv(e, d, st));
+    TRY(launch_vq_quantize(e->qPZ, e->qXE, e->F("conan.vq.embedding"), e->F("conan.vq.e2"), e->F("conan.pos_table"), e->qZC, e->qVQ,
+                           n, Tp, H, c.n_vq, st));
+    auto l1 = conv_on_rows(e, e->qZC, Tp, 0, Tp, 2 * H, e->P("conan.l1.w"), e->F("conan.l1.b"), H, n, nullptr);
+    l1.n_slots = n; out_rows(l1, e->qPE, Tp, H);
+    TRY(run_conv(e, l1, st));
+    TRY(launch_kpm(e->qPE, e->sKPM, e->sNKEYS, e->qSlots, n, Tp, H, e->tp_max, st));
+    for (int l = 0; l < 2; ++l) {
+      std::string a = "conan.align." + std::to_string(l) + ".";
+      auto kv = conv_on_rows(e, e->qPE, Tp, 0, Tp, H, e->P(a + "kv.w"), e->F(a + "kv.b"), 2 * H, n, nullptr);
+      kv.n_slots = n; out_rows(kv, e->qKVs, Tp, 2 * H);
+      TRY(run_conv(e, kv, st));
+      TRY(launch_scatter_kv(e->qKVs, e->sKV, e->qSlots, n, Tp, 2 * H, l, 2, e->tp_max, st));
+    }
+  }
+  return 0;
+}
+
+int check_ready(conan_engine* e) {
+  if (!e) { set_error("null engine"); return 1; }
+  if (!e->finalized) { set_error("engine not finalized"); return 1; }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* conan_last_error(void) { return g_last_error.c_str(); }
+int conan_abi_version(void) { return CONAN_B200_ABI_VERSION; }
+size_t conan_sizeof_config(void) { return sizeof(conan_config_t); }
+size_t conan_sizeof_conv_params(void) { return sizeof(conan_conv_params_t); }
+
+int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
+  if (!cfg || !out) { set_error("null argument"); return 1; }
+  if (cfg->abi_version != CONAN_B200_ABI_VERSION) { set_error("ABI version mismatch"); return 1; }
+  if (cfg->max_slots <= 0 || cfg->max_ref_frames <= 0) { set_error("max_slots and max_ref_frames must be positive"); return 1; }
+  if (cfg->voc_n_ups > 8 || cfg->voc_n_res > 4 || cfg->voc_n_dil > 4 || cfg->dec_blocks > 8) { set_error("config above compiled limits"); return 1; }
+  if (cfg->voc_use_tensor_cores && !cfg->voc_precision) { set_error("voc_use_tensor_cores requires voc_precision = 1 (fp16 operands)"); return 1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) {
+    set_error("no CUDA device: the conan_b200 engine has no CPU fallback");
+    return 1;
+  }
+  cudaDeviceProp prop;
+  CONAN_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) { set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library is built for sm_100a only"); return 1; }
+  CONAN_CUDA_OK(cudaSetDevice(cfg->device));
+  conan_engine* e = new conan_engine();
+  e->cfg = *cfg;
+  e->S = cfg->max_slots;
+  e->tp_max = (cfg->max_ref_frames - 1) / 4 + 1;
+  declare_weights(e);
+  *out = e;
+  return 0;
+}
+
+void conan_engine_destroy(conan_engine_t* e) {
+  if (!e) return;
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+int conan_engine_num_weights(const conan_engine_t* e) { return e ? (int)e->weights.size() : 0; }
+
+int conan_engine_weight_info(const conan_engine_t* e, int idx, const char** name, size_t* numel, int* dtype) {
+  if (!e || idx < 0 || idx >= (int)e->weights.size()) { set_error("weight index out of range"); return 1; }
+  if (name) *name = e->weights[idx].name.c_str();
+  if (numel) *numel = e->weights[idx].numel;
+  if (dtype) *dtype = e->weights[idx].dtype;
+  return 0;
+}
+
+int conan_engine_bind_weight(conan_engine_t* e, const char* name, const void* data_dev, size_t numel, int dtype) {
+  if (!e || !name || !data_dev) { set_error("null argument"); return 1; }
+  auto it = e->windex.find(name);
+  if (it == e->windex.end()) { set_error(std::string("unknown weight '") + name + "'"); return 1; }
+  WeightSlot& w = e->weights[it->second];
+  if (w.numel != numel || w.dtype != dtype) {
+    set_error(std::string("weight '") + name + "': expected " + std::to_string(w.numel) + " elements of dtype " + std::to_string(w.dtype) +
+              ", got " + std::to_string(numel) + " of dtype " + std::to_string(dtype));
+    return 1;
+  }
+  if (((uintptr_t)data_dev) % 16 != 0) { set_error(std::string("weight '") + name + "' is not 16-byte aligned"); return 1; }
+  w.ptr = data_dev;
+  return 0;
+}
+
+int conan_engine_finalize(conan_engine_t* e) {
+  if (!e) { set_error("null engine"); return 1; }
+  if (e->finalized) return 0;
+  for (auto& w : e->weights)
+    if (!w.ptr) { set_error("weight '" + w.name + "' was never bound"); return 1; }
+  CONAN_CUDA_OK(cudaSetDevice(e->cfg.device));
+  if (allocate_state(e)) return 1;
+  CONAN_CUDA_OK(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+size_t conan_engine_state_bytes(const conan_engine_t* e) { return e ? e->state_bytes : 0; }
+uint64_t conan_engine_launch_count(const conan_engine_t*) { return g_launches.load(); }
+
+int conan_slots_reset(conan_engine_t* e, int n, const int32_t* slots_host, int parts, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n <= 0) return 0;
+  if (n > e->S) { set_error("more slots than max_slots"); return 1; }
+  for (int i = 0; i < n; ++i) if (slots_host[i] < 0 || slots_host[i] >= e->S) { set_error("slot id out of range"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->hIdsSmall, slots_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (parts & 1) TRY(launch_zero_slots(e->zeroEmf, e->nZeroEmf, n, e->hIdsSmall, st));
+  if (parts & 2) TRY(launch_zero_slots(e->zeroConan, e->nZeroConan, n, e->hIdsSmall, st));
+  if (parts & 4) TRY(launch_zero_slots(e->zeroVoc, e->nZeroVoc, n, e->hIdsSmall, st));
+  CONAN_CUDA_OK(cudaStreamSynchronize(st));     // hIdsSmall is reused by the next call
+  return 0;
+}
+
+int conan_session_open(conan_engine_t* e, int n, const int32_t* slots_host, const float* ref_mel_dev, int ref_frames, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n <= 0) return 0;
+  if (ref_frames < 1 || ref_frames > e->cfg.max_ref_frames) { set_error("ref_frames outside [1, max_ref_frames]"); return 1; }
+  for (int i = 0; i < n; ++i) if (slots_host[i] < 0 || slots_host[i] >= e->S) { set_error("slot id out of range"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g = 0; g < n; g += e->SB) {
+    int nb = std::min(e->SB, n - g);
+    TRY(session_open_batch(e, nb, slots_host + g, ref_mel_dev + (size_t)g * ref_frames * e->cfg.n_mels, ref_frames, st));
+    CONAN_CUDA_OK(cudaStreamSynchronize(st));   // qSlots / scratch are reused by the next batch
+  }
+  return 0;
+}
+
+int conan_emformer_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* enc_out_dev,
+                        float* logits_out_dev, int32_t* tokens_out_dev, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n < 0 || n > e->S || !slot_ids_dev || !chunk_dev) { set_error("bad arguments to conan_emformer_step"); return 1; }
+  return emformer_step(e, n, slot_ids_dev, chunk_dev, enc_out_dev, logits_out_dev, tokens_out_dev, (cudaStream_t)stream);
+}
+
+int conan_decoder_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const int32_t* tokens_dev, float* mel_out_dev, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n < 0 || n > e->S || !slot_ids_dev || !tokens_dev) { set_error("bad arguments to conan_decoder_step"); return 1; }
+  return decoder_step(e, n, slot_ids_dev, tokens_dev, mel_out_dev, (cudaStream_t)stream);
+}
+
+int conan_vocoder_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* mel_dev, float* wav_out_dev, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n < 0 || n > e->S || !slot_ids_dev || !mel_dev || !wav_out_dev) { set_error("bad arguments to conan_vocoder_step"); return 1; }
+  return vocoder_step(e, n, slot_ids_dev, mel_dev, wav_out_dev, (cudaStream_t)stream);
+}
+
+int conan_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* wav_out_dev, float* mel_out_dev,
+               int32_t* tokens_out_dev, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n < 0 || n > e->S || !slot_ids_dev || !chunk_dev || !wav_out_dev) { set_error("bad arguments to conan_step"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(emformer_step(e, n, slot_ids_dev, chunk_dev, nullptr, nullptr, tokens_out_dev, st));
+  TRY(decoder_step(e, n, slot_ids_dev, nullptr, mel_out_dev, st));
+  TRY(vocoder_step(e, n, slot_ids_dev, nullptr, wav_out_dev, st));
+  return 0;
+}
+
+int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
+                    float* mel_out_host, int32_t* tokens_out_host, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n < 0 || n > e->S || !slot_ids_host || !chunk_host || !wav_out_host) { set_error("bad arguments to conan_step_host"); return 1; }
+  const conan_config_t& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rows = c.segment + c.right_context, Lw = e->vL[c.voc_n_ups];
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->hIds, slot_ids_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->hChunk, chunk_host, (size_t)n * rows * c.emformer_dim * 4, cudaMemcpyHostToDevice, st));
+  TRY(conan_step(e, n, e->hIds, e->hChunk, e->hWav, mel_out_host ? e->hMel : nullptr, tokens_out_host ? e->hTok : nullptr, stream));
+  CONAN_CUDA_OK(cudaMemcpyAsync(wav_out_host, e->hWav, (size_t)n * Lw * 4, cudaMemcpyDeviceToHost, st));
+  if (mel_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out_host, e->hMel, (size_t)n * c.segment * c.n_mels * 4, cudaMemcpyDeviceToHost, st));
+  if (tokens_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(tokens_out_host, e->hTok, (size_t)n * c.segment * 4, cudaMemcpyDeviceToHost, st));
+  CONAN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int conan_debug_read(conan_engine_t* e, const char* name, int slot, float* out_dev, size_t capacity, size_t* numel, void* stream) {
+  if (check_ready(e)) return 1;
+  if (slot < 0 || slot >= e->S) { set_error("slot id out of range"); return 1; }
+  const conan_config_t& c = e->cfg;
+  const void* src = nullptr; size_t cnt = 0;
+  std::string nm(name ? name : "");
+  if (nm == "style") { src = e->sSTYLE + (size_t)slot * c.hidden_size; cnt = c.hidden_size; }
+  else if (nm == "kv_cache") { cnt = (size_t)2 * e->tp_max * 2 * c.hidden_size; src = e->sKV + (size_t)slot * cnt; }
+  else if (nm == "kpm") { cnt = e->tp_max; src = e->sKPM + (size_t)slot * cnt; }
+  else if (nm == "emformer_past_len") { cnt = 1; src = e->ePast + slot; }
+  else if (nm == "uv_pred") { cnt = (size_t)c.segment * 4; src = e->dUVP + (size_t)slot * cnt; }
+  else if (nm == "vq_index") { cnt = e->tp_max; src = e->qVQ; }   // compact index 0 of the last session batch
+  else { set_error("unknown debug tensor '" + nm + "'"); return 1; }
+  if (numel) *numel = cnt;
+  if (out_dev) {
+    if (capacity < cnt) { set_error("debug buffer too small"); return 1; }
+    CONAN_CUDA_OK(cudaMemcpyAsync(out_dev, src, cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+int conan_conv_gemm(const conan_conv_params_t* p, int engine, void* stream) {
+  if (!p) { set_error("null params"); return 1; }
+  if (engine == 1) {
+    if (!conv_gemm_tc_eligible(*p)) { set_error("conv_gemm: shape/dtype not eligible for the tcgen05 engine"); return 1; }
+    return launch_conv_gemm_tc(*p, (cudaStream_t)stream);
+  }
+  return launch_conv_gemm_ffma(*p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

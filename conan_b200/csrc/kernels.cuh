@@ -1,0 +1,93 @@
+// Launchers of the non-GEMM kernels of the path (norm / softmax / gather / ring kernels).
+// All of them are HBM/L2-bound, coalesced, vectorised where the layout allows, and use
+// warp-shuffle reductions; none of them goes near the tensor cores.
+#pragma once
+#include "common.cuh"
+
+namespace conan {
+
+// A strided view of per-slot rows: element (slot, t, c) lives at
+//   base[slot * slot_stride + (row0 + t) * row_stride + c].
+struct RowView {
+  void* base = nullptr;
+  long long slot_stride = 0;
+  int row_stride = 0;
+  int row0 = 0;
+  int is_half = 0;
+};
+inline RowView view_f32(float* p, long long ss, int rs, int r0 = 0) { return RowView{p, ss, rs, r0, 0}; }
+
+struct LnArgs {
+  RowView in;            // fp32
+  RowView out;           // fp32 or fp16
+  const float* gamma; const float* beta; float eps;
+  int C, L, n;
+  const int* slot_ids;
+  const float* premask; int premask_slot_stride;    // x *= premask[slot, t] before the statistics
+  const float* postmask; int postmask_slot_stride;  // y *= postmask[slot, t]
+  float* write_mask; int write_mask_slot_stride;     // mask[slot, t] = (sum_c |x| > 0) of the raw input
+  float* write_mask2;                                // optional second copy (same stride)
+};
+int launch_layernorm(const LnArgs& a, cudaStream_t st);
+
+// Emformer ------------------------------------------------------------------------------
+// chunk [n, seg+rc, D] (utterance rows first) -> X[slot] rows ordered [rc | utt] (TA:430)
+int launch_emformer_assemble(const float* chunk, float* X, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st);
+// per stream: append utterance K/V rows to the ring, softmax(QK^T) V over [rc | left ctx | utt]
+int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, float* att, int n,
+                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, cudaStream_t st);
+int launch_advance_past_len(int* past_len, int n, const int* slot_ids, int seg, cudaStream_t st);
+int launch_argmax_rows(const float* logits, int* tokens_slot, int* tokens_out, int n, const int* slot_ids, int rows, int C, cudaStream_t st);
+int launch_copy_rows_out(const float* src_slot, long long slot_stride, int row_stride, int row0, float* dst, int n,
+                         const int* slot_ids, int rows, int C, cudaStream_t st);
+int launch_copy_rows_in(const void* src, int src_is_int, void* dst_slot, long long slot_stride_elems, int n,
+                        const int* slot_ids, int elems, cudaStream_t st);
+
+// Conan chunk path -------------------------------------------------------------------------
+int launch_embedding_rows(const int* tokens_slot, const float* table, int vocab, RowView out, int n, const int* slot_ids,
+                          int rows, int C, cudaStream_t st);
+// nn.MultiheadAttention(256, 2) over the session-cached K/V (prosody_util.py:108-127)
+int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, float* out, int n,
+                           const int* slot_ids, int rows, int H, int heads, int layer, int n_layers, int tp_max, cudaStream_t st);
+// out1 = a + b (fp32), optional second copy into a context buffer
+int launch_add_rows(const float* a, const float* b, float* out1, RowView out2, int n, const int* slot_ids, int rows, int C, cudaStream_t st);
+// uv_predictor tail + pitch embedding (nar_tts_modules.py:142-146, Conan.py:324-351, pitch/utils.py:17-28,71-82)
+int launch_pitch(const float* h, const float* ln_g, const float* ln_b, const float* lin_w, const float* lin_b,
+                 const int* tokens_slot, int silent_token, const float* pitch_table, const float* pitch_inp,
+                 float* dec_inp, float* uv_pred_out, int n, const int* slot_ids, int rows, int Cuv, int H, cudaStream_t st);
+
+// fp32 rows [slot, rows, C] -> a (possibly fp16) context-buffer view
+int launch_rows_to_view(const float* src_slot, RowView out, int n, const int* slot_ids, int rows, int C, cudaStream_t st);
+
+// vocoder ------------------------------------------------------------------------------------
+int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, int row_stride, int row0, int L, int C, int k,
+                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st);
+
+// state maintenance --------------------------------------------------------------------------
+struct RingDesc { void* base; long long slot_stride_bytes; int hist_bytes; int new_bytes; };
+// for every listed ring and active slot: move the last hist_bytes of [hist | new] to the front
+int launch_ring_shift(const RingDesc* rings_dev, int n_rings, int max_hist_bytes, int n, const int* slot_ids, cudaStream_t st);
+struct ZeroDesc { void* base; long long slot_stride_bytes; long long bytes; };
+int launch_zero_slots(const ZeroDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st);
+
+// session setup ------------------------------------------------------------------------------
+// mask[i,t] = (sum_c |x[i,t,c]| > 0)   /   mask[i,t] = (x[i,t,0] != 0)
+int launch_row_masks(const float* ref, float* mask_abs, float* mask_first, int n, int T, int C, cudaStream_t st);
+int launch_gated_tanh_sigmoid(const float* in, float* out, long long rows, int C, cudaStream_t st);   // in [rows,2C] -> out [rows,C]
+// WN residual/skip update (wavenet.py:79-85): x = (x + rs[:, :C]) * mask ; skip += rs[:, C:]   (last: skip += rs)
+int launch_wn_update(const float* rs, float* x, RowView x_ctx, float* skip, const float* mask, long long rows, int T, int C,
+                     int last, cudaStream_t st);
+// mean over groups of 4 frames of (skip * mask)  (seq_utils.py:307-325) -> [n, Tp, C]
+int launch_group_mean4(const float* skip, const float* mask, float* out, int n, int T, int Tp, int C, cudaStream_t st);
+// VQ (prosody_util.py:34-46, 88): idx = argmin_e |x|^2 + |e|^2 - 2 x.e ; z = x + (E[idx] - x); zcat = [z | sinusoid(pos)]
+int launch_vq_quantize(const float* x, const float* xe, const float* E, const float* e2, const float* pos_table, float* zcat, int* idx_out,
+                       int n, int Tp, int H, int n_codes, cudaStream_t st);
+// key padding mask of the aligner (Conan.py:249): kpm[slot, p] = (pe[i, p, 0] == 0); also n_keys[slot] = Tp
+int launch_kpm(const float* pe, float* kpm, int* n_keys, const int* slots_dev, int n, int Tp, int H, int tp_max, cudaStream_t st);
+// masked temporal mean (Conan.py:214-219): style[slot, c] = sum_t x*mask / sum_t mask
+int launch_masked_time_mean(const float* x, const float* mask, float* style, const int* slots_dev, int n, int T, int C, cudaStream_t st);
+// scatter session K/V [n, Tp, 2H] -> cache[slot, layer, tp_max, 2H]
+int launch_scatter_kv(const float* kv, float* cache, const int* slots_dev, int n, int Tp, int H2, int layer, int n_layers,
+                      int tp_max, cudaStream_t st);
+
+}  // namespace conan

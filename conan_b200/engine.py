@@ -1,0 +1,199 @@
+"""Python handle on the native engine (libconan_b200.so).
+
+PyTorch is used for device memory, streams and host<->device copies only; every op on
+the path is a hand-written CUDA kernel behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import DEFAULT_HP, DEFAULT_VOC_HP
+from .weights import pack_engine_weights
+
+PARTS_EMFORMER, PARTS_CONAN, PARTS_VOCODER, PARTS_ALL = 1, 2, 4, 7
+
+
+def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max_slots: int = 64,
+                max_ref_frames: int = 512, device: int = 0, voc_precision: str = "fp16",
+                voc_tensor_cores: bool = True, voc_group: int = 0) -> _lib.ConanConfig:
+    """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
+    SURVEY.md section 5)."""
+    hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
+    vh = {**DEFAULT_VOC_HP, **{k: v for k, v in (voc_hp or {}).items() if v is not None}}
+    if vh.get("upsample", "shuffle") != "shuffle":
+        raise ValueError("only upsample: 'shuffle' (CausalUpsampleBlock3) is on the hot path")
+    if str(vh.get("resblock", "1")) != "1":
+        raise ValueError("only resblock: '1' is on the hot path")
+    if hp.get("decoder_type", "conv") != "conv" or hp.get("f0_gen", "orig") != "orig" or not hp.get("style", True):
+        raise ValueError("config outside the hot path (decoder_type conv, f0_gen orig, style true)")
+    dil = vh["resblock_dilation_sizes"]
+    if any(list(d) != list(dil[0]) for d in dil):
+        raise ValueError("resblock_dilation_sizes must be the same for every kernel size")
+    cfg = _lib.ConanConfig()
+    cfg.abi_version = _lib.ABI_VERSION
+    cfg.device, cfg.max_slots, cfg.max_ref_frames = device, max_slots, max_ref_frames
+    cfg.emformer_layers, cfg.emformer_dim, cfg.emformer_heads, cfg.emformer_ffn = hp["emformer_layers"], 80, 8, 2048
+    cfg.segment, cfg.right_context, cfg.left_context = hp["chunk_size"] // 20, hp["right_context"], 50
+    cfg.emformer_output_dim = hp["emformer_output_dim"]
+    cfg.hidden_size, cfg.content_kernel = hp["hidden_size"], hp["kernel_size"]
+    cfg.dec_blocks, cfg.dec_kernel = len(hp["dec_dilations"]), hp["dec_kernel_size"]
+    if any(d != 1 for d in hp["dec_dilations"]) or hp["layers_in_block"] != 2:
+        raise ValueError("decoder dilations must be 1 and layers_in_block 2")
+    cfg.dec_post_kernel, cfg.predictor_kernel = hp["dec_post_net_kernel"], hp["predictor_kernel"]
+    cfg.n_vq, cfg.silent_token, cfg.n_mels = hp["nVQ"], hp["silent_token"], hp["audio_num_mel_bins"]
+    cfg.voc_initial_channel = vh["upsample_initial_channel"]
+    cfg.voc_n_ups = len(vh["upsample_rates"])
+    for i, (r, k) in enumerate(zip(vh["upsample_rates"], vh["upsample_kernel_sizes"])):
+        cfg.voc_rates[i], cfg.voc_up_kernels[i] = r, k
+    cfg.voc_n_res = len(vh["resblock_kernel_sizes"])
+    for i, k in enumerate(vh["resblock_kernel_sizes"]):
+        cfg.voc_res_kernels[i] = k
+    cfg.voc_n_dil = len(dil[0])
+    for i, d in enumerate(dil[0]):
+        cfg.voc_res_dilations[i] = d
+    cfg.voc_precision = {"fp32": 0, "fp16": 1}[voc_precision]
+    cfg.voc_use_tensor_cores = int(bool(voc_tensor_cores) and cfg.voc_precision == 1)
+    cfg.voc_group = voc_group
+    return cfg
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """Owns the native engine, the bound weight tensors and the resident per-slot state."""
+
+    def __init__(self, sd_conan, sd_emformer, sd_voc, cfg: _lib.ConanConfig):
+        if not torch.cuda.is_available():
+            raise RuntimeError("conan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device("cuda", cfg.device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        _lib.check(self.lib.conan_engine_create(C.byref(cfg), C.byref(h)), "engine_create")
+        self.h = h
+        packed = pack_engine_weights(sd_conan, sd_emformer, sd_voc, cfg)
+        self._weights = {}
+        nw = self.lib.conan_engine_num_weights(self.h)
+        name, numel, dtype = C.c_char_p(), C.c_size_t(), C.c_int()
+        for i in range(nw):
+            _lib.check(self.lib.conan_engine_weight_info(self.h, i, C.byref(name), C.byref(numel), C.byref(dtype)), "weight_info")
+            key = name.value.decode()
+            if key not in packed:
+                raise KeyError(f"packer produced no tensor for engine weight '{key}'")
+            want = {0: torch.float32, 1: torch.float16, 2: torch.int32}[dtype.value]
+            t = packed[key].to(want).contiguous().to(self.device)
+            self._weights[key] = t
+            _lib.check(self.lib.conan_engine_bind_weight(self.h, key.encode(), _ptr(t), t.numel(), dtype.value), f"bind {key}")
+        _lib.check(self.lib.conan_engine_finalize(self.h), "finalize")
+        self.segment = cfg.segment
+        self.rows_in = cfg.segment + cfg.right_context
+        self.hop_out = cfg.segment
+        for i in range(cfg.voc_n_ups):
+            self.hop_out *= cfg.voc_rates[i]
+        self.n_mels = cfg.n_mels
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.conan_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def state_bytes(self) -> int:
+        return int(self.lib.conan_engine_state_bytes(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.conan_engine_launch_count(self.h))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _host_ids(slots: Sequence[int]):
+        arr = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        return arr, arr.ctypes.data_as(C.c_void_p)
+
+    def ids_tensor(self, slots: Sequence[int]) -> torch.Tensor:
+        return torch.as_tensor(np.asarray(slots, dtype=np.int32), device=self.device)
+
+    # ------------------------------------------------------------------ state
+    def reset_slots(self, slots: Sequence[int], parts: int = PARTS_ALL):
+        arr, p = self._host_ids(slots)
+        _lib.check(self.lib.conan_slots_reset(self.h, len(arr), p, parts, self._stream()), "slots_reset")
+
+    def open_sessions(self, slots: Sequence[int], ref_mel: torch.Tensor):
+        """ref_mel [n, T_ref, n_mels] fp32 on the device (same T_ref for the whole call)."""
+        assert ref_mel.dim() == 3 and ref_mel.shape[0] == len(slots) and ref_mel.shape[2] == self.n_mels
+        ref_mel = ref_mel.to(self.device, torch.float32).contiguous()
+        arr, p = self._host_ids(slots)
+        _lib.check(self.lib.conan_session_open(self.h, len(arr), p, _ptr(ref_mel), ref_mel.shape[1], self._stream()), "session_open")
+
+    # ------------------------------------------------------------------ steps (device tensors)
+    def emformer_step(self, ids: torch.Tensor, chunk: torch.Tensor, want_enc=False, want_logits=False):
+        n = ids.numel()
+        assert chunk.shape == (n, self.rows_in, self.cfg.emformer_dim) and chunk.dtype == torch.float32 and chunk.is_contiguous()
+        tokens = torch.empty(n, self.segment, dtype=torch.int32, device=self.device)
+        enc = torch.empty(n, self.segment, self.cfg.emformer_dim, device=self.device) if want_enc else None
+        logits = torch.empty(n, self.segment, self.cfg.emformer_output_dim, device=self.device) if want_logits else None
+        _lib.check(self.lib.conan_emformer_step(self.h, n, _ptr(ids), _ptr(chunk), _ptr(enc), _ptr(logits), _ptr(tokens), self._stream()), "emformer_step")
+        return tokens, enc, logits
+
+    def decoder_step(self, ids: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
+        n = ids.numel()
+        assert tokens.shape == (n, self.segment) and tokens.dtype == torch.int32 and tokens.is_contiguous()
+        mel = torch.empty(n, self.segment, self.n_mels, device=self.device)
+        _lib.check(self.lib.conan_decoder_step(self.h, n, _ptr(ids), _ptr(tokens), _ptr(mel), self._stream()), "decoder_step")
+        return mel
+
+    def vocoder_step(self, ids: torch.Tensor, mel: torch.Tensor) -> torch.Tensor:
+        n = ids.numel()
+        assert mel.shape == (n, self.segment, self.n_mels) and mel.dtype == torch.float32 and mel.is_contiguous()
+        wav = torch.empty(n, self.hop_out, device=self.device)
+        _lib.check(self.lib.conan_vocoder_step(self.h, n, _ptr(ids), _ptr(mel), _ptr(wav), self._stream()), "vocoder_step")
+        return wav
+
+    def step(self, ids: torch.Tensor, chunk: torch.Tensor, wav: Optional[torch.Tensor] = None,
+             mel: Optional[torch.Tensor] = None, tokens: Optional[torch.Tensor] = None, want_mel=True, want_tokens=True):
+        n = ids.numel()
+        assert chunk.shape == (n, self.rows_in, self.cfg.emformer_dim) and chunk.dtype == torch.float32 and chunk.is_contiguous()
+        if wav is None:
+            wav = torch.empty(n, self.hop_out, device=self.device)
+        if mel is None and want_mel:
+            mel = torch.empty(n, self.segment, self.n_mels, device=self.device)
+        if tokens is None and want_tokens:
+            tokens = torch.empty(n, self.segment, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.conan_step(self.h, n, _ptr(ids), _ptr(chunk), _ptr(wav), _ptr(mel), _ptr(tokens), self._stream()), "step")
+        return wav, mel, tokens
+
+    # ------------------------------------------------------------------ step with HOST buffers (the plugin call)
+    def step_host(self, slots: np.ndarray, chunk: np.ndarray, wav_out: np.ndarray, mel_out: Optional[np.ndarray] = None,
+                  tokens_out: Optional[np.ndarray] = None):
+        n = len(slots)
+        assert slots.dtype == np.int32 and chunk.dtype == np.float32 and chunk.shape == (n, self.rows_in, self.cfg.emformer_dim)
+        assert wav_out.dtype == np.float32 and wav_out.shape == (n, self.hop_out)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _lib.check(self.lib.conan_step_host(self.h, n, vp(slots), vp(chunk), vp(wav_out), vp(mel_out), vp(tokens_out), self._stream()), "step_host")
+
+    # ------------------------------------------------------------------ debug
+    def debug_read(self, name: str, slot: int) -> torch.Tensor:
+        numel = C.c_size_t()
+        _lib.check(self.lib.conan_debug_read(self.h, name.encode(), slot, None, 0, C.byref(numel), self._stream()), "debug_read")
+        out = torch.empty(numel.value, device=self.device)
+        _lib.check(self.lib.conan_debug_read(self.h, name.encode(), slot, _ptr(out), out.numel(), C.byref(numel), self._stream()), "debug_read")
+        return out

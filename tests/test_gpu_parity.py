@@ -1,0 +1,426 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, against the golden vectors of the unmodified reference, and through
+size-independent properties.  Run on the B200 box:  pytest tests -m gpu
+
+Tolerances (BASELINE.json north_star): mel max-abs <= 1e-3 with fp32 operands, waveform
+SNR >= 40 dB vs the reference; tokens (argmax) must agree exactly on these seeds.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conan_b200 import synth
+from util import snr_ac_db, snr_db
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-3
+SNR_MIN_DB = 40.0
+
+
+NO_TC = bool(os.environ.get("CONAN_TEST_NO_TC"))      # first-bring-up switch: run everything on the FFMA engine only
+
+
+def _engine(state_dicts, **kw):
+    from conan_b200.engine import Engine, make_config
+    if NO_TC:
+        kw["voc_tensor_cores"] = False
+    kw.setdefault("max_slots", 8)
+    kw.setdefault("max_ref_frames", 256)
+    cfg = make_config(**kw)
+    return Engine(*state_dicts, cfg)
+
+
+@pytest.fixture(scope="module")
+def eng_fp32(state_dicts):
+    e = _engine(state_dicts, voc_precision="fp32", voc_tensor_cores=False)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_fp16_ffma(state_dicts):
+    e = _engine(state_dicts, voc_precision="fp16", voc_tensor_cores=False)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_tc(state_dicts):
+    e = _engine(state_dicts, voc_precision="fp16", voc_tensor_cores=True)
+    yield e
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------
+# operator level
+# ------------------------------------------------------------------------------------------
+def _conv_reference(ctx, w, bias, k, dil, L, row0):
+    """ctx [S, rows, cin] float64, w [cout, cin, k] float64 -> [S, L, cout]"""
+    x = ctx[:, row0:row0 + L + (k - 1) * dil].transpose(1, 2)
+    return F.conv1d(x, w, bias, dilation=dil).transpose(1, 2)
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,L,S", [
+    (80, 240, 1, 1, 6, 5), (80, 2048, 1, 1, 6, 3), (2048, 80, 1, 1, 6, 3), (256, 512, 5, 1, 4, 7),
+    (256, 256, 3, 1, 4, 2), (80, 100, 1, 1, 4, 9), (256, 512, 31, 1, 50, 2), (32, 32, 11, 5, 1280, 2),
+    (128, 2, 1, 1, 4, 3),
+])
+def test_conv_gemm_ffma_fp32_vs_torch(cin, cout, k, dil, L, S):
+    from conan_b200 import ops
+    from conan_b200.weights import pack_conv
+    g = torch.Generator().manual_seed(cin * 7 + cout + k)
+    H = (k - 1) * dil
+    ctx = torch.randn(S, H + L, cin, generator=g)
+    w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(S, L, cout, generator=g)
+    ref = _conv_reference(ctx.double(), w.double(), b.double(), k, dil, L, 0)
+    ref = F.leaky_relu(ref * 0.5, 0.1) + res.double()
+    y = torch.zeros(S, L, cout, device="cuda")
+    ops.conv_gemm(ctx.cuda(), pack_conv(w).cuda(), b.cuda(), k=k, dil=dil, L=L, row0=0, scale=0.5, act="lrelu", slope=0.1,
+                  res=res.cuda(), y=y)
+    err = (y.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5, err
+
+
+def test_conv_gemm_slot_indirection_and_outputs():
+    from conan_b200 import ops
+    from conan_b200.weights import pack_conv
+    g = torch.Generator().manual_seed(3)
+    S, cin, cout, k, dil, L = 6, 64, 64, 3, 3, 32
+    H = (k - 1) * dil
+    ctx = torch.randn(S, H + L, cin, generator=g)
+    w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ids = torch.tensor([4, 1, 5], dtype=torch.int32)
+    y = torch.full((S, L, cout), 7.0, device="cuda")
+    y2 = torch.zeros(S, 10 + L, cout, device="cuda")
+    mask = (torch.rand(S, L, generator=g) > 0.3).float()
+    ops.conv_gemm(ctx.cuda(), pack_conv(w).cuda(), b.cuda(), k=k, dil=dil, L=L, row0=0, slot_ids=ids.cuda(), y=y, accumulate=True,
+                  out_scale=1 / 3, rowmask=mask.cuda(), y2=y2, y2_row0=10, act2="lrelu", slope2=0.1)
+    ref = _conv_reference(ctx.double(), w.double(), b.double(), k, dil, L, 0) * mask[:, :, None].double() / 3 + 7.0
+    yc = y.cpu().double()
+    for s in range(S):
+        if s in (4, 1, 5):
+            assert (yc[s] - ref[s]).abs().max() < 2e-5
+            assert (y2.cpu().double()[s, 10:] - F.leaky_relu(ref[s], 0.1)).abs().max() < 2e-5
+            assert (y2.cpu()[s, :10] == 0).all()
+        else:
+            assert (yc[s] == 7.0).all() and (y2.cpu()[s] == 0).all()          # untouched slots
+
+
+TC_SHAPES = [
+    # cin, cout, k, dil, L, S      (the vocoder's layers: MRF convs per scale, upsampling convs)
+    (256, 256, 3, 1, 32, 5), (256, 256, 11, 5, 32, 4), (256, 256, 7, 3, 32, 9),
+    (128, 128, 7, 3, 160, 3), (128, 128, 11, 1, 160, 2),
+    (64, 64, 11, 5, 640, 2), (64, 64, 3, 1, 640, 1),
+    (32, 32, 3, 1, 1280, 2), (32, 32, 11, 5, 1280, 1), (32, 32, 7, 3, 1280, 3),
+    (256, 640, 10, 1, 32, 6), (128, 256, 8, 1, 160, 2), (64, 64, 4, 1, 640, 2), (512, 2048, 16, 1, 4, 40),
+]
+
+
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+@pytest.mark.parametrize("cin,cout,k,dil,L,S", TC_SHAPES)
+def test_conv_gemm_tcgen05_vs_ffma_and_torch(cin, cout, k, dil, L, S):
+    from conan_b200 import ops
+    from conan_b200.weights import pack_conv
+    g = torch.Generator().manual_seed(cin + 3 * cout + 5 * k + dil)
+    H = (k - 1) * dil + 2                       # two spare history rows: row0 = 2 exercises the row offset
+    nslots = S + 2
+    ctx = (torch.randn(nslots, H + L, cin, generator=g) * 0.5).half()
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).half()
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(nslots, L, cout, generator=g)
+    ids = torch.randperm(nslots, generator=g)[:S].to(torch.int32)
+    ref = _conv_reference(ctx.double(), w.double(), b.double(), k, dil, L, 2) + res.double()
+    outs = {}
+    for name, engine in (("ffma", ops.ENGINE_FFMA), ("tc", ops.ENGINE_TC)):
+        y = torch.zeros(nslots, L, cout, device="cuda")
+        y2 = torch.zeros(nslots, 4 + L, cout, device="cuda", dtype=torch.float16)
+        ops.conv_gemm(ctx.cuda(), pack_conv(w).cuda(), b.cuda(), k=k, dil=dil, L=L, row0=2, slot_ids=ids.cuda(), engine=engine,
+                      res=res.cuda(), y=y, y2=y2, y2_row0=4, act2="lrelu", slope2=0.1)
+        torch.cuda.synchronize()
+        outs[name] = (y.cpu(), y2.cpu())
+    sel = ids.long()
+    for name in ("ffma", "tc"):
+        err = (outs[name][0][sel].double() - ref[sel]).abs().max().item()
+        assert err < 1e-4, (name, err)
+    assert (outs["tc"][0] - outs["ffma"][0]).abs().max().item() < 1e-4
+    assert (outs["tc"][1].float() - outs["ffma"][1].float()).abs().max().item() < 4e-3      # one fp16 ulp at |v| < 4
+    untouched = [s for s in range(nslots) if s not in set(sel.tolist())]
+    assert (outs["tc"][0][untouched] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------
+# Emformer
+# ------------------------------------------------------------------------------------------
+def _chunks(src, pos):
+    from oracle.incremental import assemble_chunk
+    c, emit = assemble_chunk(src, pos)
+    return c.contiguous(), emit
+
+
+def test_emformer_step_vs_oracle_lockstep(state_dicts, eng_fp32):
+    from oracle.incremental import EmformerOracle
+    eng = eng_fp32
+    B, T = 3, 72                                   # 18 chunks: left context saturates at 50 and the 56-row ring wraps
+    src = torch.stack([synth.synth_mel(T, 40 + s) for s in range(B)])
+    o = EmformerOracle(state_dicts[1])
+    o.reset(B)
+    slots = [5, 0, 3]
+    eng.reset_slots(slots)
+    ids = eng.ids_tensor(slots)
+    worst, worst_logit = 0.0, 0.0
+    for pos in range(0, T, 4):
+        chunk, _ = _chunks(src, pos)
+        with torch.no_grad():
+            enc_ref = o.step(chunk)
+            logit_ref = o.logits(enc_ref)
+        tok, enc, logits = eng.emformer_step(ids, chunk.cuda(), want_enc=True, want_logits=True)
+        worst = max(worst, (enc.cpu() - enc_ref).abs().max().item())
+        worst_logit = max(worst_logit, (logits.cpu() - logit_ref).abs().max().item())
+        assert (tok.cpu().long() == logit_ref.argmax(-1)).all(), f"token mismatch at pos {pos}"
+    print("emformer enc max-abs", worst, "logits max-abs", worst_logit)
+    assert worst < 1e-4 and worst_logit < 1e-4
+    assert int(eng.debug_read("emformer_past_len", 5).view(torch.int32)[0]) == T
+
+
+def test_emformer_staggered_streams_match_independent_runs(state_dicts, eng_fp32):
+    """Streams of different ages packed into one launch (per-stream past_len) must equal
+    independent B=1 runs -- the case torchaudio's batched infer cannot express (TA:392)."""
+    from oracle.incremental import EmformerOracle
+    eng = eng_fp32
+    T = 40
+    srcs = [synth.synth_mel(T, 70 + s)[None] for s in range(3)]
+    starts = [0, 2, 5]                              # stream s joins at global step starts[s]
+    oracles = [EmformerOracle(state_dicts[1]) for _ in range(3)]
+    for o in oracles:
+        o.reset(1)
+    slots = [2, 6, 1]
+    eng.reset_slots(slots)
+    for step in range(12):
+        active = [s for s in range(3) if step >= starts[s] and (step - starts[s]) * 4 < T]
+        if not active:
+            continue
+        chunks, refs = [], []
+        for s in active:
+            c, _ = _chunks(srcs[s], (step - starts[s]) * 4)
+            chunks.append(c)
+            with torch.no_grad():
+                refs.append(oracles[s].step(c))
+        ids = eng.ids_tensor([slots[s] for s in active])
+        _, enc, _ = eng.emformer_step(ids, torch.cat(chunks).cuda(), want_enc=True)
+        err = (enc.cpu() - torch.cat(refs)).abs().max().item()
+        assert err < 1e-4, (step, err)
+
+
+# ------------------------------------------------------------------------------------------
+# Conan main model
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t_ref", [150, 64, 9])
+def test_session_open_vs_oracle(state_dicts, eng_fp32, t_ref):
+    from oracle.incremental import ConanOracle
+    eng = eng_fp32
+    B = 2
+    ref = torch.stack([synth.synth_mel(t_ref, 11 + s) for s in range(B)])
+    o = ConanOracle(state_dicts[0])
+    with torch.no_grad():
+        dbg = o.open(ref, return_debug=True)
+    slots = [3, 6]
+    eng.open_sessions(slots, ref.cuda())
+    Tp = (t_ref - 1) // 4 + 1
+    tp_max = (eng.cfg.max_ref_frames - 1) // 4 + 1
+    for i, s in enumerate(slots):
+        style = eng.debug_read("style", s).cpu()
+        assert (style - o.style[i]).abs().max().item() < 1e-4
+        kv = eng.debug_read("kv_cache", s).cpu().view(2, tp_max, 2, 256)
+        for l in range(2):
+            assert (kv[l, :Tp, 0] - o.K[l][i]).abs().max().item() < 2e-4
+            assert (kv[l, :Tp, 1] - o.V[l][i]).abs().max().item() < 2e-4
+        kpm = eng.debug_read("kpm", s).cpu()
+        assert (kpm[:Tp] == o.kpm[i].float()).all() and (kpm[Tp:] == 1).all()
+    idx = eng.debug_read("vq_index", 0).view(torch.int32).cpu()[:Tp]
+    assert (idx.long() == dbg["vq_idx"][0]).all()
+
+
+def test_decoder_step_vs_oracle_teacher_forced(state_dicts, eng_fp32):
+    from oracle.incremental import ConanOracle
+    eng = eng_fp32
+    B, n_chunks = 3, 14                              # 56 frames: longer than the 56-frame receptive field of the chunk path
+    ref = torch.stack([synth.synth_mel(90, 21 + s) for s in range(B)])
+    g = torch.Generator().manual_seed(9)
+    tokens = torch.randint(0, 100, (B, n_chunks * 4), generator=g)
+    tokens[0, 5:9] = 57                              # silent_token forces unvoiced (Conan.py:335-338)
+    o = ConanOracle(state_dicts[0])
+    slots = [1, 4, 2]
+    eng.reset_slots(slots)
+    eng.open_sessions(slots, ref.cuda())
+    ids = eng.ids_tensor(slots)
+    worst = 0.0
+    buckets = set()
+    with torch.no_grad():
+        o.open(ref)
+        for c in range(n_chunks):
+            tk = tokens[:, c * 4:(c + 1) * 4]
+            mel_ref, dbg = o.step(tk, return_debug=True)
+            mel = eng.decoder_step(ids, tk.to(torch.int32).contiguous().cuda())
+            worst = max(worst, (mel.cpu() - mel_ref).abs().max().item())
+            for i, s in enumerate(slots):
+                uvp = eng.debug_read("uv_pred", s).cpu().view(4, 4)
+                assert (uvp[:, 3].long() == dbg["pitch"][i]).all(), "f0 bucket mismatch"
+                buckets.update(dbg["pitch"][i].tolist())
+    print("decoder mel max-abs", worst, "distinct f0 buckets", len(buckets))
+    assert worst < MEL_TOL
+    assert len(buckets) > 8                          # the bucket arithmetic is genuinely exercised
+
+
+# ------------------------------------------------------------------------------------------
+# vocoder
+# ------------------------------------------------------------------------------------------
+def _run_vocoder(eng, mel, slots):
+    eng.reset_slots(slots)
+    ids = eng.ids_tensor(slots)
+    outs = []
+    for i in range(0, mel.shape[1], 4):
+        outs.append(eng.vocoder_step(ids, mel[:, i:i + 4].contiguous().cuda()).cpu())
+    return torch.cat(outs, 1)
+
+
+def test_vocoder_fp32_vs_oracle_and_golden(state_dicts, eng_fp32, golden_dir):
+    from oracle.incremental import HifiGanOracle
+    d = np.load(os.path.join(golden_dir, "vocoder_24f.npz"))
+    mel = torch.from_numpy(d["mel"])[None].repeat(2, 1, 1)
+    mel[1] = mel[1].flip(0)
+    o = HifiGanOracle(state_dicts[2])
+    o.reset(2)
+    with torch.no_grad():
+        ref = torch.cat([o.step(mel[:, i:i + 4]) for i in range(0, 24, 4)], 1)
+    wav = _run_vocoder(eng_fp32, mel, [7, 2])
+    err = (wav - ref).abs().max().item()
+    print("vocoder fp32 max-abs vs oracle", err, "SNR_ac vs reference golden", snr_ac_db(d["wav"], wav[0].numpy()))
+    assert err < 1e-4
+    assert np.abs(wav[0].numpy() - d["wav"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("which", ["eng_fp16_ffma", "eng_tc"])
+def test_vocoder_fp16_operands_snr(which, request, golden_dir):
+    eng = request.getfixturevalue(which)
+    d = np.load(os.path.join(golden_dir, "vocoder_24f.npz"))
+    mel = torch.from_numpy(d["mel"])[None]
+    wav = _run_vocoder(eng, mel, [3])[0].numpy()
+    s, sa = snr_db(d["wav"], wav), snr_ac_db(d["wav"], wav)
+    print(which, "SNR", s, "SNR_ac", sa)
+    assert sa >= SNR_MIN_DB
+
+
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+def test_vocoder_tcgen05_matches_ffma_same_operands(eng_fp16_ffma, eng_tc):
+    """Same fp16 operands, fp32 accumulation in TMEM vs in registers: only summation order differs."""
+    mel = (torch.randn(3, 16, 80, generator=torch.Generator().manual_seed(2)) * 0.6)
+    a = _run_vocoder(eng_fp16_ffma, mel, [0, 1, 2])
+    b = _run_vocoder(eng_tc, mel, [4, 6, 5])
+    err = (a - b).abs().max().item()
+    print("tcgen05 vs ffma (fp16 operands) max-abs", err, "SNR", snr_db(a.numpy(), b.numpy()))
+    assert snr_db(a.numpy(), b.numpy()) > 55.0
+
+
+def test_vocoder_group_blocking_is_exact(state_dicts):
+    """voc_group (L2 blocking over streams) must not change results."""
+    mel = (torch.randn(6, 8, 80, generator=torch.Generator().manual_seed(4)) * 0.6)
+    e1 = _engine(state_dicts, voc_group=0)
+    a = _run_vocoder(e1, mel, [0, 1, 2, 3, 4, 5])
+    e1.close()
+    e2 = _engine(state_dicts, voc_group=4)
+    b = _run_vocoder(e2, mel, [0, 1, 2, 3, 4, 5])
+    e2.close()
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# end to end against the unmodified reference's golden vectors
+# ------------------------------------------------------------------------------------------
+def _run_e2e(eng, ref, src, slots):
+    B, T, _ = src.shape
+    eng.reset_slots(slots)
+    eng.open_sessions(slots, ref.cuda())
+    ids = eng.ids_tensor(slots)
+    wavs, mels, toks = [], [], []
+    for pos in range(0, T, 4):
+        chunk, emit = _chunks(src, pos)
+        wav, mel, tok = eng.step(ids, chunk.cuda())
+        wavs.append(wav.cpu()[:, :emit * 320]), mels.append(mel.cpu()[:, :emit]), toks.append(tok.cpu()[:, :emit])
+    return torch.cat(wavs, 1), torch.cat(mels, 1), torch.cat(toks, 1)
+
+
+@pytest.mark.parametrize("which,name", [("eng_fp32", "e2e_short"), ("eng_tc", "e2e_short"), ("eng_tc", "e2e_long")])
+def test_end_to_end_vs_reference_golden(which, name, request, golden_dir):
+    eng = request.getfixturevalue(which)
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    ref = synth.synth_mel(int(d["ref_frames"]), int(d["ref_seed"]))[None]
+    src = synth.synth_mel(int(d["src_frames"]), int(d["src_seed"]))[None]
+    wav, mel, tok = _run_e2e(eng, ref, src, [4])
+    wav, mel, tok = wav[0].numpy(), mel[0].numpy(), tok[0].numpy()
+    assert wav.shape == d["wav"].shape and mel.shape == d["mel"].shape
+    agree = (tok == d["tokens"]).mean()
+    mel_err = np.abs(mel - d["mel"]).max()
+    s, sa = snr_db(d["wav"], wav), snr_ac_db(d["wav"], wav)
+    print(which, name, "token agreement", agree, "mel max-abs", mel_err, "wav SNR", s, "SNR_ac", sa)
+    assert agree == 1.0
+    assert mel_err <= MEL_TOL
+    assert sa >= SNR_MIN_DB
+    if which == "eng_fp32":
+        assert np.abs(wav - d["wav"]).max() < 2e-4
+
+
+def test_step_host_equals_device_step(eng_tc):
+    eng = eng_tc
+    ref = torch.stack([synth.synth_mel(40, 5), synth.synth_mel(40, 6)])
+    src = torch.stack([synth.synth_mel(12, 7), synth.synth_mel(12, 8)])
+    wav_a, mel_a, tok_a = _run_e2e(eng, ref, src, [0, 1])
+    slots = np.array([2, 3], dtype=np.int32)
+    eng.reset_slots(slots)
+    eng.open_sessions(slots, ref.cuda())
+    wavs = []
+    for pos in range(0, 12, 4):
+        chunk, _ = _chunks(src, pos)
+        wav = np.empty((2, 1280), dtype=np.float32)
+        mel = np.empty((2, 4, 80), dtype=np.float32)
+        tok = np.empty((2, 4), dtype=np.int32)
+        eng.step_host(slots, chunk.numpy(), wav, mel, tok)
+        wavs.append(torch.from_numpy(wav.copy()))
+    assert torch.equal(torch.cat(wavs, 1), wav_a)
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at a larger stream count
+# ------------------------------------------------------------------------------------------
+def test_replicated_streams_are_bitwise_identical_and_slot_order_free(state_dicts):
+    """64 streams fed the same session/input must produce bit-identical outputs regardless of
+    their slot or their position in the ready list (packing never mixes streams)."""
+    eng = _engine(state_dicts, max_slots=64, max_ref_frames=64)
+    S = 64
+    ref = synth.synth_mel(48, 3)[None].repeat(S, 1, 1)
+    src = synth.synth_mel(16, 4)[None].repeat(S, 1, 1)
+    perm = torch.randperm(S, generator=torch.Generator().manual_seed(0)).tolist()
+    wav, mel, tok = _run_e2e(eng, ref, src, perm)
+    assert (wav == wav[0:1]).all() and (mel == mel[0:1]).all() and (tok == tok[0:1]).all()
+    single, mel1, _ = _run_e2e(eng, ref[:1], src[:1], [9])
+    assert torch.equal(single[0], wav[0]) and torch.equal(mel1[0], mel[0])
+    eng.close()
+
+
+def test_causality_future_input_does_not_change_past_output(eng_tc):
+    """The reference's verify_causality (hifigan_causal.py:550-599) restated on the whole path:
+    perturbing source frames >= t must not change wav samples < t*hop."""
+    ref = synth.synth_mel(40, 1)[None]
+    src = synth.synth_mel(24, 2)[None]
+    src2 = src.clone()
+    src2[:, 14:] += 1.0                          # frame 14 is first seen (as look-ahead) by the chunk that starts at frame 12
+    a, _, _ = _run_e2e(eng_tc, ref, src, [0])
+    b, _, _ = _run_e2e(eng_tc, ref, src2, [1])
+    assert torch.equal(a[:, :12 * 320], b[:, :12 * 320])
+    assert not torch.equal(a[:, 12 * 320:], b[:, 12 * 320:])
