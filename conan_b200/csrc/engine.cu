@@ -83,6 +83,10 @@ struct conan_engine {
         *qXE = nullptr, *qZC = nullptr, *qPE = nullptr, *qKVs = nullptr, *qMGB = nullptr;
   int* qVQ = nullptr;
   int* qSlots = nullptr;
+  // ---- optional per-launch event timing of the conv engines (bench.py's roofline leg)
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t a, b; int cat; double flops; };
+  mutable std::vector<ProfRec> prof;
   // ---- host-call staging
   int* hIds = nullptr; float* hChunk = nullptr; float* hWav = nullptr; float* hMel = nullptr; int* hTok = nullptr; int* hIdsSmall = nullptr;
 
@@ -247,8 +251,17 @@ void out2_ctx(conan_conv_params_t& p, const Ctx& c, int act2, float slope2) {
 void res_rows(conan_conv_params_t& p, const float* r, int L, int C) { p.res = r; p.res_slot_stride = (long long)L * C; p.res_row_stride = C; }
 
 int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t st, bool allow_tc = false) {
-  if (allow_tc && e->cfg.voc_use_tensor_cores && conv_gemm_tc_eligible(p)) return launch_conv_gemm_tc(p, st);
-  return launch_conv_gemm_ffma(p, st);
+  const bool tc = allow_tc && e->cfg.voc_use_tensor_cores && conv_gemm_tc_eligible(p);
+  if (!e->profiling) return tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
+  conan_engine::ProfRec r;
+  r.cat = tc ? 1 : 0;
+  r.flops = 2.0 * (double)p.n_streams * p.L * p.cout * p.k * p.cin;
+  CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
+  CONAN_CUDA_OK(cudaEventRecord(r.a, st));
+  int rc = tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
+  CONAN_CUDA_OK(cudaEventRecord(r.b, st));
+  e->prof.push_back(r);
+  return rc;
 }
 
 int ln_rows(const float* in, int in_rows, int in_row0, RowView out, const float* g, const float* b, int C, int L, int n,
@@ -815,6 +828,30 @@ int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, cons
   if (mel_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out_host, e->hMel, (size_t)n * c.segment * c.n_mels * 4, cudaMemcpyDeviceToHost, st));
   if (tokens_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(tokens_out_host, e->hTok, (size_t)n * c.segment * 4, cudaMemcpyDeviceToHost, st));
   CONAN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int conan_engine_set_profiling(conan_engine_t* e, int enabled) {
+  if (!e) { set_error("null engine"); return 1; }
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof.clear();
+  e->profiling = enabled != 0;
+  return 0;
+}
+
+int conan_engine_profile_read(conan_engine_t* e, int category, double* ms, uint64_t* launches, double* flops) {
+  if (!e) { set_error("null engine"); return 1; }
+  CONAN_CUDA_OK(cudaDeviceSynchronize());
+  double t = 0, f = 0; uint64_t n = 0;
+  for (auto& r : e->prof) {
+    if (r.cat != category) continue;
+    float dt = 0.f;
+    CONAN_CUDA_OK(cudaEventElapsedTime(&dt, r.a, r.b));
+    t += dt; f += r.flops; ++n;
+  }
+  if (ms) *ms = t;
+  if (launches) *launches = n;
+  if (flops) *flops = f;
   return 0;
 }
 

@@ -190,6 +190,16 @@ class Engine:
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         _lib.check(self.lib.conan_step_host(self.h, n, vp(slots), vp(chunk), vp(wav_out), vp(mel_out), vp(tokens_out), self._stream()), "step_host")
 
+    # ------------------------------------------------------------------ measurement
+    def set_profiling(self, enabled: bool):
+        _lib.check(self.lib.conan_engine_set_profiling(self.h, int(enabled)), "set_profiling")
+
+    def profile_read(self, category: int):
+        """category 0 = FFMA conv engine, 1 = tcgen05 conv engine -> (ms, launches, algorithmic flops)."""
+        ms, n, fl = C.c_double(), C.c_uint64(), C.c_double()
+        _lib.check(self.lib.conan_engine_profile_read(self.h, category, C.byref(ms), C.byref(n), C.byref(fl)), "profile_read")
+        return ms.value, n.value, fl.value
+
     # ------------------------------------------------------------------ debug
     def debug_read(self, name: str, slot: int) -> torch.Tensor:
         numel = C.c_size_t()

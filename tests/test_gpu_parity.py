@@ -419,7 +419,9 @@ def test_causality_future_input_does_not_change_past_output(eng_tc):
     ref = synth.synth_mel(40, 1)[None]
     src = synth.synth_mel(24, 2)[None]
     src2 = src.clone()
-    src2[:, 14:] += 1.0                          # frame 14 is first seen (as look-ahead) by the chunk that starts at frame 12
+    # frame 14 is first seen (as look-ahead) by the chunk that starts at frame 12.  (A uniform offset would be
+    # invisible: the Emformer's LayerNorms remove it, so replace the tail with different content.)
+    src2[:, 14:] = synth.synth_mel(24, 99)[None][:, 14:]
     a, _, _ = _run_e2e(eng_tc, ref, src, [0])
     b, _, _ = _run_e2e(eng_tc, ref, src2, [1])
     assert torch.equal(a[:, :12 * 320], b[:, :12 * 320])
