@@ -149,7 +149,40 @@ conv_gemm_ffma_kernel(const T* __restrict__ X, long long x_slot_stride, int x_ro
     __syncthreads();
   }
 
-  // ---- fused epilogue
+  // ---- fused epilogue.  The activation is applied tile-wide first (one switch per thread, not per
+  // element), then the residual / mask / output chain.
+  switch (e.act) {
+    case ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int n = n0 + tx * 4 + j; float b = (e.bias && n < cout) ? e.bias[n] : 0.f; acc[i][j] = fmaxf((acc[i][j] + b) * e.scale, 0.f); }
+      break;
+    case ACT_LRELU:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int n = n0 + tx * 4 + j; float b = (e.bias && n < cout) ? e.bias[n] : 0.f; float v = (acc[i][j] + b) * e.scale; acc[i][j] = v > 0.f ? v : v * e.slope; }
+      break;
+    case ACT_GELU:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int n = n0 + tx * 4 + j; float b = (e.bias && n < cout) ? e.bias[n] : 0.f; float v = (acc[i][j] + b) * e.scale; acc[i][j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+      break;
+    case ACT_TANH:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int n = n0 + tx * 4 + j; float b = (e.bias && n < cout) ? e.bias[n] : 0.f; acc[i][j] = tanhf((acc[i][j] + b) * e.scale); }
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int n = n0 + tx * 4 + j; float b = (e.bias && n < cout) ? e.bias[n] : 0.f; acc[i][j] = (acc[i][j] + b) * e.scale; }
+  }
+  const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);   // second output: none / relu / leaky
   const int nb = n0 + tx * 4;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -158,24 +191,21 @@ conv_gemm_ffma_kernel(const T* __restrict__ X, long long x_slot_stride, int x_ro
     int si = m / L, t = m - si * L;
     int slot = slot_ids ? slot_ids[si] : si;
     float rm = e.rowmask ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
+    const float fsc = rm * e.out_scale;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = nb + j;
       if (n >= cout) continue;
       float v = acc[i][j];
-      if (e.bias) v += e.bias[n];
-      v *= e.scale;
-      v = apply_act(v, e.act, e.slope);
       if (e.res) v += e.res[(long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + n];
-      v *= rm;
-      v *= e.out_scale;
+      v *= fsc;
       if (e.y) {
         float* yp = e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + n;
         if (e.accumulate) v += *yp;
         *yp = v;
       }
       if (e.y2) {
-        float v2 = apply_act(v, e.act2, e.slope2);
+        float v2 = v > 0.f ? v : v * s2;
         long long o = (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + n;
         if (e.y2_is_half) reinterpret_cast<__half*>(e.y2)[o] = __float2half_rn(v2);
         else reinterpret_cast<float*>(e.y2)[o] = v2;
@@ -189,6 +219,7 @@ conv_gemm_ffma_kernel(const T* __restrict__ X, long long x_slot_stride, int x_ro
 int launch_conv_gemm_ffma(const conan_conv_params_t& p, cudaStream_t st) {
   if (p.cin % BK != 0) { set_error("conv_gemm_ffma: cin must be a multiple of 16"); return 1; }
   if (p.x_row_stride % 8 != 0 || p.x_slot_stride % 8 != 0) { set_error("conv_gemm_ffma: x strides must be multiples of 8 elements"); return 1; }
+  if (p.act2 > ACT_LRELU) { set_error("conv_gemm: act2 must be none, relu or leaky"); return 1; }
   if (p.n_streams <= 0) return 0;
   EpiArgs e{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask,
             p.mask_slot_stride, p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate,

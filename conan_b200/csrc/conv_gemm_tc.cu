@@ -107,6 +107,16 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[3
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4, [16,30) LBO >> 4 (= 1 for swizzled K-major), [32,46) SBO >> 4
 //   (8 rows * swizzle span), [46,48) version = 1, [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
@@ -132,7 +142,7 @@ struct SmemLayout {
 };
 
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, 5)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
   using SL = SmemLayout<BN, BK, STAGES>;
   constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
@@ -217,63 +227,74 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;       // tile row == TMEM lane
     const int q = r / a.TT, tt = r - q * a.TT;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const bool valid = s_valid[q] != 0;
     const int slot = s_slot[q];
     const int t = s_t0[q] + tt;
     const TcEpi& e = a.e;
     const float rm = (e.rowmask && valid) ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
     const int nbase = nt * BN;
-    const float* resp = e.res ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
-    float* yp = e.y ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
-    __half* y2p = e.y2 ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t acc[32];
-      tc_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
-      if (valid) {
-        float v[32];
+    const float* resp = (e.res && valid) ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
+    float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
+    __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
+    const bool acc_old = e.accumulate && yp;
+    // activations on this engine are none / relu / leaky only, expressed branch-free as
+    // v > 0 ? v : v * slope with slope 1 (none), 0 (relu) or the leaky slope
+    const float s1 = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.slope);
+    const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);
+    const float f = rm * e.out_scale;
+    // The residual (fp32 stream) does not depend on the accumulator: its first 16-column chunk is
+    // fetched BEFORE waiting for the MMAs and chunk c+1 is fetched while chunk c is finished, so the
+    // HBM latency of the stream overlaps the tensor work.  16 columns per step keeps the epilogue
+    // under 64 registers (5 CTAs per SM).
+    float4 rcur[4], rnext[4];
+    auto fetch_res = [&](float4 (&dst)[4], int c0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-        if (e.bias) {
+      for (int i = 0; i < 4; ++i)
+        dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch_res(rcur, 0);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + nbase + c0 + i));
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-          }
-        }
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (c0 + 16 < BN) fetch_res(rnext, c0 + 16);
+      uint32_t acc[16];
+      tc_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+      float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i] * e.scale, e.act, e.slope);
-        if (resp) {
+      for (int i = 0; i < 4; ++i) {
+        const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + nbase + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 rr = *reinterpret_cast<const float4*>(resp + c0 + i);
-            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-          }
-        }
-        const float f = rm * e.out_scale;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= f;
-        if (yp) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4* dst = reinterpret_cast<float4*>(yp + c0 + i);
-            if (e.accumulate) { float4 o = *dst; v[i] += o.x; v[i + 1] += o.y; v[i + 2] += o.z; v[i + 3] += o.w; }
-            *dst = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-        }
-        if (y2p) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            __half2 h[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              h[u] = __floats2half2_rn(apply_act(v[i + 2 * u], e.act2, e.slope2), apply_act(v[i + 2 * u + 1], e.act2, e.slope2));
-            *reinterpret_cast<uint4*>(y2p + c0 + i) = *reinterpret_cast<uint4*>(h);
-          }
+        for (int u = 0; u < 4; ++u) {
+          float x = (__uint_as_float(acc[4 * i + u]) + bb[u]) * e.scale;
+          x = x > 0.f ? x : x * s1;
+          v[4 * i + u] = (x + rr[u]) * f;
         }
       }
+      if (yp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4* dst = reinterpret_cast<float4*>(yp + c0) + i;
+          if (acc_old) { const float4 o = *dst; v[4 * i] += o.x; v[4 * i + 1] += o.y; v[4 * i + 2] += o.z; v[4 * i + 3] += o.w; }
+          *dst = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      if (y2p) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          __half2 h[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float x0 = v[8 * i + 2 * u], x1 = v[8 * i + 2 * u + 1];
+            h[u] = __floats2half2_rn(x0 > 0.f ? x0 : x0 * s2, x1 > 0.f ? x1 : x1 * s2);
+          }
+          *(reinterpret_cast<uint4*>(y2p + c0) + i) = *reinterpret_cast<uint4*>(h);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
     }
     tc_fence_before();
   }
@@ -377,6 +398,7 @@ bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
   if (p.cin % 32 != 0 || p.x_row_stride != p.cin) return false;
   if (pick_bn(p.cout) == 0 || pick_tt(p.L) == 0) return false;
   if (p.row0 < 0) return false;
+  if (p.act > ACT_LRELU || p.act2 > ACT_LRELU) return false;          // none / relu / leaky only on this engine
   if (p.y && (p.y_slot_stride % 4 || p.y_row_stride % 4)) return false;
   if (p.res && (p.res_slot_stride % 4 || p.res_row_stride % 4)) return false;
   if (p.y2 && (p.y2_slot_stride % 8 || p.y2_row_stride % 8)) return false;
@@ -408,12 +430,12 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   const long long m_tiles = (M + TILE_M - 1) / TILE_M;
   if (BK == 64) {
     if (BN == 128) return launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
-    if (BN == 64) return launch_variant<64, 64, 4>(tmA, tmW, a, m_tiles, st);
-    return launch_variant<32, 64, 4>(tmA, tmW, a, m_tiles, st);
+    if (BN == 64) return launch_variant<64, 64, 2>(tmA, tmW, a, m_tiles, st);
+    return launch_variant<32, 64, 2>(tmA, tmW, a, m_tiles, st);
   }
-  if (BN == 128) return launch_variant<128, 32, 4>(tmA, tmW, a, m_tiles, st);
-  if (BN == 64) return launch_variant<64, 32, 4>(tmA, tmW, a, m_tiles, st);
-  return launch_variant<32, 32, 4>(tmA, tmW, a, m_tiles, st);
+  if (BN == 128) return launch_variant<128, 32, 3>(tmA, tmW, a, m_tiles, st);
+  if (BN == 64) return launch_variant<64, 32, 3>(tmA, tmW, a, m_tiles, st);
+  return launch_variant<32, 32, 3>(tmA, tmW, a, m_tiles, st);
 }
 
 }  // namespace conan
