@@ -20,6 +20,8 @@
 // the next conv's context buffer (pixel shuffle is folded into the weight row order, so an
 // upsampling conv is just this kernel with a wider output row).
 #include <cuda.h>
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -94,19 +96,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -131,6 +120,76 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 template <int BN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// Fused epilogue of one accumulator row (thread = tile row = TMEM lane): waits for the accumulator,
+// then per 16-column chunk: bias, scale, activation, residual, mask, 1/3-scale (+ old output), fp32
+// store and/or activated fp16 store.  Activations on this engine are none / relu / leaky, expressed
+// branch-free as v > 0 ? v : v * slope with slope 1 (none), 0 (relu) or the leaky slope.  The residual
+// (fp32 stream) does not depend on the accumulator: its first chunk is fetched BEFORE the wait and
+// chunk c+1 while chunk c is finished, so its HBM latency overlaps the tensor work.  16 columns per
+// step keeps the kernel under 64 registers.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane_base, int nbase, bool valid, int slot, int t,
+                                              uint64_t* acc_full_bar, uint32_t parity) {
+  const float rm = (e.rowmask && valid) ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
+  const float* resp = (e.res && valid) ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
+  float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
+  __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
+  const bool acc_old = e.accumulate && yp;
+  const float s1 = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.slope);
+  const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);
+  const float f = rm * e.out_scale;
+  float4 rcur[4], rnext[4];
+  auto fetch_res = [&](float4 (&dst)[4], int c0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  fetch_res(rcur, 0);
+  mbar_wait(acc_full_bar, parity);
+  tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    if (c0 + 16 < BN) fetch_res(rnext, c0 + 16);
+    uint32_t acc[16];
+    tc_ld_32x32b_x16(tmem_lane_base + (uint32_t)c0, acc);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + nbase + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float x = (__uint_as_float(acc[4 * i + u]) + bb[u]) * e.scale;
+        x = x > 0.f ? x : x * s1;
+        v[4 * i + u] = (x + rr[u]) * f;
+      }
+    }
+    if (yp) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4* dst = reinterpret_cast<float4*>(yp + c0) + i;
+        if (acc_old) { const float4 o = *dst; v[4 * i] += o.x; v[4 * i + 1] += o.y; v[4 * i + 2] += o.z; v[4 * i + 3] += o.w; }
+        *dst = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+    if (y2p) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __half2 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float x0 = v[8 * i + 2 * u], x1 = v[8 * i + 2 * u + 1];
+          h[u] = __floats2half2_rn(x0 > 0.f ? x0 : x0 * s2, x1 > 0.f ? x1 : x1 * s2);
+        }
+        *(reinterpret_cast<uint4*>(y2p + c0) + i) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+  }
 }
 
 template <int BN, int BK, int STAGES>
@@ -227,77 +286,144 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;       // tile row == TMEM lane
     const int q = r / a.TT, tt = r - q * a.TT;
-    const bool valid = s_valid[q] != 0;
-    const int slot = s_slot[q];
-    const int t = s_t0[q] + tt;
-    const TcEpi& e = a.e;
-    const float rm = (e.rowmask && valid) ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
-    const int nbase = nt * BN;
-    const float* resp = (e.res && valid) ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
-    float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
-    __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
-    const bool acc_old = e.accumulate && yp;
-    // activations on this engine are none / relu / leaky only, expressed branch-free as
-    // v > 0 ? v : v * slope with slope 1 (none), 0 (relu) or the leaky slope
-    const float s1 = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.slope);
-    const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);
-    const float f = rm * e.out_scale;
-    // The residual (fp32 stream) does not depend on the accumulator: its first 16-column chunk is
-    // fetched BEFORE waiting for the MMAs and chunk c+1 is fetched while chunk c is finished, so the
-    // HBM latency of the stream overlaps the tensor work.  16 columns per step keeps the epilogue
-    // under 64 registers (5 CTAs per SM).
-    float4 rcur[4], rnext[4];
-    auto fetch_res = [&](float4 (&dst)[4], int c0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    fetch_res(rcur, 0);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (c0 + 16 < BN) fetch_res(rnext, c0 + 16);
-      uint32_t acc[16];
-      tc_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + nbase + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-        const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float x = (__uint_as_float(acc[4 * i + u]) + bb[u]) * e.scale;
-          x = x > 0.f ? x : x * s1;
-          v[4 * i + u] = (x + rr[u]) * f;
-        }
-      }
-      if (yp) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4* dst = reinterpret_cast<float4*>(yp + c0) + i;
-          if (acc_old) { const float4 o = *dst; v[4 * i] += o.x; v[4 * i + 1] += o.y; v[4 * i + 2] += o.z; v[4 * i + 3] += o.w; }
-          *dst = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-      }
-      if (y2p) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          __half2 h[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float x0 = v[8 * i + 2 * u], x1 = v[8 * i + 2 * u + 1];
-            h[u] = __floats2half2_rn(x0 > 0.f ? x0 : x0 * s2, x1 > 0.f ? x1 : x1 * s2);
-          }
-          *(reinterpret_cast<uint4*>(y2p + c0) + i) = *reinterpret_cast<uint4*>(h);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
-    }
+    epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16), nt * BN, s_valid[q] != 0, s_slot[q], s_t0[q] + tt,
+                      tmem_full_bar, 0);
     tc_fence_before();
   }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ==============================================================================================
+// "Window" variant for the long narrow layers (L % 128 == 0, cout = BN in {32, 64}: vocoder scales
+// 2 and 3 and the last upsampling conv), which are HBM-bound, not tensor-bound:
+//   * persistent CTAs, static round-robin over the 128-row tiles of (stream, time);
+//   * the whole packed weight matrix (k taps x [BN, C]) is loaded into shared memory ONCE per CTA;
+//   * per tile ONE TMA box brings the input window of 128 + (k-1)*dil rows; every tap's A operand is
+//     the same window at a row offset (the UMMA descriptor start address moves by j*dil rows), so the
+//     input is read from L2/HBM once instead of k times;
+//   * two TMEM accumulators: the MMAs of tile i+1 run while the epilogue warps drain tile i; with one
+//     CTA per SM two epilogue warpgroups alternate tiles so enough loads/stores are in flight.
+// ==============================================================================================
+struct WinArgs {
+  int L, k, dil, row0, win_rows, num_tiles, tiles_per_stream;
+  const int* slot_ids;
+  TcEpi e;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// A descriptor whose start address is offset by whole rows inside a swizzle atom (tap j starts
+// j*dil rows into the window).  Measured on B200: the swizzle XOR is applied on absolute shared-memory
+// address bits, so the descriptor's base_offset field must stay 0 for such starts (setting it to
+// (start >> 7) & 7 produces wrong operands) -- tests/test_gpu_parity.py covers odd offsets in both
+// the 128-byte and the 64-byte swizzle.
+
+template <int C, int BN, int NBUF, int NEPI>
+__global__ void __launch_bounds__(64 + 128 * NEPI)
+conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, WinArgs a) {
+  constexpr int ROWB = C * 2;                       // bytes per row = swizzle span (64 or 128)
+  constexpr int TAPB = BN * ROWB;                   // one tap of the weight matrix
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int winb = (a.win_rows * ROWB + 1023) & ~1023;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + ((a.k * TAPB + 1023) & ~1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NBUF * winb);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = a_full + NBUF;
+  uint64_t* acc_full = a_empty + NBUF;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    mbar_init(w_full, 1);
+    for (int s = 0; s < NBUF; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(a.k * TAPB));
+      for (int j = 0; j < a.k; ++j) tma_load_2d(sW + j * TAPB, &tmW, w_full, j * C, 0);
+      int it = 0;
+      for (int g = blockIdx.x; g < a.num_tiles; g += gridDim.x, ++it) {
+        const int buf = it % NBUF;
+        const uint32_t ph = (it / NBUF) & 1;
+        mbar_wait(&a_empty[buf], ph ^ 1);
+        const int si = g / a.tiles_per_stream, t0 = (g - si * a.tiles_per_stream) * TILE_M;
+        const int slot = a.slot_ids ? a.slot_ids[si] : si;
+        mbar_expect_tx(&a_full[buf], (uint32_t)(a.win_rows * ROWB));
+        tma_load_3d(sA + buf * winb, &tmA, &a_full[buf], 0, a.row0 + t0, slot);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t sW32 = smem_u32(sW), sA32 = smem_u32(sA);
+      int it = 0;
+      for (int g = blockIdx.x; g < a.num_tiles; g += gridDim.x, ++it) {
+        const int buf = it % NBUF, ab = it & 1;
+        const uint32_t ph = (it / NBUF) & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[ab], aph ^ 1);
+        mbar_wait(&a_full[buf], ph);
+        tc_fence_after();
+        const uint32_t win = sA32 + buf * winb;
+        for (int j = 0; j < a.k; ++j) {
+          const uint32_t arow = win + (uint32_t)(j * a.dil * ROWB);
+          const uint32_t brow = sW32 + (uint32_t)(j * TAPB);
+#pragma unroll
+          for (int kk = 0; kk < C / 16; ++kk)
+            tc_mma_f16(tmem_base + (uint32_t)(ab * BN), make_smem_desc<ROWB>(arow + kk * 32),
+                       make_smem_desc<ROWB>(brow + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
+        }
+        tc_commit(&a_empty[buf]);
+        tc_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warpgroups
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    int it = 0;
+    for (int g = blockIdx.x; g < a.num_tiles; g += gridDim.x, ++it) {
+      if (NEPI == 2 && (it & 1) != wg) continue;
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int si = g / a.tiles_per_stream, t0 = (g - si * a.tiles_per_stream) * TILE_M;
+      const int slot = a.slot_ids ? a.slot_ids[si] : si;
+      epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), 0, true, slot, t0 + r,
+                        &acc_full[ab], aph);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -390,6 +516,75 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcArgs&
   return 0;
 }
 
+int window_mode() {
+  // CONAN_TC_WINDOW=0 routes every layer through the ring kernel (A/B comparisons, debugging)
+  static int mode = [] { const char* v = getenv("CONAN_TC_WINDOW"); return v ? atoi(v) : 1; }();
+  return mode;
+}
+
+int num_sms() {
+  static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+  return n;
+}
+
+constexpr int WIN_NBUF = 3;
+size_t window_smem_bytes(const conan_conv_params_t& p) {
+  const int rowb = p.cin * 2, tapb = p.cout * rowb;
+  const int win_rows = TILE_M + (p.k - 1) * p.dil;
+  const size_t winb = ((size_t)win_rows * rowb + 1023) & ~(size_t)1023;
+  return (((size_t)p.k * tapb + 1023) & ~(size_t)1023) + WIN_NBUF * winb + 1024 + 256;
+}
+
+bool window_eligible(const conan_conv_params_t& p) {
+  if (window_mode() == 0) return false;
+  if (p.L % TILE_M != 0) return false;
+  if (!((p.cin == 32 && p.cout == 32) || (p.cin == 64 && p.cout == 64))) return false;
+  if (TILE_M + (p.k - 1) * p.dil > 256) return false;
+  return window_smem_bytes(p) <= 200 * 1024;
+}
+
+template <int C, int BN, int NEPI>
+int launch_window_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const WinArgs& a, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_window_tc_kernel<C, BN, WIN_NBUF, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  conv_window_tc_kernel<C, BN, WIN_NBUF, NEPI><<<grid, 64 + 128 * NEPI, smem, st>>>(tmA, tmW, a);
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
+  const int C = p.cin, Ktot = p.k * p.cin;
+  const int win_rows = TILE_M + (p.k - 1) * p.dil;
+  CUtensorMap tmA, tmW;
+  if (get_tensor_map(&tmA, p.x, 3, (unsigned long long)p.cin, (unsigned long long)p.x_rows, (unsigned long long)p.n_slots,
+                     (unsigned long long)p.x_row_stride * 2, (unsigned long long)p.x_slot_stride * 2, C, win_rows, 1, C * 2))
+    return 1;
+  if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, C, p.cout, 1, C * 2))
+    return 1;
+  WinArgs a;
+  a.L = p.L; a.k = p.k; a.dil = p.dil; a.row0 = p.row0; a.win_rows = win_rows;
+  a.tiles_per_stream = p.L / TILE_M; a.num_tiles = p.n_streams * a.tiles_per_stream;
+  a.slot_ids = p.slot_ids;
+  a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
+              p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
+              p.y2_row_stride, p.y2_row0, p.act2, p.slope2};
+  const size_t smem = window_smem_bytes(p);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = std::min(a.num_tiles, num_sms() * per_sm);
+  if (per_sm >= 2) {
+    if (C == 32) return launch_window_variant<32, 32, 1>(tmA, tmW, a, grid, smem, st);
+    return launch_window_variant<64, 64, 1>(tmA, tmW, a, grid, smem, st);
+  }
+  if (C == 32) return launch_window_variant<32, 32, 2>(tmA, tmW, a, grid, smem, st);
+  return launch_window_variant<64, 64, 2>(tmA, tmW, a, grid, smem, st);
+}
+
 }  // namespace
 
 bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
@@ -409,6 +604,7 @@ bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
 int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   if (!conv_gemm_tc_eligible(p)) { set_error("conv_gemm_tc: not eligible"); return 1; }
   if (p.n_streams <= 0) return 0;
+  if (window_eligible(p)) return launch_conv_window_tc(p, st);
   const int BK = (p.cin % 64 == 0) ? 64 : 32;
   const int BN = pick_bn(p.cout);
   const int TT = pick_tt(p.L);
