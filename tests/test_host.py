@@ -1,0 +1,220 @@
+"""CPU: host-side logic -- config loader, checkpoint layout, weight packing, mel front-end,
+chunk scheduler (with a recording fake engine) and the multi-rank stream partition (gloo, world 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conan_b200 import audio, ckpt, hparams as hp_mod, synth
+from conan_b200.scheduler import ChunkScheduler, shard_streams
+from conan_b200.weights import pack_conv, sinusoid_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ hparams
+def test_set_hparams_inheritance_and_overrides(tmp_path, monkeypatch):
+    (tmp_path / "base.yaml").write_text("a: 1\nb: {c: 2, d: 3}\nlst: [1, 2]\nflag: false\n")
+    (tmp_path / "sub").mkdir()
+    (tmp_path / "sub" / "mid.yaml").write_text("base_config: ../base.yaml\na: 5\nname: x\n")
+    (tmp_path / "top.yaml").write_text("base_config:\n  - ./sub/mid.yaml\nb: {c: 9}\n")
+    monkeypatch.chdir(tmp_path)
+    cfg = hp_mod.set_hparams(config="top.yaml", hparams_str="a=7,b.d=4,lst=[3 4 5],flag=True,name=y", print_hparams=False)
+    assert cfg["a"] == 7 and cfg["b"] == {"c": 9, "d": 4} and cfg["lst"] == [3, 4, 5] and cfg["flag"] is True and cfg["name"] == "y"
+    assert cfg["work_dir"] == "" and hp_mod.hparams["a"] == 7          # global dict is populated
+    local = hp_mod.set_hparams(config="base.yaml", global_hparams=False, print_hparams=False)
+    assert local["a"] == 1 and hp_mod.hparams["a"] == 7                # global untouched
+
+
+def test_shipped_configs_carry_the_hot_path_keys(monkeypatch):
+    monkeypatch.chdir(ROOT)
+    cfg = hp_mod.set_hparams(config="egs/conan_emformer.yaml", print_hparams=False, global_hparams=False)
+    for k, v in synth.DEFAULT_HP.items():
+        assert cfg[k] == v, k
+    voc = hp_mod.set_hparams(config="egs/hifi_16k320_shuffle.yaml", print_hparams=False, global_hparams=False)
+    for k in ("upsample_rates", "upsample_kernel_sizes", "upsample_initial_channel", "resblock_kernel_sizes", "resblock_dilation_sizes"):
+        assert voc[k] == synth.DEFAULT_VOC_HP[k], k
+    from conan_b200.engine import make_config
+    c = make_config(cfg, voc, max_slots=4, max_ref_frames=100)
+    assert (c.segment, c.right_context, c.hidden_size, c.voc_n_ups, list(c.voc_rates)[:4]) == (4, 2, 256, 4, [8, 5, 4, 2])
+    with pytest.raises(ValueError):
+        make_config({**cfg, "f0_gen": "flow"}, voc)
+
+
+# ------------------------------------------------------------------ checkpoints
+def test_checkpoint_layout_roundtrip_and_selection(tmp_path):
+    sd = {"a.weight": torch.randn(3, 2), "b": torch.randn(4)}
+    ckpt.save_checkpoint(sd, str(tmp_path / "m"), "model", steps=10)
+    ckpt.save_checkpoint({k: v + 1 for k, v in sd.items()}, str(tmp_path / "m"), "model", steps=200)
+    got = ckpt.load_state_dict(str(tmp_path / "m"), "model")
+    assert torch.equal(got["b"], sd["b"] + 1)                          # newest step wins
+    got = ckpt.load_state_dict(str(tmp_path / "m" / "model_ckpt_steps_10.ckpt"), "model")
+    assert torch.equal(got["b"], sd["b"])
+    flat = {"state_dict": {"model_gen.a.weight": sd["a.weight"], "model_disc.x": torch.zeros(1)}}
+    os.makedirs(tmp_path / "f")
+    torch.save(flat, tmp_path / "f" / "model_ckpt_steps_1.ckpt")
+    got = ckpt.load_state_dict(str(tmp_path / "f"), "model_gen")
+    assert list(got) == ["a.weight"]
+    os.makedirs(tmp_path / "empty")
+    with pytest.raises(AssertionError):
+        ckpt.load_state_dict(str(tmp_path / "empty"), "model")
+    assert ckpt.load_state_dict(str(tmp_path / "empty"), "model", force=False) is None
+    with pytest.raises(ValueError):
+        ckpt.filter_to_spec({"a.weight": torch.zeros(2, 2)}, [("a.weight", (3, 2), "x")], strict=False)
+
+
+def test_weight_norm_folding_matches_torch():
+    conv = torch.nn.utils.weight_norm(torch.nn.Conv1d(6, 5, 3))
+    with torch.no_grad():
+        conv.weight_g.mul_(1.7)
+    sd = {"c." + k: v for k, v in conv.state_dict().items()}
+    x = torch.randn(2, 6, 9)
+    w = ckpt.fold_weight_norm(sd, "c")
+    assert torch.allclose(F.conv1d(x, w, sd["c.bias"]), conv(x), atol=1e-6)
+
+
+# ------------------------------------------------------------------ weight packing
+def test_pack_conv_is_tap_major():
+    w = torch.randn(5, 4, 3)
+    p = pack_conv(w)
+    assert p.shape == (5, 12) and torch.equal(p[:, 1 * 4 + 2], w[:, 2, 1])
+
+
+def test_pixel_shuffle_folds_into_weight_row_order():
+    """conv with permuted rows, read as [T*r, C], equals CausalPixelShuffle1d(conv) (hifigan_causal.py:186-188)."""
+    C, r, cin, k, T = 6, 4, 8, 3, 5
+    w, b, x = torch.randn(C * r, cin, k), torch.randn(C * r), torch.randn(1, cin, T + k - 1)
+    y = F.conv1d(x, w, b)                                              # [1, C*r, T], channel c*r + j
+    ref = y.view(1, C, r, T).permute(0, 1, 3, 2).reshape(1, C, T * r)  # the reference's shuffle
+    wp = w.view(C, r, cin, k).permute(1, 0, 2, 3).reshape(r * C, cin, k)
+    bp = b.view(C, r).t().reshape(-1)
+    yp = F.conv1d(x, wp, bp).transpose(1, 2).reshape(1, T * r, C)      # channels-last rows [t, r*C] -> [t*r + j, c]
+    assert torch.allclose(yp.transpose(1, 2), ref, atol=1e-6)
+
+
+def test_sinusoid_table_layout():
+    t = sinusoid_table(20, 256)
+    assert (t[0] == 0).all() and abs(float(t[3, 0]) - np.sin(3.0)) < 1e-6 and abs(float(t[3, 128]) - np.cos(3.0)) < 1e-6
+
+
+# ------------------------------------------------------------------ mel front-end
+def test_slaney_mel_basis_matches_torchaudio():
+    import torchaudio
+    mine = audio.slaney_mel_basis(16000, 1024, 80, 80, 7600)
+    ta = torchaudio.functional.melscale_fbanks(513, 80.0, 7600.0, 80, 16000, norm="slaney", mel_scale="slaney").t().numpy()
+    assert np.abs(mine - ta).max() < 1e-6
+    wav = np.sin(2 * np.pi * 440 * np.arange(16000) / 16000).astype(np.float32) * 0.5
+    mel = audio.wav2mel(wav)
+    assert mel.shape == (16000 // 320 + 1, 80) and np.isfinite(mel).all()
+    assert 8 <= int(mel[10].argmax()) <= 16                         # 440 Hz lands in the low mel bins
+
+
+# ------------------------------------------------------------------ scheduler (fake engine)
+class FakeEngine:
+    segment, rows_in, hop_out, n_mels = 4, 6, 1280, 80
+
+    def __init__(self):
+        self.calls, self.opened, self.resets = [], [], []
+
+    def reset_slots(self, slots, parts=7):
+        self.resets.append(list(slots))
+
+    def open_sessions(self, slots, ref):
+        self.opened.append((list(slots), tuple(ref.shape)))
+
+    def step_host(self, slots, chunk, wav, mel, tok):
+        self.calls.append((slots.copy(), chunk.copy()))
+        for i, s in enumerate(slots):
+            wav[i] = chunk[i, :4, 0].repeat(320)          # echo: wav sample block t carries mel[t, 0]
+            mel[i] = chunk[i, :4]
+            tok[i] = s
+
+
+def test_scheduler_chunk_assembly_matches_reference_loop_rule():
+    from oracle.incremental import assemble_chunk
+    eng = FakeEngine()
+    sch = ChunkScheduler(eng, 4)
+    src = synth.synth_mel(23, 1).numpy()                   # 5 full chunks + a 3-frame tail
+    sid = sch.open(np.zeros((30, 80), np.float32))
+    sch.push(sid, src)
+    sch.end(sid)
+    pos, mels = 0, []
+    while not sch.finished(sid):
+        out = sch.step()[sid]
+        chunk_ref, emit = assemble_chunk(torch.from_numpy(src)[None], pos)
+        assert np.array_equal(eng.calls[-1][1][0], chunk_ref[0].numpy())
+        assert out[1].shape[0] == emit and out[0].shape[0] == emit * 320
+        mels.append(out[1])
+        pos += emit
+    assert pos == 23 and np.array_equal(np.concatenate(mels), src)
+
+
+def test_scheduler_packs_only_ready_streams_and_recycles_slots():
+    eng = FakeEngine()
+    sch = ChunkScheduler(eng, 3)
+    a, b, c = sch.open_many([np.zeros((20, 80), np.float32), np.zeros((20, 80), np.float32), np.zeros((8, 80), np.float32)])
+    assert sorted(len(o[0]) for o in eng.opened) == [1, 2]            # equal-length references share one setup call
+    with pytest.raises(RuntimeError):
+        sch.open(np.zeros((8, 80), np.float32))                        # pool exhausted
+    sch.push(a, synth.synth_mel(6, 1).numpy())                         # exactly one chunk + look-ahead
+    sch.push(b, synth.synth_mel(5, 2).numpy())                         # look-ahead not yet complete
+    assert sch.ready() == [a]
+    out = sch.step()
+    assert list(out) == [a] and len(eng.calls[-1][0]) == 1
+    sch.push(b, synth.synth_mel(3, 3).numpy())                         # now 8 frames buffered
+    sch.push(a, synth.synth_mel(2, 4).numpy())                         # a: 8 frames, pos 4 -> needs 10
+    assert sch.ready() == [b]
+    sch.end(a)
+    assert sorted(sch.ready()) == [a, b]
+    out = sch.step()
+    assert out[a][1].shape[0] == 4 and out[b][1].shape[0] == 4 and len(eng.calls[-1][0]) == 2
+    assert sch.finished(a) and not sch.finished(b)
+    slot_a = sch.streams[a].slot
+    sch.close(a)
+    d = sch.open(np.zeros((8, 80), np.float32))
+    assert sch.streams[d].slot == slot_a and eng.resets[-1] == [slot_a]
+    sch.end(c)
+    assert c not in sch.ready()                                        # ended with nothing buffered
+
+
+# ------------------------------------------------------------------ multi-rank partition (gloo)
+def _rank_main(rank, world, port, n_streams, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard_streams(n_streams, world, rank)
+    # no data-path collective: the only exchange is bench-style metadata (units per rank, max time)
+    counts = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([mine.start, mine.stop], dtype=torch.int64))
+    t = torch.tensor([1.0 + rank])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, [c.tolist() for c in counts], float(t)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_streams", [8192, 1001])
+def test_stream_sharding_world2_gloo(n_streams):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (n_streams % 7)
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, n_streams, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    for rank, counts, tmax in res:
+        assert tmax == 2.0
+        spans = sorted(counts)
+        assert spans[0][0] == 0 and spans[-1][1] == n_streams and spans[0][1] == spans[1][0]   # disjoint, contiguous, complete
+        assert abs((spans[0][1] - spans[0][0]) - (spans[1][1] - spans[1][0])) <= 1
+
+
+def test_reference_arm_is_rank0_only(monkeypatch, capsys):
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference(type("A", (), {"steps": 1, "warmup": 1, "gpus": 2})())
+    assert capsys.readouterr().out == ""
