@@ -192,14 +192,31 @@ __global__ void conv_post_tanh_kernel(const T* __restrict__ x, long long slot_st
   extern __shared__ float ws[];                // [k*C]
   for (int q = threadIdx.x; q < k * C; q += blockDim.x) ws[q] = w[q];
   __syncthreads();
+  constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte load (C % VEC == 0, rows 16-byte aligned)
   long long total = (long long)n * L;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     int t = idx % L; int i = idx / L;
     const T* xp = x + (long long)slot_of(slot_ids, i) * slot_stride + (long long)(row0 + t) * row_stride;
     float acc = bias[0];
     for (int j = 0; j < k; ++j) {
-      const T* r = xp + (long long)j * row_stride;
-      for (int c = 0; c < C; ++c) acc = fmaf((float)r[c], ws[j * C + c], acc);
+      const uint4* r = reinterpret_cast<const uint4*>(xp + (long long)j * row_stride);
+      const float* wj = ws + j * C;
+      for (int v = 0; v < C / VEC; ++v) {
+        uint4 u = r[v];
+        if (sizeof(T) == 2) {
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 f = __half22float2(h[q]);
+            acc = fmaf(f.x, wj[v * 8 + 2 * q], acc);
+            acc = fmaf(f.y, wj[v * 8 + 2 * q + 1], acc);
+          }
+        } else {
+          const float* f = reinterpret_cast<const float*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc = fmaf(f[q], wj[v * 4 + q], acc);
+        }
+      }
     }
     wav[idx] = tanhf(acc);
   }

@@ -15,9 +15,9 @@ def test_hparams_loader_agrees_with_reference_on_reference_yamls(monkeypatch):
     monkeypatch.chdir(ref_import.REF_ROOT)
     from utils.commons.hparams import set_hparams as ref_set
     from conan_b200.hparams import set_hparams as my_set
-    for cfgfile in ("egs/conan_emformer.yaml", "egs/hifi_16k320_shuffle.yaml"):
-        a = ref_set(config=cfgfile, print_hparams=False, global_hparams=False, hparams_str="hidden_size=256")
-        b = my_set(config=cfgfile, print_hparams=False, global_hparams=False, hparams_str="hidden_size=256")
+    for cfgfile, ov in (("egs/conan_emformer.yaml", "hidden_size=256,dec_dilations=[1 1 1 1]"), ("egs/hifi_16k320_shuffle.yaml", "max_updates=7")):
+        a = ref_set(config=cfgfile, print_hparams=False, global_hparams=False, hparams_str=ov)
+        b = my_set(config=cfgfile, print_hparams=False, global_hparams=False, hparams_str=ov)
         for k in a:
             if k in ("infer", "debug", "validate"):
                 continue
