@@ -277,9 +277,9 @@ def run_b200(args):
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cv, cdt, cthreads = cpu_oracle_throughput(8, 3)
+            cv, cdt, cthreads = cpu_oracle_throughput(16, 120)
             line["cpu_baseline"] = {"value": cv, "unit": "streams", "cores": cthreads, "kind": "port",
-                                    "sample": f"8 lock-step streams x 3 chunks of the same workload in {cdt:.1f} s "
+                                    "sample": f"16 lock-step streams x 120 chunks of the same workload in {cdt:.1f} s "
                                               "(oracle/incremental.py on all host cores)"}
         print(json.dumps(line), flush=True)
     eng.close()

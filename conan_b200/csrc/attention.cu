@@ -26,7 +26,7 @@ constexpr int EMF_MAX_HD = 16;
 __global__ void __launch_bounds__(256)
 emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ ring, const int* __restrict__ past_len,
                           float* __restrict__ att, const int* __restrict__ slot_ids, int seg, int rc, int lc,
-                          int ring_rows, int D, int heads) {
+                          int ring_rows, int D, int heads, int ldq, int lda) {
   extern __shared__ float sm[];
   const int rows = seg + rc;
   const int slot = slot_of(slot_ids, blockIdx.x);
@@ -36,27 +36,27 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
   float* sK = sm;                         // [nkeys][D]
   float* sV = sK + (size_t)(rc + lc + seg) * D;
   float* sQ = sV + (size_t)(rc + lc + seg) * D;   // [rows][D]
-  const float* q_in = qkv + (long long)slot * rows * 3 * D;
+  const float* q_in = qkv + (long long)blockIdx.x * rows * ldq;      // compact scratch: index i, row stride ldq
   float* rg = ring + (long long)slot * ring_rows * 2 * D;
   const int tid = threadIdx.x;
 
   // stage Q, and K/V in key order
   for (int idx = tid; idx < rows * D; idx += blockDim.x) {
     int r = idx / D, c = idx % D;
-    sQ[idx] = q_in[(long long)r * 3 * D + c];
+    sQ[idx] = q_in[(long long)r * ldq + c];
   }
   for (int idx = tid; idx < nkeys * D; idx += blockDim.x) {
     int key = idx / D, c = idx % D;
     float kval, vval;
     if (key < rc) {                                   // look-ahead rows
-      kval = q_in[(long long)key * 3 * D + D + c]; vval = q_in[(long long)key * 3 * D + 2 * D + c];
+      kval = q_in[(long long)key * ldq + D + c]; vval = q_in[(long long)key * ldq + 2 * D + c];
     } else if (key < rc + lc_len) {                   // cached left context, oldest first
       int logical = past - lc_len + (key - rc);
       int rr = logical % ring_rows;
       kval = rg[(long long)rr * 2 * D + c]; vval = rg[(long long)rr * 2 * D + D + c];
     } else {                                          // this chunk's utterance rows
       int r = rc + (key - rc - lc_len);
-      kval = q_in[(long long)r * 3 * D + D + c]; vval = q_in[(long long)r * 3 * D + 2 * D + c];
+      kval = q_in[(long long)r * ldq + D + c]; vval = q_in[(long long)r * ldq + 2 * D + c];
     }
     sK[idx] = kval; sV[idx] = vval;
   }
@@ -66,7 +66,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
   for (int idx = tid; idx < seg * 2 * D; idx += blockDim.x) {
     int t = idx / (2 * D), c = idx % (2 * D);
     int rr = (past + t) % ring_rows;
-    rg[(long long)rr * 2 * D + c] = q_in[(long long)(rc + t) * 3 * D + D + c];
+    rg[(long long)rr * 2 * D + c] = q_in[(long long)(rc + t) * ldq + D + c];
   }
 
   const int hd = D / heads;
@@ -116,7 +116,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
       for (int d = 0; d < EMF_MAX_HD; ++d) {
         if (d < hd) {
           float v = warp_sum(o[d]);
-          if (lane == 0) att[((long long)slot * rows + qr) * D + h * hd + d] = v;
+          if (lane == 0) att[((long long)blockIdx.x * rows + qr) * lda + h * hd + d] = v;
         }
       }
     }
@@ -143,7 +143,7 @@ cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ ca
   const float scaling = sqrtf(1.0f / (float)hd);     // q * math.sqrt(1.0 / head_dim)
   for (int r = warp; r < rows; r += (blockDim.x >> 5)) {
     float* s = sc + (size_t)r * tp_max;
-    const float* qr = q + ((long long)slot * rows + r) * H + h * hd;
+    const float* qr = q + ((long long)blockIdx.x * rows + r) * H + h * hd;
     float qv[4];                                      // hd = 128 -> 4 per lane
     for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; qv[j] = d < hd ? qr[d] * scaling : 0.f; }
     float mx = -INFINITY;
@@ -168,7 +168,7 @@ cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ ca
       const float* vr = kv + (long long)key * 2 * H + H + h * hd;
       for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) o[j] = fmaf(p, vr[d], o[j]); }
     }
-    float* orow = out + ((long long)slot * rows + r) * H + h * hd;
+    float* orow = out + ((long long)blockIdx.x * rows + r) * H + h * hd;
     for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) orow[d] = o[j]; }
   }
 }
@@ -176,7 +176,8 @@ cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ ca
 }  // namespace
 
 int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, float* att, int n,
-                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, cudaStream_t st) {
+                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv, int ld_att,
+                              cudaStream_t st) {
   if (n <= 0) return 0;
   if (rc + lc + seg > EMF_MAX_KEYS || D / heads > EMF_MAX_HD) { set_error("emformer_attention: key count or head_dim above compiled limits"); return 1; }
   if (ring_rows < lc + seg) { set_error("emformer_attention: ring too short"); return 1; }
@@ -184,7 +185,7 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; }
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }
-  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads);
+  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv, ld_att);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

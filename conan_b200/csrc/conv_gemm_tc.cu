@@ -6,9 +6,10 @@
 // The vocoder keeps the input of every causal conv in a per-slot fp16 context buffer
 // [slot, H + L, cin] (H history rows + the L rows of this chunk), so for one tap j and one
 // 64-channel slice the 128 A rows of a tile are contiguous row ranges of that buffer: the
-// producer warp fetches them with TMA boxes {BK channels, TT rows, 1 slot} (TT = largest
-// power of two <= 128 dividing L, 128/TT boxes per tile, each box with its own slot from the
-// ready list) straight into the 128B-swizzled K-major layout tcgen05.mma reads.  No im2col
+// producer warp fetches them with ONE TMA box {BK channels, TT rows, 128/TT streams} per K-block
+// (TT = largest power of two <= 128 dividing L; the engine's working buffers are compact over the
+// ready list, so consecutive streams are adjacent) straight into the swizzled K-major layout
+// tcgen05.mma reads.  No im2col
 // buffer exists anywhere; dilation is a row offset of the box.  Weights are pre-packed
 // [cout, k*cin] fp16 and fetched as {BK, BN} boxes.
 //
@@ -33,7 +34,6 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 192;
-constexpr int MAX_SUB = 32;
 
 struct TcEpi {
   const float* bias; float scale; int act; float slope;
@@ -47,7 +47,6 @@ struct TcArgs {
   int n_streams, L, TT, cin, k, dil, cout, row0;
   int kblocks;               // k * cin / BK
   int n_tiles;               // cout / BN
-  const int* slot_ids;
   TcEpi e;
 };
 
@@ -212,21 +211,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  __shared__ int s_slot[MAX_SUB], s_t0[MAX_SUB], s_valid[MAX_SUB];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x % a.n_tiles, mt = blockIdx.x / a.n_tiles;
-  const int NSUB = TILE_M / a.TT, TPS = a.L / a.TT;
+  // a tile is NS = 128/TT consecutive streams x TT consecutive time steps: one rectangular TMA box
+  const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
+  const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
 
-  if (threadIdx.x < NSUB) {
-    int g = mt * NSUB + threadIdx.x;
-    int i = g / TPS;
-    int ok = i < a.n_streams;
-    int ic = ok ? i : a.n_streams - 1;
-    s_slot[threadIdx.x] = a.slot_ids ? a.slot_ids[ic] : ic;
-    s_t0[threadIdx.x] = (g % TPS) * a.TT;
-    s_valid[threadIdx.x] = ok;
-  }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -255,8 +246,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* sb = sa + SL::A_BYTES;
         mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
         const int j = kb / kb_per_tap, c0 = (kb - j * kb_per_tap) * BK;
-        for (int q = 0; q < NSUB; ++q)
-          tma_load_3d(sa + q * a.TT * SWZ, &tmA, &full_bar[s], c0, a.row0 + s_t0[q] + j * a.dil, s_slot[q]);
+        tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0);     // box {BK, TT, NS}
         tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
       }
     }
@@ -286,7 +276,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;       // tile row == TMEM lane
     const int q = r / a.TT, tt = r - q * a.TT;
-    epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16), nt * BN, s_valid[q] != 0, s_slot[q], s_t0[q] + tt,
+    const int stream = stream0 + q;
+    epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16), nt * BN, stream < a.n_streams, stream, t0 + tt,
                       tmem_full_bar, 0);
     tc_fence_before();
   }
@@ -311,7 +302,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ==============================================================================================
 struct WinArgs {
   int L, k, dil, row0, win_rows, num_tiles, tiles_per_stream;
-  const int* slot_ids;
   TcEpi e;
 };
 
@@ -373,9 +363,8 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t ph = (it / NBUF) & 1;
         mbar_wait(&a_empty[buf], ph ^ 1);
         const int si = g / a.tiles_per_stream, t0 = (g - si * a.tiles_per_stream) * TILE_M;
-        const int slot = a.slot_ids ? a.slot_ids[si] : si;
         mbar_expect_tx(&a_full[buf], (uint32_t)(a.win_rows * ROWB));
-        tma_load_3d(sA + buf * winb, &tmA, &a_full[buf], 0, a.row0 + t0, slot);
+        tma_load_3d(sA + buf * winb, &tmA, &a_full[buf], 0, a.row0 + t0, si);
       }
     }
   } else if (warp == 1) {
@@ -416,8 +405,7 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int si = g / a.tiles_per_stream, t0 = (g - si * a.tiles_per_stream) * TILE_M;
-      const int slot = a.slot_ids ? a.slot_ids[si] : si;
-      epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), 0, true, slot, t0 + r,
+      epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), 0, true, si, t0 + r,
                         &acc_full[ab], aph);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
@@ -568,7 +556,6 @@ int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
   WinArgs a;
   a.L = p.L; a.k = p.k; a.dil = p.dil; a.row0 = p.row0; a.win_rows = win_rows;
   a.tiles_per_stream = p.L / TILE_M; a.num_tiles = p.n_streams * a.tiles_per_stream;
-  a.slot_ids = p.slot_ids;
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
               p.y2_row_stride, p.y2_row0, p.act2, p.slope2};
@@ -589,6 +576,7 @@ int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
 
 bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
   if (!p.x_is_half) return false;
+  if (p.slot_ids) return false;                   // compact operands only: a tile's input must be one rectangular TMA box
   if (p.y2 && !p.y2_is_half) return false;
   if (p.cin % 32 != 0 || p.x_row_stride != p.cin) return false;
   if (pick_bn(p.cout) == 0 || pick_tt(p.L) == 0) return false;
@@ -611,19 +599,19 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   const int Ktot = p.k * p.cin;
   CUtensorMap tmA, tmW;
   if (get_tensor_map(&tmA, p.x, 3, (unsigned long long)p.cin, (unsigned long long)p.x_rows, (unsigned long long)p.n_slots,
-                     (unsigned long long)p.x_row_stride * 2, (unsigned long long)p.x_slot_stride * 2, BK, TT, 1, BK * 2))
+                     (unsigned long long)p.x_row_stride * 2, (unsigned long long)p.x_slot_stride * 2, BK, TT, TILE_M / TT, BK * 2))
     return 1;
   if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, BN, 1,
                      BK * 2))
     return 1;
   TcArgs a;
   a.n_streams = p.n_streams; a.L = p.L; a.TT = TT; a.cin = p.cin; a.k = p.k; a.dil = p.dil; a.cout = p.cout; a.row0 = p.row0;
-  a.kblocks = Ktot / BK; a.n_tiles = p.cout / BN; a.slot_ids = p.slot_ids;
+  a.kblocks = Ktot / BK; a.n_tiles = p.cout / BN;
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
               p.y2_row_stride, p.y2_row0, p.act2, p.slope2};
-  const long long M = (long long)p.n_streams * p.L;
-  const long long m_tiles = (M + TILE_M - 1) / TILE_M;
+  const int NS = TILE_M / TT;
+  const long long m_tiles = (long long)((p.n_streams + NS - 1) / NS) * (p.L / TT);
   if (BK == 64) {
     if (BN == 128) return launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
     if (BN == 64) return launch_variant<64, 64, 2>(tmA, tmW, a, m_tiles, st);

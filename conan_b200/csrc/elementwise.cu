@@ -64,12 +64,10 @@ __global__ void advance_past_len_kernel(int* past_len, int n, const int* slot_id
   if (i < n) past_len[slot_of(slot_ids, i)] += seg;
 }
 
-__global__ void argmax_rows_kernel(const float* __restrict__ logits, int* tokens_slot, int* tokens_out, int n,
-                                   const int* slot_ids, int rows, int C) {
+__global__ void argmax_rows_kernel(const float* __restrict__ logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n * rows) return;
-  int i = warp / rows, t = warp - i * rows, slot = slot_of(slot_ids, i);
-  const float* x = logits + ((long long)slot * rows + t) * C;
+  const float* x = logits + (long long)warp * ld;
   float best = -INFINITY; int bi = 0x7fffffff;
   for (int c = lane; c < C; c += 32) { float v = x[c]; if (v > best) { best = v; bi = c; } }   // first max within a lane
 #pragma unroll
@@ -77,7 +75,7 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, int* tokens
     float ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }                        // torch.argmax: first occurrence
   }
-  if (lane == 0) { tokens_slot[slot * rows + t] = bi; if (tokens_out) tokens_out[i * rows + t] = bi; }
+  if (lane == 0) { if (tokens_a) tokens_a[warp] = bi; if (tokens_b) tokens_b[warp] = bi; }
 }
 
 __global__ void copy_rows_out_kernel(const float* __restrict__ src, long long slot_stride, int row_stride, int row0,
@@ -223,19 +221,16 @@ __global__ void conv_post_tanh_kernel(const T* __restrict__ x, long long slot_st
 }
 
 // ------------------------------------------------------------------ ring maintenance
-__global__ void ring_shift_kernel(const RingDesc* __restrict__ rings, int n, const int* slot_ids) {
-  extern __shared__ __align__(16) unsigned char sh[];
-  RingDesc d = rings[blockIdx.x];
+__global__ void hist_move_kernel(const HistDesc* __restrict__ descs, const int* slot_ids, int scatter) {
+  HistDesc d = descs[blockIdx.x];
+  if (scatter && !d.scatter_back) return;
   int slot = slot_of(slot_ids, blockIdx.y);
-  unsigned char* base = reinterpret_cast<unsigned char*>(d.base) + (long long)slot * d.slot_stride_bytes;
-  // [hist | new] -> keep the last hist bytes.  Sizes are multiples of 16 bytes.
-  const uint4* src = reinterpret_cast<const uint4*>(base + d.new_bytes);
-  uint4* stage = reinterpret_cast<uint4*>(sh);
-  int nv = d.hist_bytes >> 4;
-  for (int q = threadIdx.x; q < nv; q += blockDim.x) stage[q] = src[q];
-  __syncthreads();
-  uint4* dst = reinterpret_cast<uint4*>(base);
-  for (int q = threadIdx.x; q < nv; q += blockDim.x) dst[q] = stage[q];
+  unsigned char* w = reinterpret_cast<unsigned char*>(d.work) + (long long)blockIdx.y * d.work_stride_bytes + (scatter ? d.new_bytes : 0);
+  unsigned char* h = reinterpret_cast<unsigned char*>(d.hist) + (long long)slot * d.hist_bytes;
+  const uint4* src = reinterpret_cast<const uint4*>(scatter ? w : h);
+  uint4* dst = reinterpret_cast<uint4*>(scatter ? h : w);
+  int nv = d.hist_bytes >> 4;                              // sizes are multiples of 16 bytes
+  for (int q = threadIdx.x; q < nv; q += blockDim.x) dst[q] = src[q];
 }
 
 __global__ void zero_slots_kernel(const ZeroDesc* __restrict__ descs, int n, const int* slot_ids) {
@@ -398,10 +393,10 @@ int launch_advance_past_len(int* past_len, int n, const int* slot_ids, int seg, 
   return 0;
 }
 
-int launch_argmax_rows(const float* logits, int* tokens_slot, int* tokens_out, int n, const int* slot_ids, int rows, int C, cudaStream_t st) {
+int launch_argmax_rows(const float* logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C, cudaStream_t st) {
   if (n <= 0) return 0;
   long long warps = (long long)n * rows;
-  argmax_rows_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(logits, tokens_slot, tokens_out, n, slot_ids, rows, C);
+  argmax_rows_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(logits, ld, tokens_a, tokens_b, n, rows, C);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -467,15 +462,16 @@ int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, i
   return 0;
 }
 
-int launch_ring_shift(const RingDesc* rings_dev, int n_rings, int max_hist_bytes, int n, const int* slot_ids, cudaStream_t st) {
-  if (n <= 0 || n_rings <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ring_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
-  if (max_hist_bytes > 200 * 1024) { set_error("ring_shift: history larger than 200 KB"); return 1; }
-  ring_shift_kernel<<<dim3(n_rings, n), 256, max_hist_bytes, st>>>(rings_dev, n, slot_ids);
+int launch_hist_gather(const HistDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st) {
+  if (n <= 0 || n_descs <= 0) return 0;
+  hist_move_kernel<<<dim3(n_descs, n), 128, 0, st>>>(descs_dev, slot_ids, 0);
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_hist_scatter(const HistDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st) {
+  if (n <= 0 || n_descs <= 0) return 0;
+  hist_move_kernel<<<dim3(n_descs, n), 128, 0, st>>>(descs_dev, slot_ids, 1);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

@@ -1,15 +1,16 @@
 // The resident-state engine behind the C ABI (include/conan_b200.h).
 //
-// State lives in HBM as a slab of per-slot buffers (struct-of-arrays: one allocation per
-// logical tensor, `max_slots` slots each):
+// Resident state lives in HBM as a slab of per-slot tensors (struct-of-arrays, `max_slots` entries):
 //   * Emformer: K|V ring per layer [slot, ring_rows, 2D] + past_len[slot]
-//   * Conan   : causal "context buffers" [slot, H + L, C] in front of every causal conv
-//               (H = (k-1)*dil zero-initialised history rows, L = rows produced per chunk),
+//   * Conan / vocoder: the H = (k-1)*dil history rows in front of every causal conv, [slot, H, C]
+//               (fp32 for Conan, fp16 = tensor-core operand type or fp32 for the vocoder),
 //               per-session style vector and aligner K/V cache
-//   * vocoder : the same context buffers, fp16 (tensor-core operand type) or fp32
-// A chunk step runs every layer over the n ready streams named by slot_ids (one launch per
-// layer, the slot indirection is resolved inside the kernels), then one ring-shift kernel per
-// sub-model moves the last H rows of every context buffer to its front.
+// A chunk step works on COMPACT buffers indexed by the position i of a stream in the ready list:
+// every causal conv reads a context buffer [i, H + L, C]; one gather launch per sub-model copies the
+// H history rows of slot_ids[i] in front of the L rows this chunk produces, every layer then runs
+// as one launch over contiguous rows (so a tile's operand is one TMA box, whatever slots are ready),
+// and one scatter launch writes the last H rows back to the slots.  Gather + scatter move exactly the
+// bytes an in-place ring shift would.
 #include <cstdio>
 #include <cstring>
 #include <atomic>
@@ -27,8 +28,9 @@ static std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-struct Ctx {                 // context buffer [slot, H + L + R, C]
+struct Ctx {                 // compact context buffer [i, H + L + R, C]; resident history [slot, H, C]
   void* p = nullptr;
+  void* hist = nullptr;
   int H = 0, L = 0, R = 0, C = 0, is_half = 0;
   int rows() const { return H + L + R; }
   long long slot_stride() const { return (long long)rows() * C; }
@@ -69,9 +71,10 @@ struct conan_engine {
   Ctx vPRE, vUP[8], vXA[8], vC1[8][4][4], vC2[8][4][4], vPOST;
   float *vXS = nullptr, *vXR[2] = {nullptr, nullptr}, *vSUM = nullptr;
   int vL[9], vC[9];     // rows / channels entering scale i (vL[0] = segment, vC[0] = initial channel)
-  // ---- ring tables
-  RingDesc* ringsConan = nullptr; int nRingsConan = 0, maxHistConan = 0;
-  RingDesc* ringsVoc = nullptr; int nRingsVoc = 0, maxHistVoc = 0;
+  // ---- history gather/scatter tables
+  HistDesc* histConan = nullptr; int nHistConan = 0;
+  HistDesc* histVoc = nullptr; int nHistVoc = 0;
+  float* sSTYLEW = nullptr;      // compact copy of the style vectors of the ready streams
   ZeroDesc* zeroEmf = nullptr; int nZeroEmf = 0;
   ZeroDesc* zeroConan = nullptr; int nZeroConan = 0;
   ZeroDesc* zeroVoc = nullptr; int nZeroVoc = 0;
@@ -210,33 +213,39 @@ int dalloc(conan_engine* e, T** out, size_t count) {
   return 0;
 }
 
-int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half) {
+int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half, bool resident = true) {
   c->H = H; c->L = L; c->R = R; c->C = C; c->is_half = is_half;
-  size_t count = (size_t)e->S * c->rows() * C;
-  if (is_half) { __half* p; if (dalloc(e, &p, count)) return 1; c->p = p; }
-  else { float* p; if (dalloc(e, &p, count)) return 1; c->p = p; }
+  size_t count = (size_t)e->S * c->rows() * C;           // compact work buffer (up to max_slots streams per step)
+  size_t hcount = (resident && H > 0) ? (size_t)e->S * H * C : 0;
+  if (is_half) {
+    __half* p; if (dalloc(e, &p, count)) return 1; c->p = p;
+    if (hcount) { __half* h; if (dalloc(e, &h, hcount)) return 1; c->hist = h; }
+  } else {
+    float* p; if (dalloc(e, &p, count)) return 1; c->p = p;
+    if (hcount) { float* h; if (dalloc(e, &h, hcount)) return 1; c->hist = h; }
+  }
   return 0;
 }
 
-// ---- conv parameter builders ---------------------------------------------------------------
+// ---- conv parameter builders (all compact: stream i of the ready list, no slot indirection) -----
 conan_conv_params_t conv_on_ctx(const conan_engine* e, const Ctx& in, int k, int dil, const void* w, const float* bias,
-                                int cout, int n, const int* ids, bool causal = true) {
+                                int cout, int n, bool causal = true) {
   conan_conv_params_t p;
   memset(&p, 0, sizeof(p));
   p.x = in.p; p.x_slot_stride = in.slot_stride(); p.x_row_stride = in.C; p.x_rows = in.rows(); p.x_is_half = in.is_half;
   p.row0 = causal ? in.H - (k - 1) * dil : in.H - ((k - 1) * dil) / 2;
   p.L = in.L; p.cin = in.C; p.k = k; p.dil = dil; p.cout = cout; p.w = w; p.bias = bias;
-  p.n_streams = n; p.slot_ids = ids; p.n_slots = e->S;
+  p.n_streams = n; p.slot_ids = nullptr; p.n_slots = e->S;
   p.scale = 1.f; p.out_scale = 1.f;
   return p;
 }
 conan_conv_params_t conv_on_rows(const conan_engine* e, const float* x, int rows_per_slot, int row0, int L, int C,
-                                 const void* w, const float* bias, int cout, int n, const int* ids) {
+                                 const void* w, const float* bias, int cout, int n) {
   conan_conv_params_t p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.x_slot_stride = (long long)rows_per_slot * C; p.x_row_stride = C; p.x_rows = rows_per_slot; p.x_is_half = 0;
   p.row0 = row0; p.L = L; p.cin = C; p.k = 1; p.dil = 1; p.cout = cout; p.w = w; p.bias = bias;
-  p.n_streams = n; p.slot_ids = ids; p.n_slots = e->S;
+  p.n_streams = n; p.slot_ids = nullptr; p.n_slots = e->S;
   p.scale = 1.f; p.out_scale = 1.f;
   return p;
 }
@@ -265,11 +274,11 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
 }
 
 int ln_rows(const float* in, int in_rows, int in_row0, RowView out, const float* g, const float* b, int C, int L, int n,
-            const int* ids, cudaStream_t st, const float* premask = nullptr, const float* postmask = nullptr, int mask_stride = 0,
+            cudaStream_t st, const float* premask = nullptr, const float* postmask = nullptr, int mask_stride = 0,
             float* write_mask = nullptr, float* write_mask2 = nullptr) {
   LnArgs a;
   a.in = RowView{(void*)in, (long long)in_rows * C, C, in_row0, 0};
-  a.out = out; a.gamma = g; a.beta = b; a.eps = 1e-5f; a.C = C; a.L = L; a.n = n; a.slot_ids = ids;
+  a.out = out; a.gamma = g; a.beta = b; a.eps = 1e-5f; a.C = C; a.L = L; a.n = n; a.slot_ids = nullptr;
   a.premask = premask; a.premask_slot_stride = mask_stride;
   a.postmask = postmask; a.postmask_slot_stride = mask_stride;
   a.write_mask = write_mask; a.write_mask_slot_stride = mask_stride; a.write_mask2 = write_mask2;
@@ -282,7 +291,7 @@ int ln_rows(const float* in, int in_rows, int in_row0, RowView out, const float*
 int allocate_state(conan_engine* e) {
   const conan_config_t& c = e->cfg;
   const int S = e->S, D = c.emformer_dim, H = c.hidden_size, seg = c.segment, rows = c.segment + c.right_context;
-  // ---- Emformer
+  // ---- Emformer (scratch compact, K|V ring + past_len resident)
   e->ring_rows = ((c.left_context + seg + seg - 1) / seg) * seg;      // >= lc + seg, multiple of seg
   TRY(dalloc(e, &e->eX, (size_t)S * rows * D)); TRY(dalloc(e, &e->eXN, (size_t)S * rows * D));
   TRY(dalloc(e, &e->eQKV, (size_t)S * rows * 3 * D)); TRY(dalloc(e, &e->eATT, (size_t)S * rows * D));
@@ -308,7 +317,8 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->dPOST, (size_t)S * seg * H)); TRY(dalloc(e, &e->dMEL, (size_t)S * seg * c.n_mels));
   TRY(dalloc(e, &e->dUVP, (size_t)S * seg * 4)); TRY(dalloc(e, &e->dMASK0, (size_t)S * seg));
   TRY(dalloc(e, &e->dMASKB, (size_t)S * seg));
-  TRY(dalloc(e, &e->sSTYLE, (size_t)S * H)); TRY(dalloc(e, &e->sKV, (size_t)S * 2 * e->tp_max * 2 * H));
+  TRY(dalloc(e, &e->sSTYLE, (size_t)S * H)); TRY(dalloc(e, &e->sSTYLEW, (size_t)S * H));
+  TRY(dalloc(e, &e->sKV, (size_t)S * 2 * e->tp_max * 2 * H));
   TRY(dalloc(e, &e->sKPM, (size_t)S * e->tp_max)); TRY(dalloc(e, &e->sNKEYS, (size_t)S));
   // ---- vocoder
   const int hf = c.voc_precision ? 1 : 0;
@@ -333,24 +343,22 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->vXS, (size_t)S * maxLC)); TRY(dalloc(e, &e->vXR[0], (size_t)S * maxLC));
   TRY(dalloc(e, &e->vXR[1], (size_t)S * maxLC)); TRY(dalloc(e, &e->vSUM, (size_t)S * maxLC));
 
-  // ---- ring / zero tables
-  auto build_tables = [&](std::vector<const Ctx*> ctxs, RingDesc** rings, int* nrings, int* maxhist, ZeroDesc** zeros, int* nzeros,
-                          std::vector<ZeroDesc> extra_zero) -> int {
-    std::vector<RingDesc> r; std::vector<ZeroDesc> z = extra_zero;
-    int mh = 0;
+  // ---- history / zero tables
+  auto build_tables = [&](std::vector<const Ctx*> ctxs, std::vector<HistDesc> extra, HistDesc** hist, int* nhist, ZeroDesc** zeros,
+                          int* nzeros, std::vector<ZeroDesc> extra_zero) -> int {
+    std::vector<HistDesc> r = extra; std::vector<ZeroDesc> z = extra_zero;
     for (const Ctx* cx : ctxs) {
+      if (cx->H <= 0) continue;
       size_t rowb = (size_t)cx->C * cx->elem();
-      if (cx->H > 0) {
-        RingDesc d{cx->p, (long long)(cx->slot_stride() * cx->elem()), (int)(cx->H * rowb), (int)(cx->L * rowb)};
-        if (d.hist_bytes % 16 || d.new_bytes % 16 || d.slot_stride_bytes % 16) { set_error("ring sizes must be multiples of 16 bytes"); return 1; }
-        r.push_back(d); mh = std::max(mh, d.hist_bytes);
-      }
-      z.push_back(ZeroDesc{cx->p, (long long)(cx->slot_stride() * cx->elem()), (long long)(cx->slot_stride() * cx->elem())});
+      HistDesc d{cx->p, (long long)(cx->slot_stride() * cx->elem()), cx->hist, (int)(cx->H * rowb), (int)(cx->L * rowb), 1};
+      if (d.hist_bytes % 16 || d.new_bytes % 16 || d.work_stride_bytes % 16) { set_error("context sizes must be multiples of 16 bytes"); return 1; }
+      r.push_back(d);
+      z.push_back(ZeroDesc{cx->hist, (long long)d.hist_bytes, (long long)d.hist_bytes});
     }
-    *nrings = (int)r.size(); *maxhist = mh; *nzeros = (int)z.size();
+    *nhist = (int)r.size(); *nzeros = (int)z.size();
     if (!r.empty()) {
-      TRY(dalloc(e, rings, r.size()));
-      CONAN_CUDA_OK(cudaMemcpy(*rings, r.data(), r.size() * sizeof(RingDesc), cudaMemcpyHostToDevice));
+      TRY(dalloc(e, hist, r.size()));
+      CONAN_CUDA_OK(cudaMemcpy(*hist, r.data(), r.size() * sizeof(HistDesc), cudaMemcpyHostToDevice));
     }
     if (!z.empty()) {
       TRY(dalloc(e, zeros, z.size()));
@@ -363,14 +371,16 @@ int allocate_state(conan_engine* e) {
     for (int l = 0; l < c.emformer_layers; ++l)
       ez.push_back(ZeroDesc{e->eRing[l], (long long)e->ring_rows * 2 * D * 4, (long long)e->ring_rows * 2 * D * 4});
     ez.push_back(ZeroDesc{e->ePast, 4, 4});
-    RingDesc* dummy = nullptr; int nd = 0, mh = 0;
-    TRY(build_tables({}, &dummy, &nd, &mh, &e->zeroEmf, &e->nZeroEmf, ez));
+    HistDesc* dummy = nullptr; int nd = 0;
+    TRY(build_tables({}, {}, &dummy, &nd, &e->zeroEmf, &e->nZeroEmf, ez));
   }
   {
     std::vector<const Ctx*> cs{&e->cC, &e->cP};
     for (int i = 0; i < 5; ++i) cs.push_back(&e->cUV[i]);
     for (int b = 0; b < c.dec_blocks; ++b) for (int s = 0; s < 2; ++s) cs.push_back(&e->cD[b][s]);
-    TRY(build_tables(cs, &e->ringsConan, &e->nRingsConan, &e->maxHistConan, &e->zeroConan, &e->nZeroConan, {}));
+    // the session's style vector is read-only state: gathered into a compact copy, never scattered back
+    std::vector<HistDesc> extra{HistDesc{e->sSTYLEW, (long long)H * 4, e->sSTYLE, H * 4, 0, 0}};
+    TRY(build_tables(cs, extra, &e->histConan, &e->nHistConan, &e->zeroConan, &e->nZeroConan, {}));
   }
   {
     std::vector<const Ctx*> cs{&e->vPRE, &e->vPOST};
@@ -379,7 +389,7 @@ int allocate_state(conan_engine* e) {
       for (int r = 0; r < c.voc_n_res; ++r)
         for (int j = 0; j < c.voc_n_dil; ++j) { if (j > 0) cs.push_back(&e->vC1[i][r][j]); cs.push_back(&e->vC2[i][r][j]); }
     }
-    TRY(build_tables(cs, &e->ringsVoc, &e->nRingsVoc, &e->maxHistVoc, &e->zeroVoc, &e->nZeroVoc, {}));
+    TRY(build_tables(cs, {}, &e->histVoc, &e->nHistVoc, &e->zeroVoc, &e->nZeroVoc, {}));
   }
   // ---- session scratch
   e->SB = std::min(S, 32);
@@ -411,34 +421,35 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
                   int* tokens_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
   const int D = c.emformer_dim, seg = c.segment, rc = c.right_context, rows = seg + rc, F = c.emformer_ffn;
-  TRY(launch_emformer_assemble(chunk, e->eX, n, ids, seg, rc, D, st));
+  TRY(launch_emformer_assemble(chunk, e->eX, n, nullptr, seg, rc, D, st));
   for (int l = 0; l < c.emformer_layers; ++l) {
     std::string p = "emf." + std::to_string(l) + ".";
-    TRY(ln_rows(e->eX, rows, 0, view_f32(e->eXN, (long long)rows * D, D), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, ids, st));
-    auto q = conv_on_rows(e, e->eXN, rows, 0, rows, D, e->P(p + "qkv.w"), e->F(p + "qkv.b"), 3 * D, n, ids);
+    TRY(ln_rows(e->eX, rows, 0, view_f32(e->eXN, (long long)rows * D, D), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, st));
+    auto q = conv_on_rows(e, e->eXN, rows, 0, rows, D, e->P(p + "qkv.w"), e->F(p + "qkv.b"), 3 * D, n);
     out_rows(q, e->eQKV, rows, 3 * D);
     TRY(run_conv(e, q, st));
     TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT, n, ids, seg, rc, c.left_context, e->ring_rows, D,
-                                  c.emformer_heads, st));
-    auto o = conv_on_rows(e, e->eATT, rows, 0, rows, D, e->P(p + "out.w"), e->F(p + "out.b"), D, n, ids);
+                                  c.emformer_heads, 3 * D, D, st));
+    auto o = conv_on_rows(e, e->eATT, rows, 0, rows, D, e->P(p + "out.w"), e->F(p + "out.b"), D, n);
     out_rows(o, e->eR1, rows, D); res_rows(o, e->eX, rows, D);
     TRY(run_conv(e, o, st));
-    TRY(ln_rows(e->eR1, rows, 0, view_f32(e->eFN, (long long)rows * D, D), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, ids, st));
-    auto f1 = conv_on_rows(e, e->eFN, rows, 0, rows, D, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n, ids);
+    TRY(ln_rows(e->eR1, rows, 0, view_f32(e->eFN, (long long)rows * D, D), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
+    auto f1 = conv_on_rows(e, e->eFN, rows, 0, rows, D, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
     out_rows(f1, e->eHF, rows, F); f1.act = ACT_RELU;
     TRY(run_conv(e, f1, st));
-    auto f2 = conv_on_rows(e, e->eHF, rows, 0, rows, F, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), D, n, ids);
+    auto f2 = conv_on_rows(e, e->eHF, rows, 0, rows, F, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), D, n);
     out_rows(f2, e->eR2, rows, D); res_rows(f2, e->eR1, rows, D);
     TRY(run_conv(e, f2, st));
-    TRY(ln_rows(e->eR2, rows, 0, view_f32(e->eX, (long long)rows * D, D), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, ids, st));
+    TRY(ln_rows(e->eR2, rows, 0, view_f32(e->eX, (long long)rows * D, D), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st));
   }
   TRY(launch_advance_past_len(e->ePast, n, ids, seg, st));
-  auto pj = conv_on_rows(e, e->eX, rows, rc, seg, D, e->P("emf.proj.w"), e->F("emf.proj.b"), c.emformer_output_dim, n, ids);
+  auto pj = conv_on_rows(e, e->eX, rows, rc, seg, D, e->P("emf.proj.w"), e->F("emf.proj.b"), c.emformer_output_dim, n);
   out_rows(pj, e->eLOG, seg, c.emformer_output_dim);
   TRY(run_conv(e, pj, st));
-  TRY(launch_argmax_rows(e->eLOG, e->TOK, tokens_out, n, ids, seg, c.emformer_output_dim, st));
-  if (enc_out) TRY(launch_copy_rows_out(e->eX, (long long)rows * D, D, rc, enc_out, n, ids, seg, D, st));
-  if (logits_out) TRY(launch_copy_rows_out(e->eLOG, (long long)seg * c.emformer_output_dim, c.emformer_output_dim, 0, logits_out, n, ids, seg, c.emformer_output_dim, st));
+  TRY(launch_argmax_rows(e->eLOG, c.emformer_output_dim, e->TOK, tokens_out, n, seg, c.emformer_output_dim, st));
+  if (enc_out) TRY(launch_copy_rows_out(e->eX, (long long)rows * D, D, rc, enc_out, n, nullptr, seg, D, st));
+  if (logits_out)
+    CONAN_CUDA_OK(cudaMemcpyAsync(logits_out, e->eLOG, (size_t)n * seg * c.emformer_output_dim * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -446,78 +457,81 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
 int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, float* mel_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
   const int H = c.hidden_size, seg = c.segment;
-  if (tokens_ext) TRY(launch_copy_rows_in(tokens_ext, 1, e->TOK, seg, n, ids, seg, st));
-  TRY(launch_embedding_rows(e->TOK, e->F("conan.content_embedding"), 102, e->cC.new_rows(), n, ids, seg, H, st));
+  const int* tok = tokens_ext ? tokens_ext : e->TOK;            // compact [n, seg]
+  TRY(launch_hist_gather(e->histConan, e->nHistConan, n, ids, st));
+  TRY(launch_embedding_rows(tok, e->F("conan.content_embedding"), 102, e->cC.new_rows(), n, nullptr, seg, H, st));
   {
-    auto p = conv_on_ctx(e, e->cC, c.content_kernel, 1, e->P("conan.content_proj.w"), e->F("conan.content_proj.b"), H, n, ids);
+    auto p = conv_on_ctx(e, e->cC, c.content_kernel, 1, e->P("conan.content_proj.w"), e->F("conan.content_proj.b"), H, n);
     out_rows(p, e->dX0, seg, H); p.act = ACT_LRELU; p.slope = 0.01f;
-    p.res = e->sSTYLE; p.res_slot_stride = H; p.res_row_stride = 0;                  // + style_embed (Conan.py:162)
+    p.res = e->sSTYLEW; p.res_slot_stride = H; p.res_row_stride = 0;                 // + style_embed (Conan.py:162)
     TRY(run_conv(e, p, st));
   }
   const float* cur = e->dX0;
   for (int l = 0; l < 2; ++l) {
     std::string a = "conan.align." + std::to_string(l) + ".";
-    auto q = conv_on_rows(e, cur, seg, 0, seg, H, e->P(a + "q.w"), e->F(a + "q.b"), H, n, ids);
+    auto q = conv_on_rows(e, cur, seg, 0, seg, H, e->P(a + "q.w"), e->F(a + "q.b"), H, n);
     out_rows(q, e->dQ, seg, H);
     TRY(run_conv(e, q, st));
     TRY(launch_cross_attention(e->dQ, e->sKV, e->sKPM, e->sNKEYS, e->dATT, n, ids, seg, H, 2, l, 2, e->tp_max, st));
-    auto o = conv_on_rows(e, e->dATT, seg, 0, seg, H, e->P(a + "out.w"), e->F(a + "out.b"), H, n, ids);
+    auto o = conv_on_rows(e, e->dATT, seg, 0, seg, H, e->P(a + "out.w"), e->F(a + "out.b"), H, n);
     out_rows(o, e->dT1, seg, H); res_rows(o, cur, seg, H);
     TRY(run_conv(e, o, st));
-    TRY(ln_rows(e->dT1, seg, 0, view_f32(e->dO1, (long long)seg * H, H), e->F(a + "norm1.g"), e->F(a + "norm1.b"), H, seg, n, ids, st));
-    auto f1 = conv_on_rows(e, e->dO1, seg, 0, seg, H, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, n, ids);
+    TRY(ln_rows(e->dT1, seg, 0, view_f32(e->dO1, (long long)seg * H, H), e->F(a + "norm1.g"), e->F(a + "norm1.b"), H, seg, n, st));
+    auto f1 = conv_on_rows(e, e->dO1, seg, 0, seg, H, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, n);
     out_rows(f1, e->dHF, seg, 2048); f1.act = ACT_RELU;
     TRY(run_conv(e, f1, st));
-    auto f2 = conv_on_rows(e, e->dHF, seg, 0, seg, 2048, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n, ids);
+    auto f2 = conv_on_rows(e, e->dHF, seg, 0, seg, 2048, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n);
     out_rows(f2, e->dT2, seg, H); res_rows(f2, e->dO1, seg, H);
     TRY(run_conv(e, f2, st));
-    TRY(ln_rows(e->dT2, seg, 0, view_f32(e->dPROS[l], (long long)seg * H, H), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, ids, st));
+    TRY(ln_rows(e->dT2, seg, 0, view_f32(e->dPROS[l], (long long)seg * H, H), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st));
     cur = e->dPROS[l];
   }
-  TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, ids, seg, H, st));      // Conan.py:168
+  TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, nullptr, seg, H, st));  // Conan.py:168
   for (int i = 0; i < 5; ++i) {                                                                // uv_predictor convs
     std::string u = "conan.uv." + std::to_string(i) + ".";
-    auto p = conv_on_ctx(e, e->cUV[i], c.predictor_kernel, 1, e->P(u + "w"), e->F(u + "b"), 128, n, ids);
+    auto p = conv_on_ctx(e, e->cUV[i], c.predictor_kernel, 1, e->P(u + "w"), e->F(u + "b"), 128, n);
     p.act = ACT_RELU;
     if (i < 4) out_ctx(p, e->cUV[i + 1]); else out_rows(p, e->dUVH, seg, 128);
     TRY(run_conv(e, p, st));
   }
-  TRY(launch_pitch(e->dUVH, e->F("conan.uv.ln.g"), e->F("conan.uv.ln.b"), e->F("conan.uv.lin.w"), e->F("conan.uv.lin.b"), e->TOK,
-                   c.silent_token, e->F("conan.pitch_embed"), e->dPINP, e->dDECX, e->dUVP, n, ids, seg, 128, H, st));
+  TRY(launch_pitch(e->dUVH, e->F("conan.uv.ln.g"), e->F("conan.uv.ln.b"), e->F("conan.uv.lin.w"), e->F("conan.uv.lin.b"), tok,
+                   c.silent_token, e->F("conan.pitch_embed"), e->dPINP, e->dDECX, e->dUVP, n, nullptr, seg, 128, H, st));
   for (int b = 0; b < c.dec_blocks; ++b)
     for (int s = 0; s < 2; ++s) {
       std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
-      TRY(ln_rows(e->dDECX, seg, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, ids, st, nullptr, nullptr, seg,
+      TRY(ln_rows(e->dDECX, seg, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, st, nullptr, nullptr, seg,
                   s == 0 ? e->dMASKB : nullptr, (b == 0 && s == 0) ? e->dMASK0 : nullptr));
-      auto p = conv_on_ctx(e, e->cD[b][s], c.dec_kernel, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, n, ids);
+      auto p = conv_on_ctx(e, e->cD[b][s], c.dec_kernel, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, n);
       out_rows(p, e->dDECH, seg, 2 * H); p.scale = 1.0f / sqrtf((float)c.dec_kernel); p.act = ACT_GELU;
       TRY(run_conv(e, p, st));
-      auto w = conv_on_rows(e, e->dDECH, seg, 0, seg, 2 * H, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n, ids);
+      auto w = conv_on_rows(e, e->dDECH, seg, 0, seg, 2 * H, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n);
       out_rows(w, e->dDECX, seg, H); res_rows(w, e->dDECX, seg, H); w.rowmask = e->dMASKB; w.mask_slot_stride = seg;
       TRY(run_conv(e, w, st));
     }
-  TRY(ln_rows(e->dDECX, seg, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, ids, st,
+  TRY(ln_rows(e->dDECX, seg, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, st,
               e->dMASK0, e->dMASK0, seg));
   {
-    auto p = conv_on_ctx(e, e->cP, c.dec_post_kernel, 1, e->P("conan.dec.post.w"), e->F("conan.dec.post.b"), H, n, ids);
+    auto p = conv_on_ctx(e, e->cP, c.dec_post_kernel, 1, e->P("conan.dec.post.w"), e->F("conan.dec.post.b"), H, n);
     out_rows(p, e->dPOST, seg, H); p.rowmask = e->dMASK0; p.mask_slot_stride = seg;
     TRY(run_conv(e, p, st));
-    auto m = conv_on_rows(e, e->dPOST, seg, 0, seg, H, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), c.n_mels, n, ids);
+    auto m = conv_on_rows(e, e->dPOST, seg, 0, seg, H, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), c.n_mels, n);
     out_rows(m, e->dMEL, seg, c.n_mels);
-    out2_ctx(m, e->vPRE, ACT_NONE, 0.f);                                                       // feeds conv_pre of the vocoder
     TRY(run_conv(e, m, st));
   }
-  TRY(launch_ring_shift(e->ringsConan, e->nRingsConan, e->maxHistConan, n, ids, st));
-  if (mel_out) TRY(launch_copy_rows_out(e->dMEL, (long long)seg * c.n_mels, c.n_mels, 0, mel_out, n, ids, seg, c.n_mels, st));
+  TRY(launch_hist_scatter(e->histConan, e->nHistConan, n, ids, st));
+  if (mel_out) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out, e->dMEL, (size_t)n * seg * c.n_mels * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
 // ============================================================================ vocoder step
-int vocoder_pass(conan_engine* e, int n, const int* ids, float* wav_out, cudaStream_t st) {
+// mel: compact fp32 rows [n, seg, n_mels] of the streams ids[0..n)
+int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float* wav_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
   const float sl = 0.1f;
+  TRY(launch_hist_gather(e->histVoc, e->nHistVoc, n, ids, st));
+  TRY(launch_rows_to_view(mel, e->vPRE.new_rows(), n, nullptr, c.segment, c.n_mels, st));
   {
-    auto p = conv_on_ctx(e, e->vPRE, 7, 1, e->P("voc.pre.w"), e->F("voc.pre.b"), e->vC[0], n, ids);
+    auto p = conv_on_ctx(e, e->vPRE, 7, 1, e->P("voc.pre.w"), e->F("voc.pre.b"), e->vC[0], n);
     out2_ctx(p, e->vUP[0], ACT_LRELU, sl);
     TRY(run_conv(e, p, st, true));
   }
@@ -526,8 +540,8 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, float* wav_out, cudaStr
     std::string u = "voc.up." + std::to_string(i) + ".";
     {
       // conv -> pixel shuffle folded into the weight row order: output row t holds r_up consecutive
-      // output frames, i.e. [slot, L_in, r*C] viewed as [slot, L_in*r, C]  (hifigan_causal.py:186-188)
-      auto p = conv_on_ctx(e, e->vUP[i], c.voc_up_kernels[i], 1, e->P(u + "w"), e->F(u + "b"), r_up * C, n, ids);
+      // output frames, i.e. [i, L_in, r*C] viewed as [i, L_in*r, C]  (hifigan_causal.py:186-188)
+      auto p = conv_on_ctx(e, e->vUP[i], c.voc_up_kernels[i], 1, e->P(u + "w"), e->F(u + "b"), r_up * C, n);
       p.y = e->vXS; p.y_slot_stride = (long long)L * C; p.y_row_stride = r_up * C; p.y_row0 = 0;
       p.y2 = e->vXA[i].at_row(e->vXA[i].H); p.y2_slot_stride = e->vXA[i].slot_stride(); p.y2_row_stride = r_up * C; p.y2_row0 = 0;
       p.y2_is_half = e->vXA[i].is_half; p.act2 = ACT_LRELU; p.slope2 = sl;
@@ -542,11 +556,11 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, float* wav_out, cudaStr
       for (int j = 0; j < c.voc_n_dil; ++j) {
         const Ctx& in1 = (j == 0) ? e->vXA[i] : e->vC1[i][r][j];
         auto p1 = conv_on_ctx(e, in1, k, c.voc_res_dilations[j], e->P(q + "c1." + std::to_string(j) + ".w"),
-                              e->F(q + "c1." + std::to_string(j) + ".b"), C, n, ids);
+                              e->F(q + "c1." + std::to_string(j) + ".b"), C, n);
         out2_ctx(p1, e->vC2[i][r][j], ACT_LRELU, sl);
         TRY(run_conv(e, p1, st, true));
         auto p2 = conv_on_ctx(e, e->vC2[i][r][j], k, 1, e->P(q + "c2." + std::to_string(j) + ".w"),
-                              e->F(q + "c2." + std::to_string(j) + ".b"), C, n, ids);
+                              e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
         res_rows(p2, xj, L, C);
         if (j + 1 < c.voc_n_dil) {
           float* xn = e->vXR[j & 1];
@@ -564,20 +578,20 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, float* wav_out, cudaStr
   }
   const int Lw = e->vL[c.voc_n_ups];
   TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
-                            e->F("voc.post.w"), e->F("voc.post.b"), wav_out, n, ids, st));
-  TRY(launch_ring_shift(e->ringsVoc, e->nRingsVoc, e->maxHistVoc, n, ids, st));
+                            e->F("voc.post.w"), e->F("voc.post.b"), wav_out, n, nullptr, st));
+  TRY(launch_hist_scatter(e->histVoc, e->nHistVoc, n, ids, st));
   return 0;
 }
 
 int vocoder_step(conan_engine* e, int n, const int* ids, const float* mel_ext, float* wav_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
-  if (mel_ext) {
-    TRY(launch_copy_rows_in(mel_ext, 0, e->dMEL, (long long)c.segment * c.n_mels, n, ids, c.segment * c.n_mels, st));
-    TRY(launch_rows_to_view(e->dMEL, e->vPRE.new_rows(), n, ids, c.segment, c.n_mels, st));
-  }
+  const float* mel = mel_ext ? mel_ext : e->dMEL;
+  // voc_group > 0: the compact buffers [0, G) are reused by consecutive groups of streams, so one group's
+  // activations (G x ~5 MB) can stay L2-resident between producer and consumer layers
   const int G = c.voc_group > 0 ? c.voc_group : n;
   const int Lw = e->vL[c.voc_n_ups];
-  for (int g = 0; g < n; g += G) TRY(vocoder_pass(e, std::min(G, n - g), ids + g, wav_out + (size_t)g * Lw, st));
+  for (int g = 0; g < n; g += G)
+    TRY(vocoder_pass(e, std::min(G, n - g), ids + g, mel + (size_t)g * c.segment * c.n_mels, wav_out + (size_t)g * Lw, st));
   return 0;
 }
 
@@ -593,17 +607,17 @@ int conv_blocks_noncausal(conan_engine* e, const std::string& pre, float* X, int
   for (int b = 0; b < 5; ++b)
     for (int s = 0; s < 2; ++s) {
       std::string d = pre + "." + std::to_string(b) + "." + std::to_string(s) + ".";
-      TRY(ln_rows(X, T, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, nullptr, st, nullptr, nullptr, T,
+      TRY(ln_rows(X, T, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, st, nullptr, nullptr, T,
                   s == 0 ? maskb : nullptr, nullptr));
-      auto p = conv_on_ctx(e, ck, k, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * C, n, nullptr, false);
+      auto p = conv_on_ctx(e, ck, k, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * C, n, false);
       p.n_slots = n; out_rows(p, Hbuf, T, 2 * C); p.scale = 1.0f / sqrtf((float)k); p.act = ACT_GELU;
       TRY(run_conv(e, p, st));
-      auto w = conv_on_rows(e, Hbuf, T, 0, T, 2 * C, e->P(d + "pw.w"), e->F(d + "pw.b"), C, n, nullptr);
+      auto w = conv_on_rows(e, Hbuf, T, 0, T, 2 * C, e->P(d + "pw.w"), e->F(d + "pw.b"), C, n);
       w.n_slots = n; out_rows(w, X, T, C); res_rows(w, X, T, C); w.rowmask = maskb; w.mask_slot_stride = T;
       TRY(run_conv(e, w, st));
     }
-  TRY(ln_rows(X, T, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, nullptr, st, nonpad, nonpad, T));
-  auto p = conv_on_ctx(e, c3, 3, 1, e->P(pre + ".post.w"), e->F(pre + ".post.b"), outC, n, nullptr, false);
+  TRY(ln_rows(X, T, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, st, nonpad, nonpad, T));
+  auto p = conv_on_ctx(e, c3, 3, 1, e->P(pre + ".post.w"), e->F(pre + ".post.b"), outC, n, false);
   p.n_slots = n; out_rows(p, OUT, T, outC); p.rowmask = nonpad; p.mask_slot_stride = T;
   TRY(run_conv(e, p, st));
   return 0;
@@ -617,7 +631,7 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
   TRY(launch_row_masks(ref, e->qMA, e->qMF, n, T, M, st));
   // ---- global style encoder (Conan.py:200-219)
   {
-    auto p = conv_on_rows(e, ref, T, 0, T, M, e->P("conan.global_in.w"), e->F("conan.global_in.b"), H, n, nullptr);
+    auto p = conv_on_rows(e, ref, T, 0, T, M, e->P("conan.global_in.w"), e->F("conan.global_in.b"), H, n);
     p.n_slots = n; out_rows(p, e->qXG, T, H); p.rowmask = e->qMA; p.mask_slot_stride = T;
     TRY(run_conv(e, p, st));
     TRY(conv_blocks_noncausal(e, "conan.genc", e->qXG, H, 31, e->qC31, e->qHG, e->qC3G, e->qPG, H, e->qMA, e->qMGB, n, T, st));
@@ -633,12 +647,12 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
                                     cudaMemcpyDeviceToDevice, st));
     for (int i = 0; i < 4; ++i) {
       std::string w = "conan.wn." + std::to_string(i) + ".";
-      auto p = conv_on_ctx(e, cw, 3, 1, e->P(w + "in.w"), e->F(w + "in.b"), 2 * M, n, nullptr, false);
+      auto p = conv_on_ctx(e, cw, 3, 1, e->P(w + "in.w"), e->F(w + "in.b"), 2 * M, n, false);
       p.n_slots = n; out_rows(p, e->qAW, T, 2 * M);
       TRY(run_conv(e, p, st));
       TRY(launch_gated_tanh_sigmoid(e->qAW, e->qACT, (long long)n * T, M, st));
       int co = i < 3 ? 2 * M : M;
-      auto r = conv_on_rows(e, e->qACT, T, 0, T, M, e->P(w + "rs.w"), e->F(w + "rs.b"), co, n, nullptr);
+      auto r = conv_on_rows(e, e->qACT, T, 0, T, M, e->P(w + "rs.w"), e->F(w + "rs.b"), co, n);
       r.n_slots = n; out_rows(r, e->qRS, T, co);
       TRY(run_conv(e, r, st));
       TRY(launch_wn_update(e->qRS, e->qXW, cw.new_rows(), e->qSKIP, e->qMF, (long long)n * T, T, M, i == 3, st));
@@ -650,18 +664,18 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
     TRY(launch_row_masks(e->qGRP, e->qMP, e->qMPB, n, Tp, M, st));      // qMPB is overwritten by the block masks below
     CONAN_CUDA_OK(cudaMemcpyAsync(e->qXP, e->qGRP, (size_t)n * Tp * M * 4, cudaMemcpyDeviceToDevice, st));
     TRY(conv_blocks_noncausal(e, "conan.penc", e->qXP, M, 5, e->qC5, e->qHP, e->qC3P, e->qPZ, H, e->qMP, e->qMPB, n, Tp, st));
-    auto d = conv_on_rows(e, e->qPZ, Tp, 0, Tp, H, e->P("conan.vq.embedding"), nullptr, c.n_vq, n, nullptr);
+    auto d = conv_on_rows(e, e->qPZ, Tp, 0, Tp, H, e->P("conan.vq.embedding"), nullptr, c.n_vq, n);
     d.n_slots = n; out_rows(d, e->qXE, Tp, c.n_vq);
     TRY(run_conv(e, d, st));
     TRY(launch_vq_quantize(e->qPZ, e->qXE, e->F("conan.vq.embedding"), e->F("conan.vq.e2"), e->F("conan.pos_table"), e->qZC, e->qVQ,
                            n, Tp, H, c.n_vq, st));
-    auto l1 = conv_on_rows(e, e->qZC, Tp, 0, Tp, 2 * H, e->P("conan.l1.w"), e->F("conan.l1.b"), H, n, nullptr);
+    auto l1 = conv_on_rows(e, e->qZC, Tp, 0, Tp, 2 * H, e->P("conan.l1.w"), e->F("conan.l1.b"), H, n);
     l1.n_slots = n; out_rows(l1, e->qPE, Tp, H);
     TRY(run_conv(e, l1, st));
     TRY(launch_kpm(e->qPE, e->sKPM, e->sNKEYS, e->qSlots, n, Tp, H, e->tp_max, st));
     for (int l = 0; l < 2; ++l) {
       std::string a = "conan.align." + std::to_string(l) + ".";
-      auto kv = conv_on_rows(e, e->qPE, Tp, 0, Tp, H, e->P(a + "kv.w"), e->F(a + "kv.b"), 2 * H, n, nullptr);
+      auto kv = conv_on_rows(e, e->qPE, Tp, 0, Tp, H, e->P(a + "kv.w"), e->F(a + "kv.b"), 2 * H, n);
       kv.n_slots = n; out_rows(kv, e->qKVs, Tp, 2 * H);
       TRY(run_conv(e, kv, st));
       TRY(launch_scatter_kv(e->qKVs, e->sKV, e->qSlots, n, Tp, 2 * H, l, 2, e->tp_max, st));
@@ -865,7 +879,7 @@ int conan_debug_read(conan_engine_t* e, const char* name, int slot, float* out_d
   else if (nm == "kv_cache") { cnt = (size_t)2 * e->tp_max * 2 * c.hidden_size; src = e->sKV + (size_t)slot * cnt; }
   else if (nm == "kpm") { cnt = e->tp_max; src = e->sKPM + (size_t)slot * cnt; }
   else if (nm == "emformer_past_len") { cnt = 1; src = e->ePast + slot; }
-  else if (nm == "uv_pred") { cnt = (size_t)c.segment * 4; src = e->dUVP + (size_t)slot * cnt; }
+  else if (nm == "uv_pred") { cnt = (size_t)c.segment * 4; src = e->dUVP + (size_t)slot * cnt; }   // `slot` = index in the last ready list
   else if (nm == "vq_index") { cnt = e->tp_max; src = e->qVQ; }   // compact index 0 of the last session batch
   else { set_error("unknown debug tensor '" + nm + "'"); return 1; }
   if (numel) *numel = cnt;

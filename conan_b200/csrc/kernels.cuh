@@ -33,11 +33,13 @@ int launch_layernorm(const LnArgs& a, cudaStream_t st);
 // Emformer ------------------------------------------------------------------------------
 // chunk [n, seg+rc, D] (utterance rows first) -> X[slot] rows ordered [rc | utt] (TA:430)
 int launch_emformer_assemble(const float* chunk, float* X, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st);
-// per stream: append utterance K/V rows to the ring, softmax(QK^T) V over [rc | left ctx | utt]
+// per stream: append utterance K/V rows to the ring, softmax(QK^T) V over [rc | left ctx | utt].
+// qkv / att are compact (index i, row stride ld); kv_ring / past_len are resident state indexed by slot_ids[i].
 int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, float* att, int n,
-                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, cudaStream_t st);
+                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv, int ld_att,
+                              cudaStream_t st);
 int launch_advance_past_len(int* past_len, int n, const int* slot_ids, int seg, cudaStream_t st);
-int launch_argmax_rows(const float* logits, int* tokens_slot, int* tokens_out, int n, const int* slot_ids, int rows, int C, cudaStream_t st);
+int launch_argmax_rows(const float* logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C, cudaStream_t st);
 int launch_copy_rows_out(const float* src_slot, long long slot_stride, int row_stride, int row0, float* dst, int n,
                          const int* slot_ids, int rows, int C, cudaStream_t st);
 int launch_copy_rows_in(const void* src, int src_is_int, void* dst_slot, long long slot_stride_elems, int n,
@@ -47,6 +49,7 @@ int launch_copy_rows_in(const void* src, int src_is_int, void* dst_slot, long lo
 int launch_embedding_rows(const int* tokens_slot, const float* table, int vocab, RowView out, int n, const int* slot_ids,
                           int rows, int C, cudaStream_t st);
 // nn.MultiheadAttention(256, 2) over the session-cached K/V (prosody_util.py:108-127)
+// q / out compact; kv_cache, kpm, n_keys are session state indexed by slot_ids[i]
 int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, float* out, int n,
                            const int* slot_ids, int rows, int H, int heads, int layer, int n_layers, int tp_max, cudaStream_t st);
 // out1 = a + b (fp32), optional second copy into a context buffer
@@ -64,9 +67,12 @@ int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, i
                           const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st);
 
 // state maintenance --------------------------------------------------------------------------
-struct RingDesc { void* base; long long slot_stride_bytes; int hist_bytes; int new_bytes; };
-// for every listed ring and active slot: move the last hist_bytes of [hist | new] to the front
-int launch_ring_shift(const RingDesc* rings_dev, int n_rings, int max_hist_bytes, int n, const int* slot_ids, cudaStream_t st);
+// Resident history of a context buffer lives per slot in `hist` [slot, hist_bytes]; the step works on a compact
+// buffer `work` [i, hist_bytes + new_bytes].  gather: hist[slot_i] -> work[i][0 : hist);  scatter: the last
+// hist_bytes of work[i] -> hist[slot_i].  scatter_back = 0 marks read-only session state (style vector).
+struct HistDesc { void* work; long long work_stride_bytes; void* hist; int hist_bytes; int new_bytes; int scatter_back; };
+int launch_hist_gather(const HistDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st);
+int launch_hist_scatter(const HistDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st);
 struct ZeroDesc { void* base; long long slot_stride_bytes; long long bytes; };
 int launch_zero_slots(const ZeroDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st);
 

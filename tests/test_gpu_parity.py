@@ -135,13 +135,13 @@ def test_conv_gemm_tcgen05_vs_ffma_and_torch(cin, cout, k, dil, L, S):
     w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).half()
     b = torch.randn(cout, generator=g)
     res = torch.randn(nslots, L, cout, generator=g)
-    ids = torch.randperm(nslots, generator=g)[:S].to(torch.int32)
+    ids = torch.arange(S, dtype=torch.int32)        # the tcgen05 engine works on compact operands: streams 0..S-1 of S+2 rows
     ref = _conv_reference(ctx.double(), w.double(), b.double(), k, dil, L, 2) + res.double()
     outs = {}
     for name, engine in (("ffma", ops.ENGINE_FFMA), ("tc", ops.ENGINE_TC)):
         y = torch.zeros(nslots, L, cout, device="cuda")
         y2 = torch.zeros(nslots, 4 + L, cout, device="cuda", dtype=torch.float16)
-        ops.conv_gemm(ctx.cuda(), pack_conv(w).cuda(), b.cuda(), k=k, dil=dil, L=L, row0=2, slot_ids=ids.cuda(), engine=engine,
+        ops.conv_gemm(ctx.cuda(), pack_conv(w).cuda(), b.cuda(), k=k, dil=dil, L=L, row0=2, n_streams=S, engine=engine,
                       res=res.cuda(), y=y, y2=y2, y2_row0=4, act2="lrelu", slope2=0.1)
         torch.cuda.synchronize()
         outs[name] = (y.cpu(), y2.cpu())
@@ -270,7 +270,7 @@ def test_decoder_step_vs_oracle_teacher_forced(state_dicts, eng_fp32):
             mel = eng.decoder_step(ids, tk.to(torch.int32).contiguous().cuda())
             worst = max(worst, (mel.cpu() - mel_ref).abs().max().item())
             for i, s in enumerate(slots):
-                uvp = eng.debug_read("uv_pred", s).cpu().view(4, 4)
+                uvp = eng.debug_read("uv_pred", i).cpu().view(4, 4)      # scratch is compact: index in the ready list
                 assert (uvp[:, 3].long() == dbg["pitch"][i]).all(), "f0 bucket mismatch"
                 buckets.update(dbg["pitch"][i].tolist())
     print("decoder mel max-abs", worst, "distinct f0 buckets", len(buckets))
