@@ -25,8 +25,8 @@ constexpr int EMF_MAX_HD = 16;
 
 __global__ void __launch_bounds__(256)
 emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ ring, const int* __restrict__ past_len,
-                          float* __restrict__ att, const int* __restrict__ slot_ids, int seg, int rc, int lc,
-                          int ring_rows, int D, int heads, int ldq, int lda) {
+                          RowView att, const int* __restrict__ slot_ids, int seg, int rc, int lc,
+                          int ring_rows, int D, int heads, int ldq) {
   extern __shared__ float sm[];
   const int rows = seg + rc;
   const int slot = slot_of(slot_ids, blockIdx.x);
@@ -116,7 +116,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
       for (int d = 0; d < EMF_MAX_HD; ++d) {
         if (d < hd) {
           float v = warp_sum(o[d]);
-          if (lane == 0) att[((long long)blockIdx.x * rows + qr) * lda + h * hd + d] = v;
+          if (lane == 0) store_view(att, (long long)blockIdx.x * att.slot_stride + (long long)qr * att.row_stride + h * hd + d, v);
         }
       }
     }
@@ -131,7 +131,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ cache, const float* __restrict__ kpm,
-                       const int* __restrict__ n_keys, float* __restrict__ out, const int* __restrict__ slot_ids, int rows,
+                       const int* __restrict__ n_keys, RowView out, const int* __restrict__ slot_ids, int rows,
                        int H, int heads, int layer, int n_layers, int tp_max) {
   extern __shared__ float sc[];                      // [rows][tp_max]
   const int slot = slot_of(slot_ids, blockIdx.x), h = blockIdx.y;
@@ -168,15 +168,15 @@ cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ ca
       const float* vr = kv + (long long)key * 2 * H + H + h * hd;
       for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) o[j] = fmaf(p, vr[d], o[j]); }
     }
-    float* orow = out + ((long long)blockIdx.x * rows + r) * H + h * hd;
-    for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) orow[d] = o[j]; }
+    const long long orow = (long long)blockIdx.x * out.slot_stride + (long long)r * out.row_stride + h * hd;
+    for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) store_view(out, orow + d, o[j]); }
   }
 }
 
 }  // namespace
 
-int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, float* att, int n,
-                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv, int ld_att,
+int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, RowView att, int n,
+                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv,
                               cudaStream_t st) {
   if (n <= 0) return 0;
   if (rc + lc + seg > EMF_MAX_KEYS || D / heads > EMF_MAX_HD) { set_error("emformer_attention: key count or head_dim above compiled limits"); return 1; }
@@ -185,12 +185,12 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; }
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }
-  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv, ld_att);
+  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, float* out, int n,
+int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, RowView out, int n,
                            const int* slot_ids, int rows, int H, int heads, int layer, int n_layers, int tp_max, cudaStream_t st) {
   if (n <= 0) return 0;
   if (H / heads > 128) { set_error("cross_attention: head_dim above 128"); return 1; }

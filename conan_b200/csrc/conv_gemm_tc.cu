@@ -41,12 +41,15 @@ struct TcEpi {
   const float* rowmask; int mask_slot_stride; float out_scale;
   float* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
   __half* y2; long long y2_slot_stride; int y2_row_stride, y2_row0; int act2; float slope2;
+  float acc_scale; long long y2_lo_off;      // y2_lo_off != 0: y2 is a split fp16 pair (hi, lo = fp16(v - hi))
 };
 
 struct TcArgs {
   int n_streams, L, TT, cin, k, dil, cout, row0;
-  int kblocks;               // k * cin / BK
+  int kblocks;               // nseg * k * cin / BK
   int n_tiles;               // cout / BN
+  int nseg;                  // 1, or 3 for split operands: K' = [x_hi*W_hi | x_hi*W_lo | x_lo*W_hi]
+  int lo_slot_off;           // slot offset of the lo plane of a split x
   TcEpi e;
 };
 
@@ -136,6 +139,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane
   float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
   __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
   const bool acc_old = e.accumulate && yp;
+  const bool gelu = e.act == ACT_GELU;
   const float s1 = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.slope);
   const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);
   const float f = rm * e.out_scale;
@@ -161,8 +165,9 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane
       const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        float x = (__uint_as_float(acc[4 * i + u]) + bb[u]) * e.scale;
-        x = x > 0.f ? x : x * s1;
+        float x = fmaf(__uint_as_float(acc[4 * i + u]), e.acc_scale, bb[u]) * e.scale;
+        if (gelu) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));     // warp-uniform branch (exact-erf GELU)
+        else x = x > 0.f ? x : x * s1;
         v[4 * i + u] = (x + rr[u]) * f;
       }
     }
@@ -177,13 +182,17 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane
     if (y2p) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        __half2 h[4];
+        __half2 h[4], l[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float x0 = v[8 * i + 2 * u], x1 = v[8 * i + 2 * u + 1];
-          h[u] = __floats2half2_rn(x0 > 0.f ? x0 : x0 * s2, x1 > 0.f ? x1 : x1 * s2);
+          float x0 = v[8 * i + 2 * u], x1 = v[8 * i + 2 * u + 1];
+          x0 = x0 > 0.f ? x0 : x0 * s2; x1 = x1 > 0.f ? x1 : x1 * s2;
+          h[u] = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h[u]);
+          l[u] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
         }
         *(reinterpret_cast<uint4*>(y2p + c0) + i) = *reinterpret_cast<uint4*>(h);
+        if (e.y2_lo_off) *(reinterpret_cast<uint4*>(y2p + e.y2_lo_off + c0) + i) = *reinterpret_cast<uint4*>(l);
       }
     }
 #pragma unroll
@@ -238,6 +247,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================================================== TMA producer
     if (lane == 0) {
       const int kb_per_tap = a.cin / BK;
+      const int kb_per_seg = a.kblocks / a.nseg;
       for (int kb = 0; kb < a.kblocks; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -245,8 +255,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* sa = smem + s * SL::STAGE_BYTES;
         uint8_t* sb = sa + SL::A_BYTES;
         mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
-        const int j = kb / kb_per_tap, c0 = (kb - j * kb_per_tap) * BK;
-        tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0);     // box {BK, TT, NS}
+        const int seg = kb / kb_per_seg, kbl = kb - seg * kb_per_seg;
+        const int j = kbl / kb_per_tap, c0 = (kbl - j * kb_per_tap) * BK;
+        tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
         tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
       }
     }
@@ -479,7 +490,7 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, unsigned long lo
 }
 
 int pick_tt(int L) {
-  for (int tt = 128; tt >= 4; tt >>= 1)
+  for (int tt = 128; tt >= 1; tt >>= 1)
     if (L % tt == 0) return tt;
   return 0;
 }
@@ -524,7 +535,7 @@ size_t window_smem_bytes(const conan_conv_params_t& p) {
 }
 
 bool window_eligible(const conan_conv_params_t& p) {
-  if (window_mode() == 0) return false;
+  if (window_mode() == 0 || p.x_split) return false;
   if (p.L % TILE_M != 0) return false;
   if (!((p.cin == 32 && p.cout == 32) || (p.cin == 64 && p.cout == 64))) return false;
   if (TILE_M + (p.k - 1) * p.dil > 256) return false;
@@ -558,7 +569,7 @@ int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
   a.tiles_per_stream = p.L / TILE_M; a.num_tiles = p.n_streams * a.tiles_per_stream;
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
-              p.y2_row_stride, p.y2_row0, p.act2, p.slope2};
+              p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0};
   const size_t smem = window_smem_bytes(p);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > 4) per_sm = 4;
@@ -581,7 +592,8 @@ bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
   if (p.cin % 32 != 0 || p.x_row_stride != p.cin) return false;
   if (pick_bn(p.cout) == 0 || pick_tt(p.L) == 0) return false;
   if (p.row0 < 0) return false;
-  if (p.act > ACT_LRELU || p.act2 > ACT_LRELU) return false;          // none / relu / leaky only on this engine
+  if (p.act == ACT_TANH || p.act2 > ACT_LRELU) return false;          // none / relu / leaky / gelu (first), none / relu / leaky (second)
+  if (p.y2_split && (!p.y2 || p.y2_lo_off % 8)) return false;
   if (p.y && (p.y_slot_stride % 4 || p.y_row_stride % 4)) return false;
   if (p.res && (p.res_slot_stride % 4 || p.res_row_stride % 4)) return false;
   if (p.y2 && (p.y2_slot_stride % 8 || p.y2_row_stride % 8)) return false;
@@ -596,9 +608,11 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   const int BK = (p.cin % 64 == 0) ? 64 : 32;
   const int BN = pick_bn(p.cout);
   const int TT = pick_tt(p.L);
-  const int Ktot = p.k * p.cin;
+  const int nseg = p.x_split ? 3 : 1;
+  const int Ktot = nseg * p.k * p.cin;
   CUtensorMap tmA, tmW;
-  if (get_tensor_map(&tmA, p.x, 3, (unsigned long long)p.cin, (unsigned long long)p.x_rows, (unsigned long long)p.n_slots,
+  if (get_tensor_map(&tmA, p.x, 3, (unsigned long long)p.cin, (unsigned long long)p.x_rows,
+                     (unsigned long long)(p.x_split ? p.x_lo_slot_off + p.n_slots : p.n_slots),
                      (unsigned long long)p.x_row_stride * 2, (unsigned long long)p.x_slot_stride * 2, BK, TT, TILE_M / TT, BK * 2))
     return 1;
   if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, BN, 1,
@@ -606,10 +620,10 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
     return 1;
   TcArgs a;
   a.n_streams = p.n_streams; a.L = p.L; a.TT = TT; a.cin = p.cin; a.k = p.k; a.dil = p.dil; a.cout = p.cout; a.row0 = p.row0;
-  a.kblocks = Ktot / BK; a.n_tiles = p.cout / BN;
+  a.kblocks = Ktot / BK; a.n_tiles = p.cout / BN; a.nseg = nseg; a.lo_slot_off = (int)p.x_lo_slot_off;
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
-              p.y2_row_stride, p.y2_row0, p.act2, p.slope2};
+              p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0};
   const int NS = TILE_M / TT;
   const long long m_tiles = (long long)((p.n_streams + NS - 1) / NS) * (p.L / TT);
   if (BK == 64) {

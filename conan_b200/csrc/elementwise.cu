@@ -39,15 +39,16 @@ __global__ void layernorm_kernel(LnArgs a) {
   float rstd = 1.f / sqrtf(q / a.C + a.eps);
   float post = a.postmask ? a.postmask[(long long)slot * a.postmask_slot_stride + t] : 1.f;
   long long o = (long long)slot * a.out.slot_stride + (long long)(a.out.row0 + t) * a.out.row_stride;
+  long long o2 = (long long)slot * a.out2.slot_stride + (long long)(a.out2.row0 + t) * a.out2.row_stride;
   for (int c = lane; c < a.C; c += 32) {
     float y = ((x[c] * pm - mean) * rstd * a.gamma[c] + a.beta[c]) * post;
-    if (a.out.is_half) reinterpret_cast<__half*>(a.out.base)[o + c] = __float2half_rn(y);
-    else reinterpret_cast<float*>(a.out.base)[o + c] = y;
+    store_view(a.out, o + c, y);
+    if (a.out2.base) store_view(a.out2, o2 + c, y);
   }
 }
 
 // ------------------------------------------------------------------ Emformer chunk assembly
-__global__ void emformer_assemble_kernel(const float* __restrict__ chunk, float* __restrict__ X, int n,
+__global__ void emformer_assemble_kernel(const float* __restrict__ chunk, float* __restrict__ X, int ldx, int n,
                                          const int* __restrict__ slot_ids, int seg, int rc, int D) {
   int rows = seg + rc;
   long long total = (long long)n * rows * D;
@@ -55,7 +56,7 @@ __global__ void emformer_assemble_kernel(const float* __restrict__ chunk, float*
     int c = idx % D; long long r = idx / D; int row = r % rows; int i = r / rows;
     // internal order [rc | utt]: internal row q <- chunk row (q < rc ? seg + q : q - rc)
     int src = row < rc ? seg + row : row - rc;
-    X[((long long)slot_of(slot_ids, i) * rows + row) * D + c] = chunk[((long long)i * rows + src) * D + c];
+    X[((long long)slot_of(slot_ids, i) * rows + row) * ldx + c] = chunk[((long long)i * rows + src) * D + c];
   }
 }
 
@@ -105,8 +106,7 @@ __global__ void embedding_rows_kernel(const int* __restrict__ tokens_slot, const
     int slot = slot_of(slot_ids, i);
     int tok = tokens_slot[slot * rows + t];
     tok = min(max(tok, 0), vocab - 1);
-    reinterpret_cast<float*>(out.base)[(long long)slot * out.slot_stride + (long long)(out.row0 + t) * out.row_stride + c] =
-        table[(long long)tok * C + c];
+    store_view(out, (long long)slot * out.slot_stride + (long long)(out.row0 + t) * out.row_stride + c, table[(long long)tok * C + c]);
   }
 }
 
@@ -119,8 +119,7 @@ __global__ void add_rows_kernel(const float* __restrict__ a, const float* __rest
     long long o = ((long long)slot * rows + t) * C + c;
     float v = a[o] + b[o];
     if (out1) out1[o] = v;
-    if (out2.base)
-      reinterpret_cast<float*>(out2.base)[(long long)slot * out2.slot_stride + (long long)(out2.row0 + t) * out2.row_stride + c] = v;
+    if (out2.base) store_view(out2, (long long)slot * out2.slot_stride + (long long)(out2.row0 + t) * out2.row_stride + c, v);
   }
 }
 
@@ -130,9 +129,7 @@ __global__ void rows_to_view_kernel(const float* __restrict__ src, RowView out, 
     int c = idx % C; long long r = idx / C; int t = r % rows; int i = r / rows;
     int slot = slot_of(slot_ids, i);
     float v = src[((long long)slot * rows + t) * C + c];
-    long long o = (long long)slot * out.slot_stride + (long long)(out.row0 + t) * out.row_stride + c;
-    if (out.is_half) reinterpret_cast<__half*>(out.base)[o] = __float2half_rn(v);
-    else reinterpret_cast<float*>(out.base)[o] = v;
+    store_view(out, (long long)slot * out.slot_stride + (long long)(out.row0 + t) * out.row_stride + c, v);
   }
 }
 
@@ -379,9 +376,9 @@ int launch_layernorm(const LnArgs& a, cudaStream_t st) {
   return 0;
 }
 
-int launch_emformer_assemble(const float* chunk, float* X, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st) {
+int launch_emformer_assemble(const float* chunk, float* X, int ldx, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st) {
   if (n <= 0) return 0;
-  emformer_assemble_kernel<<<grid_for((long long)n * (seg + rc) * D, 256), 256, 0, st>>>(chunk, X, n, slot_ids, seg, rc, D);
+  emformer_assemble_kernel<<<grid_for((long long)n * (seg + rc) * D, 256), 256, 0, st>>>(chunk, X, ldx, n, slot_ids, seg, rc, D);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

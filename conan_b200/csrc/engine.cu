@@ -31,11 +31,14 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 struct Ctx {                 // compact context buffer [i, H + L + R, C]; resident history [slot, H, C]
   void* p = nullptr;
   void* hist = nullptr;
-  int H = 0, L = 0, R = 0, C = 0, is_half = 0;
+  int H = 0, L = 0, R = 0, C = 0;
+  int is_half = 0;           // 0 fp32, 1 fp16, 2 split fp16 pair (two planes: hi, lo)
+  long long plane = 0;       // elements between the hi and the lo plane of a split buffer
+  long long hist_plane = 0;
   int rows() const { return H + L + R; }
   long long slot_stride() const { return (long long)rows() * C; }
   size_t elem() const { return is_half ? 2 : 4; }
-  RowView new_rows() const { return RowView{p, slot_stride(), C, H, is_half}; }
+  RowView new_rows() const { return RowView{p, slot_stride(), C, H, is_half, plane}; }
   void* at_row(int r) const { return (char*)p + (size_t)r * C * elem(); }
 };
 
@@ -53,17 +56,20 @@ struct conan_engine {
   std::vector<void*> allocs;
   size_t state_bytes = 0;
   int S = 0, tp_max = 0;
+  bool lin_tc = false;       // Emformer / Conan contractions on tcgen05 with split-fp16 operands
+  int DP = 0, QP = 0, LP = 0;   // (padded) Emformer model dim, QKV width, logits width
   // ---- Emformer
   int ring_rows = 0;
-  float *eX = nullptr, *eXN = nullptr, *eQKV = nullptr, *eATT = nullptr, *eR1 = nullptr, *eFN = nullptr, *eHF = nullptr,
-        *eR2 = nullptr, *eLOG = nullptr;
+  float *eX = nullptr, *eQKV = nullptr, *eR1 = nullptr, *eR2 = nullptr, *eLOG = nullptr;
+  Ctx eXN, eATT, eFN, eHF;   // GEMM operands (fp32 or split fp16)
   std::vector<float*> eRing;
   int* ePast = nullptr;
   int* TOK = nullptr;
   // ---- Conan chunk path
   Ctx cC, cUV[5], cD[8][2], cP;
-  float *dX0 = nullptr, *dQ = nullptr, *dATT = nullptr, *dT1 = nullptr, *dO1 = nullptr, *dHF = nullptr, *dT2 = nullptr,
-        *dPROS[2] = {nullptr, nullptr}, *dPINP = nullptr, *dUVH = nullptr, *dDECX = nullptr, *dDECH = nullptr, *dPOST = nullptr,
+  Ctx cX0, cATT, cO1, cHF, cPROS[2], cDECH;     // GEMM operands without history (fp32 or split fp16)
+  float *dX0 = nullptr, *dQ = nullptr, *dT1 = nullptr, *dO1 = nullptr, *dT2 = nullptr,
+        *dPROS[2] = {nullptr, nullptr}, *dPINP = nullptr, *dUVH = nullptr, *dDECX = nullptr, *dPOST = nullptr,
         *dMEL = nullptr, *dUVP = nullptr, *dMASK0 = nullptr, *dMASKB = nullptr;
   float *sSTYLE = nullptr, *sKV = nullptr, *sKPM = nullptr;
   int* sNKEYS = nullptr;
@@ -108,37 +114,48 @@ void need(conan_engine* e, const std::string& name, size_t numel, int dtype = CO
   e->weights.push_back(WeightSlot{name, numel, dtype, nullptr});
 }
 
+inline int pad32(int x) { return (x + 31) / 32 * 32; }
+
+// A contraction that runs on the tensor cores when lin_tc is on: fp16 [Npad, 3*k*Kpad] = [W_hi | W_lo | W_hi]
+// (pre-scaled by 2^10) + fp32 bias [Npad]; otherwise fp32 [N, k*K] + bias [N].
+void need_linear(conan_engine* e, const std::string& name, int N, int K, int k = 1) {
+  if (e->lin_tc) {
+    need(e, name + ".w", (size_t)pad32(N) * 3 * k * pad32(K), CONAN_DTYPE_F16);
+    need(e, name + ".b", pad32(N));
+  } else {
+    need(e, name + ".w", (size_t)N * k * K);
+    need(e, name + ".b", N);
+  }
+}
+
 void declare_weights(conan_engine* e) {
   const conan_config_t& c = e->cfg;
   const int D = c.emformer_dim, F = c.emformer_ffn, H = c.hidden_size;
   for (int l = 0; l < c.emformer_layers; ++l) {
     std::string p = "emf." + std::to_string(l) + ".";
     need(e, p + "ln_in.g", D); need(e, p + "ln_in.b", D);
-    need(e, p + "qkv.w", (size_t)3 * D * D); need(e, p + "qkv.b", 3 * D);
-    need(e, p + "out.w", (size_t)D * D); need(e, p + "out.b", D);
+    need_linear(e, p + "qkv", 3 * D, D);
+    need_linear(e, p + "out", D, D);
     need(e, p + "ffn_ln.g", D); need(e, p + "ffn_ln.b", D);
-    need(e, p + "ffn1.w", (size_t)F * D); need(e, p + "ffn1.b", F);
-    need(e, p + "ffn2.w", (size_t)D * F); need(e, p + "ffn2.b", D);
+    need_linear(e, p + "ffn1", F, D);
+    need_linear(e, p + "ffn2", D, F);
     need(e, p + "ln_out.g", D); need(e, p + "ln_out.b", D);
   }
-  need(e, "emf.proj.w", (size_t)c.emformer_output_dim * D); need(e, "emf.proj.b", c.emformer_output_dim);
+  need_linear(e, "emf.proj", c.emformer_output_dim, D);
 
   need(e, "conan.content_embedding", (size_t)102 * H);
-  need(e, "conan.content_proj.w", (size_t)H * c.content_kernel * H); need(e, "conan.content_proj.b", H);
+  need_linear(e, "conan.content_proj", H, H, c.content_kernel);
   for (int l = 0; l < 2; ++l) {
     std::string p = "conan.align." + std::to_string(l) + ".";
-    need(e, p + "q.w", (size_t)H * H); need(e, p + "q.b", H);
-    need(e, p + "kv.w", (size_t)2 * H * H); need(e, p + "kv.b", 2 * H);
-    need(e, p + "out.w", (size_t)H * H); need(e, p + "out.b", H);
+    need_linear(e, p + "q", H, H);
+    need(e, p + "kv.w", (size_t)2 * H * H); need(e, p + "kv.b", 2 * H);          // session setup: fp32
+    need_linear(e, p + "out", H, H);
     need(e, p + "norm1.g", H); need(e, p + "norm1.b", H);
-    need(e, p + "ffn1.w", (size_t)2048 * H); need(e, p + "ffn1.b", 2048);
-    need(e, p + "ffn2.w", (size_t)H * 2048); need(e, p + "ffn2.b", H);
+    need_linear(e, p + "ffn1", 2048, H);
+    need_linear(e, p + "ffn2", H, 2048);
     need(e, p + "norm2.g", H); need(e, p + "norm2.b", H);
   }
-  for (int i = 0; i < 5; ++i) {
-    std::string p = "conan.uv." + std::to_string(i) + ".";
-    need(e, p + "w", (size_t)128 * c.predictor_kernel * (i == 0 ? H : 128)); need(e, p + "b", 128);
-  }
+  for (int i = 0; i < 5; ++i) need_linear(e, "conan.uv." + std::to_string(i), 128, i == 0 ? H : 128, c.predictor_kernel);
   need(e, "conan.uv.ln.g", 128); need(e, "conan.uv.ln.b", 128);
   need(e, "conan.uv.lin.w", 256); need(e, "conan.uv.lin.b", 2);
   need(e, "conan.pitch_embed", (size_t)300 * H);
@@ -146,11 +163,11 @@ void declare_weights(conan_engine* e) {
     for (int s = 0; s < 2; ++s) {
       std::string p = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
       need(e, p + "ln.g", H); need(e, p + "ln.b", H);
-      need(e, p + "conv.w", (size_t)2 * H * c.dec_kernel * H); need(e, p + "conv.b", 2 * H);
-      need(e, p + "pw.w", (size_t)H * 2 * H); need(e, p + "pw.b", H);
+      need_linear(e, p + "conv", 2 * H, H, c.dec_kernel);
+      need_linear(e, p + "pw", H, 2 * H);
     }
   need(e, "conan.dec.last_norm.g", H); need(e, "conan.dec.last_norm.b", H);
-  need(e, "conan.dec.post.w", (size_t)H * c.dec_post_kernel * H); need(e, "conan.dec.post.b", H);
+  need_linear(e, "conan.dec.post", H, H, c.dec_post_kernel);
   need(e, "conan.mel_out.w", (size_t)c.n_mels * H); need(e, "conan.mel_out.b", c.n_mels);
   // session-setup branch
   need(e, "conan.global_in.w", (size_t)H * c.n_mels); need(e, "conan.global_in.b", H);
@@ -213,10 +230,13 @@ int dalloc(conan_engine* e, T** out, size_t count) {
   return 0;
 }
 
-int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half, bool resident = true) {
+// is_half: 0 fp32, 1 fp16, 2 split fp16 pair
+int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half) {
   c->H = H; c->L = L; c->R = R; c->C = C; c->is_half = is_half;
-  size_t count = (size_t)e->S * c->rows() * C;           // compact work buffer (up to max_slots streams per step)
-  size_t hcount = (resident && H > 0) ? (size_t)e->S * H * C : 0;
+  const int planes = is_half == 2 ? 2 : 1;
+  c->plane = (long long)e->S * c->rows() * C;            // compact work buffer (up to max_slots streams per step)
+  c->hist_plane = (long long)e->S * H * C;
+  size_t count = (size_t)planes * c->plane, hcount = (size_t)planes * c->hist_plane;
   if (is_half) {
     __half* p; if (dalloc(e, &p, count)) return 1; c->p = p;
     if (hcount) { __half* h; if (dalloc(e, &h, hcount)) return 1; c->hist = h; }
@@ -227,16 +247,19 @@ int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half, 
   return 0;
 }
 
+constexpr float kSplitWeightScale = 1024.f;      // split weights are packed as 2^10 * W (keeps W_lo out of the fp16 subnormals)
+
 // ---- conv parameter builders (all compact: stream i of the ready list, no slot indirection) -----
 conan_conv_params_t conv_on_ctx(const conan_engine* e, const Ctx& in, int k, int dil, const void* w, const float* bias,
-                                int cout, int n, bool causal = true) {
+                                int cout, int n, bool causal = true, int row0_extra = 0, int L = -1) {
   conan_conv_params_t p;
   memset(&p, 0, sizeof(p));
-  p.x = in.p; p.x_slot_stride = in.slot_stride(); p.x_row_stride = in.C; p.x_rows = in.rows(); p.x_is_half = in.is_half;
-  p.row0 = causal ? in.H - (k - 1) * dil : in.H - ((k - 1) * dil) / 2;
-  p.L = in.L; p.cin = in.C; p.k = k; p.dil = dil; p.cout = cout; p.w = w; p.bias = bias;
+  p.x = in.p; p.x_slot_stride = in.slot_stride(); p.x_row_stride = in.C; p.x_rows = in.rows(); p.x_is_half = in.is_half ? 1 : 0;
+  p.row0 = (causal ? in.H - (k - 1) * dil : in.H - ((k - 1) * dil) / 2) + row0_extra;
+  p.L = L < 0 ? in.L : L; p.cin = in.C; p.k = k; p.dil = dil; p.cout = cout; p.w = w; p.bias = bias;
   p.n_streams = n; p.slot_ids = nullptr; p.n_slots = e->S;
   p.scale = 1.f; p.out_scale = 1.f;
+  if (in.is_half == 2) { p.x_split = 1; p.x_lo_slot_off = e->S; p.acc_scale = 1.f / kSplitWeightScale; }
   return p;
 }
 conan_conv_params_t conv_on_rows(const conan_engine* e, const float* x, int rows_per_slot, int row0, int L, int C,
@@ -254,13 +277,15 @@ void out_ctx(conan_conv_params_t& p, const Ctx& c) {     // fp32 context buffer 
   p.y = (float*)c.p; p.y_slot_stride = c.slot_stride(); p.y_row_stride = c.C; p.y_row0 = c.H;
 }
 void out2_ctx(conan_conv_params_t& p, const Ctx& c, int act2, float slope2) {
-  p.y2 = c.p; p.y2_slot_stride = c.slot_stride(); p.y2_row_stride = c.C; p.y2_row0 = c.H; p.y2_is_half = c.is_half;
+  p.y2 = c.p; p.y2_slot_stride = c.slot_stride(); p.y2_row_stride = c.C; p.y2_row0 = c.H; p.y2_is_half = c.is_half ? 1 : 0;
   p.act2 = act2; p.slope2 = slope2;
+  if (c.is_half == 2) { p.y2_split = 1; p.y2_lo_off = c.plane; }
 }
 void res_rows(conan_conv_params_t& p, const float* r, int L, int C) { p.res = r; p.res_slot_stride = (long long)L * C; p.res_row_stride = C; }
 
 int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t st, bool allow_tc = false) {
-  const bool tc = allow_tc && e->cfg.voc_use_tensor_cores && conv_gemm_tc_eligible(p);
+  const bool tc = allow_tc && conv_gemm_tc_eligible(p);
+  if (p.x_split && !tc) { set_error("internal: split-fp16 operand on a shape the tcgen05 engine cannot run"); return 1; }
   if (!e->profiling) return tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
   conan_engine::ProfRec r;
   r.cat = tc ? 1 : 0;
@@ -273,12 +298,12 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
   return rc;
 }
 
-int ln_rows(const float* in, int in_rows, int in_row0, RowView out, const float* g, const float* b, int C, int L, int n,
+int ln_rows(const float* in, int in_rows, int in_ld, int in_row0, RowView out, const float* g, const float* b, int C, int L, int n,
             cudaStream_t st, const float* premask = nullptr, const float* postmask = nullptr, int mask_stride = 0,
-            float* write_mask = nullptr, float* write_mask2 = nullptr) {
+            float* write_mask = nullptr, float* write_mask2 = nullptr, RowView out2 = RowView{}) {
   LnArgs a;
-  a.in = RowView{(void*)in, (long long)in_rows * C, C, in_row0, 0};
-  a.out = out; a.gamma = g; a.beta = b; a.eps = 1e-5f; a.C = C; a.L = L; a.n = n; a.slot_ids = nullptr;
+  a.in = RowView{(void*)in, (long long)in_rows * in_ld, in_ld, in_row0, 0, 0};
+  a.out = out; a.out2 = out2; a.gamma = g; a.beta = b; a.eps = 1e-5f; a.C = C; a.L = L; a.n = n; a.slot_ids = nullptr;
   a.premask = premask; a.premask_slot_stride = mask_stride;
   a.postmask = postmask; a.postmask_slot_stride = mask_stride;
   a.write_mask = write_mask; a.write_mask_slot_stride = mask_stride; a.write_mask2 = write_mask2;
@@ -291,29 +316,37 @@ int ln_rows(const float* in, int in_rows, int in_row0, RowView out, const float*
 int allocate_state(conan_engine* e) {
   const conan_config_t& c = e->cfg;
   const int S = e->S, D = c.emformer_dim, H = c.hidden_size, seg = c.segment, rows = c.segment + c.right_context;
-  // ---- Emformer (scratch compact, K|V ring + past_len resident)
+  // ---- Emformer (scratch compact, K|V ring + past_len resident).  GEMM operands are fp32 rows (FFMA mode) or
+  // split-fp16 pairs with the model dim padded to a multiple of 32 (tensor-core mode); pad columns stay zero.
+  const int lt = e->lin_tc ? 2 : 0;
+  e->DP = e->lin_tc ? pad32(D) : D; e->QP = e->lin_tc ? pad32(3 * D) : 3 * D;
+  e->LP = e->lin_tc ? pad32(c.emformer_output_dim) : c.emformer_output_dim;
+  const int DP = e->DP;
   e->ring_rows = ((c.left_context + seg + seg - 1) / seg) * seg;      // >= lc + seg, multiple of seg
-  TRY(dalloc(e, &e->eX, (size_t)S * rows * D)); TRY(dalloc(e, &e->eXN, (size_t)S * rows * D));
-  TRY(dalloc(e, &e->eQKV, (size_t)S * rows * 3 * D)); TRY(dalloc(e, &e->eATT, (size_t)S * rows * D));
-  TRY(dalloc(e, &e->eR1, (size_t)S * rows * D)); TRY(dalloc(e, &e->eFN, (size_t)S * rows * D));
-  TRY(dalloc(e, &e->eHF, (size_t)S * rows * c.emformer_ffn)); TRY(dalloc(e, &e->eR2, (size_t)S * rows * D));
-  TRY(dalloc(e, &e->eLOG, (size_t)S * seg * c.emformer_output_dim));
+  TRY(dalloc(e, &e->eX, (size_t)S * rows * DP)); TRY(dalloc(e, &e->eQKV, (size_t)S * rows * e->QP));
+  TRY(dalloc(e, &e->eR1, (size_t)S * rows * DP)); TRY(dalloc(e, &e->eR2, (size_t)S * rows * DP));
+  TRY(dalloc(e, &e->eLOG, (size_t)S * seg * e->LP));
+  TRY(alloc_ctx(e, &e->eXN, 0, rows, 0, DP, lt)); TRY(alloc_ctx(e, &e->eATT, 0, rows, 0, DP, lt));
+  TRY(alloc_ctx(e, &e->eFN, 0, rows, 0, DP, lt)); TRY(alloc_ctx(e, &e->eHF, 0, rows, 0, c.emformer_ffn, lt));
   e->eRing.resize(c.emformer_layers);
   for (int l = 0; l < c.emformer_layers; ++l) TRY(dalloc(e, &e->eRing[l], (size_t)S * e->ring_rows * 2 * D));
   TRY(dalloc(e, &e->ePast, (size_t)S)); TRY(dalloc(e, &e->TOK, (size_t)S * seg));
   // ---- Conan chunk path
-  TRY(alloc_ctx(e, &e->cC, c.content_kernel - 1, seg, 0, H, 0));
-  for (int i = 0; i < 5; ++i) TRY(alloc_ctx(e, &e->cUV[i], c.predictor_kernel - 1, seg, 0, i == 0 ? H : 128, 0));
+  TRY(alloc_ctx(e, &e->cC, c.content_kernel - 1, seg, 0, H, lt));
+  for (int i = 0; i < 5; ++i) TRY(alloc_ctx(e, &e->cUV[i], c.predictor_kernel - 1, seg, 0, i == 0 ? H : 128, lt));
   for (int b = 0; b < c.dec_blocks; ++b)
-    for (int s = 0; s < 2; ++s) TRY(alloc_ctx(e, &e->cD[b][s], c.dec_kernel - 1, seg, 0, H, 0));
-  TRY(alloc_ctx(e, &e->cP, c.dec_post_kernel - 1, seg, 0, H, 0));
+    for (int s = 0; s < 2; ++s) TRY(alloc_ctx(e, &e->cD[b][s], c.dec_kernel - 1, seg, 0, H, lt));
+  TRY(alloc_ctx(e, &e->cP, c.dec_post_kernel - 1, seg, 0, H, lt));
+  TRY(alloc_ctx(e, &e->cX0, 0, seg, 0, H, lt)); TRY(alloc_ctx(e, &e->cATT, 0, seg, 0, H, lt));
+  TRY(alloc_ctx(e, &e->cO1, 0, seg, 0, H, lt)); TRY(alloc_ctx(e, &e->cHF, 0, seg, 0, 2048, lt));
+  TRY(alloc_ctx(e, &e->cPROS[0], 0, seg, 0, H, lt)); TRY(alloc_ctx(e, &e->cPROS[1], 0, seg, 0, H, lt));
+  TRY(alloc_ctx(e, &e->cDECH, 0, seg, 0, 2 * H, lt));
   TRY(dalloc(e, &e->dX0, (size_t)S * seg * H)); TRY(dalloc(e, &e->dQ, (size_t)S * seg * H));
-  TRY(dalloc(e, &e->dATT, (size_t)S * seg * H)); TRY(dalloc(e, &e->dT1, (size_t)S * seg * H));
-  TRY(dalloc(e, &e->dO1, (size_t)S * seg * H)); TRY(dalloc(e, &e->dHF, (size_t)S * seg * 2048));
+  TRY(dalloc(e, &e->dT1, (size_t)S * seg * H)); TRY(dalloc(e, &e->dO1, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dT2, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dPROS[0], (size_t)S * seg * H)); TRY(dalloc(e, &e->dPROS[1], (size_t)S * seg * H));
   TRY(dalloc(e, &e->dPINP, (size_t)S * seg * H)); TRY(dalloc(e, &e->dUVH, (size_t)S * seg * 128));
-  TRY(dalloc(e, &e->dDECX, (size_t)S * seg * H)); TRY(dalloc(e, &e->dDECH, (size_t)S * seg * 2 * H));
+  TRY(dalloc(e, &e->dDECX, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dPOST, (size_t)S * seg * H)); TRY(dalloc(e, &e->dMEL, (size_t)S * seg * c.n_mels));
   TRY(dalloc(e, &e->dUVP, (size_t)S * seg * 4)); TRY(dalloc(e, &e->dMASK0, (size_t)S * seg));
   TRY(dalloc(e, &e->dMASKB, (size_t)S * seg));
@@ -350,10 +383,13 @@ int allocate_state(conan_engine* e) {
     for (const Ctx* cx : ctxs) {
       if (cx->H <= 0) continue;
       size_t rowb = (size_t)cx->C * cx->elem();
-      HistDesc d{cx->p, (long long)(cx->slot_stride() * cx->elem()), cx->hist, (int)(cx->H * rowb), (int)(cx->L * rowb), 1};
-      if (d.hist_bytes % 16 || d.new_bytes % 16 || d.work_stride_bytes % 16) { set_error("context sizes must be multiples of 16 bytes"); return 1; }
-      r.push_back(d);
-      z.push_back(ZeroDesc{cx->hist, (long long)d.hist_bytes, (long long)d.hist_bytes});
+      for (int pl = 0; pl < (cx->is_half == 2 ? 2 : 1); ++pl) {          // a split buffer is two planes (hi, lo)
+        HistDesc d{(char*)cx->p + (size_t)pl * cx->plane * cx->elem(), (long long)(cx->slot_stride() * cx->elem()),
+                   (char*)cx->hist + (size_t)pl * cx->hist_plane * cx->elem(), (int)(cx->H * rowb), (int)(cx->L * rowb), 1};
+        if (d.hist_bytes % 16 || d.new_bytes % 16 || d.work_stride_bytes % 16) { set_error("context sizes must be multiples of 16 bytes"); return 1; }
+        r.push_back(d);
+        z.push_back(ZeroDesc{d.hist, (long long)d.hist_bytes, (long long)d.hist_bytes});
+      }
     }
     *nhist = (int)r.size(); *nzeros = (int)z.size();
     if (!r.empty()) {
@@ -420,36 +456,41 @@ int allocate_state(conan_engine* e) {
 int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, float* enc_out, float* logits_out,
                   int* tokens_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
-  const int D = c.emformer_dim, seg = c.segment, rc = c.right_context, rows = seg + rc, F = c.emformer_ffn;
-  TRY(launch_emformer_assemble(chunk, e->eX, n, nullptr, seg, rc, D, st));
+  const int D = c.emformer_dim, DP = e->DP, QP = e->QP, LP = e->LP, seg = c.segment, rc = c.right_context, rows = seg + rc,
+            F = c.emformer_ffn;
+  const bool tc = e->lin_tc;
+  TRY(launch_emformer_assemble(chunk, e->eX, DP, n, nullptr, seg, rc, D, st));
   for (int l = 0; l < c.emformer_layers; ++l) {
     std::string p = "emf." + std::to_string(l) + ".";
-    TRY(ln_rows(e->eX, rows, 0, view_f32(e->eXN, (long long)rows * D, D), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, st));
-    auto q = conv_on_rows(e, e->eXN, rows, 0, rows, D, e->P(p + "qkv.w"), e->F(p + "qkv.b"), 3 * D, n);
-    out_rows(q, e->eQKV, rows, 3 * D);
-    TRY(run_conv(e, q, st));
-    TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT, n, ids, seg, rc, c.left_context, e->ring_rows, D,
-                                  c.emformer_heads, 3 * D, D, st));
-    auto o = conv_on_rows(e, e->eATT, rows, 0, rows, D, e->P(p + "out.w"), e->F(p + "out.b"), D, n);
-    out_rows(o, e->eR1, rows, D); res_rows(o, e->eX, rows, D);
-    TRY(run_conv(e, o, st));
-    TRY(ln_rows(e->eR1, rows, 0, view_f32(e->eFN, (long long)rows * D, D), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
-    auto f1 = conv_on_rows(e, e->eFN, rows, 0, rows, D, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
-    out_rows(f1, e->eHF, rows, F); f1.act = ACT_RELU;
-    TRY(run_conv(e, f1, st));
-    auto f2 = conv_on_rows(e, e->eHF, rows, 0, rows, F, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), D, n);
-    out_rows(f2, e->eR2, rows, D); res_rows(f2, e->eR1, rows, D);
-    TRY(run_conv(e, f2, st));
-    TRY(ln_rows(e->eR2, rows, 0, view_f32(e->eX, (long long)rows * D, D), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st));
+    TRY(ln_rows(e->eX, rows, DP, 0, e->eXN.new_rows(), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, st));
+    auto q = conv_on_ctx(e, e->eXN, 1, 1, e->P(p + "qkv.w"), e->F(p + "qkv.b"), QP, n);
+    out_rows(q, e->eQKV, rows, QP);
+    TRY(run_conv(e, q, st, tc));
+    TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT.new_rows(), n, ids, seg, rc, c.left_context, e->ring_rows, D,
+                                  c.emformer_heads, QP, st));
+    auto o = conv_on_ctx(e, e->eATT, 1, 1, e->P(p + "out.w"), e->F(p + "out.b"), DP, n);
+    out_rows(o, e->eR1, rows, DP); res_rows(o, e->eX, rows, DP);
+    TRY(run_conv(e, o, st, tc));
+    TRY(ln_rows(e->eR1, rows, DP, 0, e->eFN.new_rows(), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
+    auto f1 = conv_on_ctx(e, e->eFN, 1, 1, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
+    out2_ctx(f1, e->eHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
+    TRY(run_conv(e, f1, st, tc));
+    auto f2 = conv_on_ctx(e, e->eHF, 1, 1, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), DP, n);
+    out_rows(f2, e->eR2, rows, DP); res_rows(f2, e->eR1, rows, DP);
+    TRY(run_conv(e, f2, st, tc));
+    // the last layer's output is also the operand of the projection GEMM
+    const bool last = (l == c.emformer_layers - 1);
+    TRY(ln_rows(e->eR2, rows, DP, 0, view_f32(e->eX, (long long)rows * DP, DP), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st,
+                nullptr, nullptr, 0, nullptr, nullptr, last ? e->eXN.new_rows() : RowView{}));
   }
   TRY(launch_advance_past_len(e->ePast, n, ids, seg, st));
-  auto pj = conv_on_rows(e, e->eX, rows, rc, seg, D, e->P("emf.proj.w"), e->F("emf.proj.b"), c.emformer_output_dim, n);
-  out_rows(pj, e->eLOG, seg, c.emformer_output_dim);
-  TRY(run_conv(e, pj, st));
-  TRY(launch_argmax_rows(e->eLOG, c.emformer_output_dim, e->TOK, tokens_out, n, seg, c.emformer_output_dim, st));
-  if (enc_out) TRY(launch_copy_rows_out(e->eX, (long long)rows * D, D, rc, enc_out, n, nullptr, seg, D, st));
+  auto pj = conv_on_ctx(e, e->eXN, 1, 1, e->P("emf.proj.w"), e->F("emf.proj.b"), LP, n, true, rc, seg);   // utterance rows only
+  out_rows(pj, e->eLOG, seg, LP);
+  TRY(run_conv(e, pj, st, tc));
+  TRY(launch_argmax_rows(e->eLOG, LP, e->TOK, tokens_out, n, seg, c.emformer_output_dim, st));
+  if (enc_out) TRY(launch_copy_rows_out(e->eX, (long long)rows * DP, DP, rc, enc_out, n, nullptr, seg, D, st));
   if (logits_out)
-    CONAN_CUDA_OK(cudaMemcpyAsync(logits_out, e->eLOG, (size_t)n * seg * c.emformer_output_dim * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(launch_copy_rows_out(e->eLOG, (long long)seg * LP, LP, 0, logits_out, n, nullptr, seg, c.emformer_output_dim, st));
   return 0;
 }
 
@@ -457,6 +498,7 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
 int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, float* mel_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
   const int H = c.hidden_size, seg = c.segment;
+  const bool tc = e->lin_tc;
   const int* tok = tokens_ext ? tokens_ext : e->TOK;            // compact [n, seg]
   TRY(launch_hist_gather(e->histConan, e->nHistConan, n, ids, st));
   TRY(launch_embedding_rows(tok, e->F("conan.content_embedding"), 102, e->cC.new_rows(), n, nullptr, seg, H, st));
@@ -464,56 +506,60 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
     auto p = conv_on_ctx(e, e->cC, c.content_kernel, 1, e->P("conan.content_proj.w"), e->F("conan.content_proj.b"), H, n);
     out_rows(p, e->dX0, seg, H); p.act = ACT_LRELU; p.slope = 0.01f;
     p.res = e->sSTYLEW; p.res_slot_stride = H; p.res_row_stride = 0;                 // + style_embed (Conan.py:162)
-    TRY(run_conv(e, p, st));
+    out2_ctx(p, e->cX0, ACT_NONE, 0.f);
+    TRY(run_conv(e, p, st, tc));
   }
   const float* cur = e->dX0;
+  const Ctx* curc = &e->cX0;
   for (int l = 0; l < 2; ++l) {
     std::string a = "conan.align." + std::to_string(l) + ".";
-    auto q = conv_on_rows(e, cur, seg, 0, seg, H, e->P(a + "q.w"), e->F(a + "q.b"), H, n);
+    auto q = conv_on_ctx(e, *curc, 1, 1, e->P(a + "q.w"), e->F(a + "q.b"), H, n);
     out_rows(q, e->dQ, seg, H);
-    TRY(run_conv(e, q, st));
-    TRY(launch_cross_attention(e->dQ, e->sKV, e->sKPM, e->sNKEYS, e->dATT, n, ids, seg, H, 2, l, 2, e->tp_max, st));
-    auto o = conv_on_rows(e, e->dATT, seg, 0, seg, H, e->P(a + "out.w"), e->F(a + "out.b"), H, n);
+    TRY(run_conv(e, q, st, tc));
+    TRY(launch_cross_attention(e->dQ, e->sKV, e->sKPM, e->sNKEYS, e->cATT.new_rows(), n, ids, seg, H, 2, l, 2, e->tp_max, st));
+    auto o = conv_on_ctx(e, e->cATT, 1, 1, e->P(a + "out.w"), e->F(a + "out.b"), H, n);
     out_rows(o, e->dT1, seg, H); res_rows(o, cur, seg, H);
-    TRY(run_conv(e, o, st));
-    TRY(ln_rows(e->dT1, seg, 0, view_f32(e->dO1, (long long)seg * H, H), e->F(a + "norm1.g"), e->F(a + "norm1.b"), H, seg, n, st));
-    auto f1 = conv_on_rows(e, e->dO1, seg, 0, seg, H, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, n);
-    out_rows(f1, e->dHF, seg, 2048); f1.act = ACT_RELU;
-    TRY(run_conv(e, f1, st));
-    auto f2 = conv_on_rows(e, e->dHF, seg, 0, seg, 2048, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n);
+    TRY(run_conv(e, o, st, tc));
+    TRY(ln_rows(e->dT1, seg, H, 0, e->cO1.new_rows(), e->F(a + "norm1.g"), e->F(a + "norm1.b"), H, seg, n, st, nullptr, nullptr, 0,
+                nullptr, nullptr, view_f32(e->dO1, (long long)seg * H, H)));
+    auto f1 = conv_on_ctx(e, e->cO1, 1, 1, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, n);
+    out2_ctx(f1, e->cHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
+    TRY(run_conv(e, f1, st, tc));
+    auto f2 = conv_on_ctx(e, e->cHF, 1, 1, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n);
     out_rows(f2, e->dT2, seg, H); res_rows(f2, e->dO1, seg, H);
-    TRY(run_conv(e, f2, st));
-    TRY(ln_rows(e->dT2, seg, 0, view_f32(e->dPROS[l], (long long)seg * H, H), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st));
-    cur = e->dPROS[l];
+    TRY(run_conv(e, f2, st, tc));
+    TRY(ln_rows(e->dT2, seg, H, 0, e->cPROS[l].new_rows(), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st, nullptr, nullptr, 0,
+                nullptr, nullptr, view_f32(e->dPROS[l], (long long)seg * H, H)));
+    cur = e->dPROS[l]; curc = &e->cPROS[l];
   }
   TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, nullptr, seg, H, st));  // Conan.py:168
   for (int i = 0; i < 5; ++i) {                                                                // uv_predictor convs
     std::string u = "conan.uv." + std::to_string(i) + ".";
     auto p = conv_on_ctx(e, e->cUV[i], c.predictor_kernel, 1, e->P(u + "w"), e->F(u + "b"), 128, n);
     p.act = ACT_RELU;
-    if (i < 4) out_ctx(p, e->cUV[i + 1]); else out_rows(p, e->dUVH, seg, 128);
-    TRY(run_conv(e, p, st));
+    if (i < 4) out2_ctx(p, e->cUV[i + 1], ACT_NONE, 0.f); else out_rows(p, e->dUVH, seg, 128);
+    TRY(run_conv(e, p, st, tc));
   }
   TRY(launch_pitch(e->dUVH, e->F("conan.uv.ln.g"), e->F("conan.uv.ln.b"), e->F("conan.uv.lin.w"), e->F("conan.uv.lin.b"), tok,
                    c.silent_token, e->F("conan.pitch_embed"), e->dPINP, e->dDECX, e->dUVP, n, nullptr, seg, 128, H, st));
   for (int b = 0; b < c.dec_blocks; ++b)
     for (int s = 0; s < 2; ++s) {
       std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
-      TRY(ln_rows(e->dDECX, seg, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, st, nullptr, nullptr, seg,
+      TRY(ln_rows(e->dDECX, seg, H, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, st, nullptr, nullptr, seg,
                   s == 0 ? e->dMASKB : nullptr, (b == 0 && s == 0) ? e->dMASK0 : nullptr));
       auto p = conv_on_ctx(e, e->cD[b][s], c.dec_kernel, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, n);
-      out_rows(p, e->dDECH, seg, 2 * H); p.scale = 1.0f / sqrtf((float)c.dec_kernel); p.act = ACT_GELU;
-      TRY(run_conv(e, p, st));
-      auto w = conv_on_rows(e, e->dDECH, seg, 0, seg, 2 * H, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n);
+      out2_ctx(p, e->cDECH, ACT_NONE, 0.f); p.scale = 1.0f / sqrtf((float)c.dec_kernel); p.act = ACT_GELU;
+      TRY(run_conv(e, p, st, tc));
+      auto w = conv_on_ctx(e, e->cDECH, 1, 1, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n);
       out_rows(w, e->dDECX, seg, H); res_rows(w, e->dDECX, seg, H); w.rowmask = e->dMASKB; w.mask_slot_stride = seg;
-      TRY(run_conv(e, w, st));
+      TRY(run_conv(e, w, st, tc));
     }
-  TRY(ln_rows(e->dDECX, seg, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, st,
+  TRY(ln_rows(e->dDECX, seg, H, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, st,
               e->dMASK0, e->dMASK0, seg));
   {
     auto p = conv_on_ctx(e, e->cP, c.dec_post_kernel, 1, e->P("conan.dec.post.w"), e->F("conan.dec.post.b"), H, n);
     out_rows(p, e->dPOST, seg, H); p.rowmask = e->dMASK0; p.mask_slot_stride = seg;
-    TRY(run_conv(e, p, st));
+    TRY(run_conv(e, p, st, tc));
     auto m = conv_on_rows(e, e->dPOST, seg, 0, seg, H, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), c.n_mels, n);
     out_rows(m, e->dMEL, seg, c.n_mels);
     TRY(run_conv(e, m, st));
@@ -533,7 +579,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
   {
     auto p = conv_on_ctx(e, e->vPRE, 7, 1, e->P("voc.pre.w"), e->F("voc.pre.b"), e->vC[0], n);
     out2_ctx(p, e->vUP[0], ACT_LRELU, sl);
-    TRY(run_conv(e, p, st, true));
+    TRY(run_conv(e, p, st, e->cfg.voc_use_tensor_cores != 0));
   }
   for (int i = 0; i < c.voc_n_ups; ++i) {
     const int r_up = c.voc_rates[i], L = e->vL[i + 1], C = e->vC[i + 1];
@@ -545,7 +591,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
       p.y = e->vXS; p.y_slot_stride = (long long)L * C; p.y_row_stride = r_up * C; p.y_row0 = 0;
       p.y2 = e->vXA[i].at_row(e->vXA[i].H); p.y2_slot_stride = e->vXA[i].slot_stride(); p.y2_row_stride = r_up * C; p.y2_row0 = 0;
       p.y2_is_half = e->vXA[i].is_half; p.act2 = ACT_LRELU; p.slope2 = sl;
-      TRY(run_conv(e, p, st, true));
+      TRY(run_conv(e, p, st, e->cfg.voc_use_tensor_cores != 0));
     }
     const bool last_scale = (i == c.voc_n_ups - 1);
     const Ctx& next = last_scale ? e->vPOST : e->vUP[i + 1];
@@ -558,7 +604,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
         auto p1 = conv_on_ctx(e, in1, k, c.voc_res_dilations[j], e->P(q + "c1." + std::to_string(j) + ".w"),
                               e->F(q + "c1." + std::to_string(j) + ".b"), C, n);
         out2_ctx(p1, e->vC2[i][r][j], ACT_LRELU, sl);
-        TRY(run_conv(e, p1, st, true));
+        TRY(run_conv(e, p1, st, e->cfg.voc_use_tensor_cores != 0));
         auto p2 = conv_on_ctx(e, e->vC2[i][r][j], k, 1, e->P(q + "c2." + std::to_string(j) + ".w"),
                               e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
         res_rows(p2, xj, L, C);
@@ -572,7 +618,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
           p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)
           if (r == c.voc_n_res - 1) out2_ctx(p2, next, ACT_LRELU, sl);
         }
-        TRY(run_conv(e, p2, st, true));
+        TRY(run_conv(e, p2, st, e->cfg.voc_use_tensor_cores != 0));
       }
     }
   }
@@ -607,7 +653,7 @@ int conv_blocks_noncausal(conan_engine* e, const std::string& pre, float* X, int
   for (int b = 0; b < 5; ++b)
     for (int s = 0; s < 2; ++s) {
       std::string d = pre + "." + std::to_string(b) + "." + std::to_string(s) + ".";
-      TRY(ln_rows(X, T, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, st, nullptr, nullptr, T,
+      TRY(ln_rows(X, T, C, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, st, nullptr, nullptr, T,
                   s == 0 ? maskb : nullptr, nullptr));
       auto p = conv_on_ctx(e, ck, k, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * C, n, false);
       p.n_slots = n; out_rows(p, Hbuf, T, 2 * C); p.scale = 1.0f / sqrtf((float)k); p.act = ACT_GELU;
@@ -616,7 +662,7 @@ int conv_blocks_noncausal(conan_engine* e, const std::string& pre, float* X, int
       w.n_slots = n; out_rows(w, X, T, C); res_rows(w, X, T, C); w.rowmask = maskb; w.mask_slot_stride = T;
       TRY(run_conv(e, w, st));
     }
-  TRY(ln_rows(X, T, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, st, nonpad, nonpad, T));
+  TRY(ln_rows(X, T, C, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, st, nonpad, nonpad, T));
   auto p = conv_on_ctx(e, c3, 3, 1, e->P(pre + ".post.w"), e->F(pre + ".post.b"), outC, n, false);
   p.n_slots = n; out_rows(p, OUT, T, outC); p.rowmask = nonpad; p.mask_slot_stride = T;
   TRY(run_conv(e, p, st));
@@ -719,6 +765,7 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
   e->cfg = *cfg;
   e->S = cfg->max_slots;
   e->tp_max = (cfg->max_ref_frames - 1) / 4 + 1;
+  e->lin_tc = cfg->lin_use_tensor_cores != 0;
   declare_weights(e);
   *out = e;
   return 0;

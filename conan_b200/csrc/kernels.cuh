@@ -8,18 +8,29 @@ namespace conan {
 
 // A strided view of per-slot rows: element (slot, t, c) lives at
 //   base[slot * slot_stride + (row0 + t) * row_stride + c].
+//   is_half: 0 = fp32, 1 = fp16, 2 = split fp16 pair: hi = fp16(v) at base, lo = fp16(v - hi) at base + lo_off
+//   (the operand format of the fp32-grade tensor-core GEMMs, see conv_gemm_tc.cu)
 struct RowView {
   void* base = nullptr;
   long long slot_stride = 0;
   int row_stride = 0;
   int row0 = 0;
   int is_half = 0;
+  long long lo_off = 0;
 };
+
+__device__ __forceinline__ void store_view(const RowView& v, long long off, float x) {
+  if (v.is_half == 0) { reinterpret_cast<float*>(v.base)[off] = x; return; }
+  __half h = __float2half_rn(x);
+  reinterpret_cast<__half*>(v.base)[off] = h;
+  if (v.is_half == 2) reinterpret_cast<__half*>(v.base)[off + v.lo_off] = __float2half_rn(x - __half2float(h));
+}
 inline RowView view_f32(float* p, long long ss, int rs, int r0 = 0) { return RowView{p, ss, rs, r0, 0}; }
 
 struct LnArgs {
   RowView in;            // fp32
-  RowView out;           // fp32 or fp16
+  RowView out;           // fp32, fp16 or split fp16
+  RowView out2;          // optional second copy (base == nullptr: none), e.g. fp32 residual next to a split GEMM operand
   const float* gamma; const float* beta; float eps;
   int C, L, n;
   const int* slot_ids;
@@ -32,11 +43,11 @@ int launch_layernorm(const LnArgs& a, cudaStream_t st);
 
 // Emformer ------------------------------------------------------------------------------
 // chunk [n, seg+rc, D] (utterance rows first) -> X[slot] rows ordered [rc | utt] (TA:430)
-int launch_emformer_assemble(const float* chunk, float* X, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st);
+int launch_emformer_assemble(const float* chunk, float* X, int ldx, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st);
 // per stream: append utterance K/V rows to the ring, softmax(QK^T) V over [rc | left ctx | utt].
 // qkv / att are compact (index i, row stride ld); kv_ring / past_len are resident state indexed by slot_ids[i].
-int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, float* att, int n,
-                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv, int ld_att,
+int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, RowView att, int n,
+                              const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv,
                               cudaStream_t st);
 int launch_advance_past_len(int* past_len, int n, const int* slot_ids, int seg, cudaStream_t st);
 int launch_argmax_rows(const float* logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C, cudaStream_t st);
@@ -50,7 +61,7 @@ int launch_embedding_rows(const int* tokens_slot, const float* table, int vocab,
                           int rows, int C, cudaStream_t st);
 // nn.MultiheadAttention(256, 2) over the session-cached K/V (prosody_util.py:108-127)
 // q / out compact; kv_cache, kpm, n_keys are session state indexed by slot_ids[i]
-int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, float* out, int n,
+int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, RowView out, int n,
                            const int* slot_ids, int rows, int H, int heads, int layer, int n_layers, int tp_max, cudaStream_t st);
 // out1 = a + b (fp32), optional second copy into a context buffer
 int launch_add_rows(const float* a, const float* b, float* out1, RowView out2, int n, const int* slot_ids, int rows, int C, cudaStream_t st);

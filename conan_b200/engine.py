@@ -20,7 +20,7 @@ PARTS_EMFORMER, PARTS_CONAN, PARTS_VOCODER, PARTS_ALL = 1, 2, 4, 7
 
 def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max_slots: int = 64,
                 max_ref_frames: int = 512, device: int = 0, voc_precision: str = "fp16",
-                voc_tensor_cores: bool = True, voc_group: int = 0) -> _lib.ConanConfig:
+                voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -59,6 +59,9 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     cfg.voc_precision = {"fp32": 0, "fp16": 1}[voc_precision]
     cfg.voc_use_tensor_cores = int(bool(voc_tensor_cores) and cfg.voc_precision == 1)
     cfg.voc_group = voc_group
+    # Emformer / Conan contractions: split-fp16 tensor-core GEMMs (fp32-grade) by default whenever the tensor-core
+    # vocoder is on; lin_tensor_cores=False keeps them on the exact-fp32 FFMA engine
+    cfg.lin_use_tensor_cores = int(cfg.voc_use_tensor_cores if lin_tensor_cores is None else bool(lin_tensor_cores))
     return cfg
 
 
@@ -93,6 +96,9 @@ class Engine:
             self._weights[key] = t
             _lib.check(self.lib.conan_engine_bind_weight(self.h, key.encode(), _ptr(t), t.numel(), dtype.value), f"bind {key}")
         _lib.check(self.lib.conan_engine_finalize(self.h), "finalize")
+        # fp32 copy of the content-token projection for the module-level `emformer.proj` view
+        self.aux = {"emf.proj.w": sd_emformer["proj.weight"].float().contiguous().to(self.device),
+                    "emf.proj.b": sd_emformer["proj.bias"].float().contiguous().to(self.device)} if "proj.weight" in sd_emformer else {}
         self.segment = cfg.segment
         self.rows_in = cfg.segment + cfg.right_context
         self.hop_out = cfg.segment

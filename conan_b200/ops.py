@@ -23,14 +23,18 @@ def conv_gemm(ctx: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
               scale: float = 1.0, act: str = "none", slope: float = 0.0, res: Optional[torch.Tensor] = None,
               rowmask: Optional[torch.Tensor] = None, out_scale: float = 1.0, y: Optional[torch.Tensor] = None,
               accumulate: bool = False, y2: Optional[torch.Tensor] = None, y2_row0: int = 0, act2: str = "none",
-              slope2: float = 0.0):
+              slope2: float = 0.0, x_split: bool = False, acc_scale: float = 1.0, y2_split: bool = False):
     """ctx [slots, rows, cin] (fp32 or fp16), w_packed [cout, k*cin] (same dtype), bias [cout] fp32.
     y [slots, L, cout] fp32 (optional), y2 [slots, rows2, cout] fp32/fp16 written at rows y2_row0.. (optional),
     res [slots, L, cout] fp32 (optional), rowmask [slots, L] fp32 (optional)."""
     lib = _lib.load()
-    slots, rows, cin = ctx.shape
+    if x_split:          # ctx [2, slots, rows, cin] fp16 (hi plane, lo plane); w_packed [cout, 3*k*cin]
+        assert ctx.dim() == 4 and ctx.shape[0] == 2 and ctx.dtype == torch.float16
+        _, slots, rows, cin = ctx.shape
+    else:
+        slots, rows, cin = ctx.shape
     cout = w_packed.shape[0]
-    assert ctx.is_cuda and ctx.is_contiguous() and w_packed.is_contiguous() and w_packed.shape[1] == k * cin
+    assert ctx.is_cuda and ctx.is_contiguous() and w_packed.is_contiguous() and w_packed.shape[1] == (3 if x_split else 1) * k * cin
     assert ctx.dtype == w_packed.dtype and ctx.dtype in (torch.float32, torch.float16)
     p = _lib.ConvParams()
     p.x, p.x_slot_stride, p.x_row_stride, p.x_rows = _p(ctx), rows * cin, cin, rows
@@ -51,10 +55,17 @@ def conv_gemm(ctx: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
         assert y.dtype == torch.float32 and y.shape == (slots, L, cout) and y.is_contiguous()
         p.y, p.y_slot_stride, p.y_row_stride, p.y_row0 = _p(y), L * cout, cout, 0
     p.accumulate = int(accumulate)
-    if y2 is not None:
+    if y2 is not None and y2_split:      # y2 [2, slots, rows2, cout] fp16
+        assert y2.dim() == 4 and y2.shape[0] == 2 and y2.dtype == torch.float16 and y2.is_contiguous()
+        p.y2, p.y2_slot_stride, p.y2_row_stride, p.y2_row0 = _p(y2), y2.shape[2] * cout, cout, y2_row0
+        p.y2_is_half, p.y2_split, p.y2_lo_off = 1, 1, y2.shape[1] * y2.shape[2] * cout
+    elif y2 is not None:
         assert y2.shape[0] == slots and y2.shape[2] == cout and y2.is_contiguous()
         p.y2, p.y2_slot_stride, p.y2_row_stride, p.y2_row0 = _p(y2), y2.shape[1] * cout, cout, y2_row0
         p.y2_is_half = int(y2.dtype == torch.float16)
+    if x_split:
+        p.x_split, p.x_lo_slot_off = 1, slots
+    p.acc_scale = acc_scale
     p.act2, p.slope2 = ACT[act2], slope2
     st = C.c_void_p(torch.cuda.current_stream(ctx.device).cuda_stream)
     _lib.check(lib.conan_conv_gemm(C.byref(p), engine, st), "conv_gemm")

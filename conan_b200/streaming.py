@@ -94,7 +94,7 @@ class EmformerView:
         """Linear(80 -> emformer_output_dim) through the FFMA conv-GEMM operator."""
         from . import ops
         B, T, D = x.shape
-        w, b = self.eng._weights["emf.proj.w"], self.eng._weights["emf.proj.b"]
+        w, b = self.eng.aux["emf.proj.w"], self.eng.aux["emf.proj.b"]
         y = torch.empty(B, T, w.shape[0], device=self.eng.device)
         ops.conv_gemm(x.to(self.eng.device, torch.float32).contiguous(), w, b, k=1, dil=1, L=T, row0=0, y=y)
         return y

@@ -25,6 +25,27 @@ def pack_conv(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()
 
 
+SPLIT_WEIGHT_SCALE = 1024.0      # must match kSplitWeightScale in csrc/engine.cu
+
+
+def split_linear(w_packed: torch.Tensor, bias: torch.Tensor, k: int = 1):
+    """fp32 packed weight [N, k*K] -> the operand of the fp32-grade tensor-core GEMM:
+    fp16 [Npad, 3*k*Kpad] = [W_hi | W_lo | W_hi] of 2^10 * W (W_hi = fp16(W'), W_lo = fp16(W' - W_hi)), N and K
+    zero-padded to multiples of 32, plus the bias zero-padded to Npad.  The kernel accumulates
+    x_hi*W_hi + x_hi*W_lo + x_lo*W_hi in fp32 and multiplies by 2^-10."""
+    N, KK = w_packed.shape
+    K = KK // k
+    Np, Kp = (N + 31) // 32 * 32, (K + 31) // 32 * 32
+    w = torch.zeros(Np, k, Kp, dtype=torch.float32)
+    w[:N, :, :K] = w_packed.view(N, k, K) * SPLIT_WEIGHT_SCALE
+    w = w.view(Np, k * Kp)
+    hi = w.half()
+    lo = (w - hi.float()).half()
+    b = torch.zeros(Np, dtype=torch.float32)
+    b[:N] = bias
+    return torch.cat([hi, lo, hi], dim=1).contiguous(), b
+
+
 def sinusoid_table(n_pos: int, dim: int, padding_idx: int = 0) -> torch.Tensor:
     """Sinusoidal position table laid out as the reference builds it
     (modules/commons/transformer.py:31-47): [sin | cos] halves, log(10000)/(half-1) spacing,
@@ -130,4 +151,16 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
     wpost = fold_weight_norm(v, "conv_post.conv")                                # [1, ch, 7]
     out["voc.post.w"] = wpost[0].t().contiguous().reshape(-1)                    # [7, ch]
     out["voc.post.b"] = v["conv_post.conv.bias"]
+    # ---- fp32-grade tensor-core mode: the per-chunk linear / conv contractions take split-fp16 weights
+    if cfg.lin_use_tensor_cores:
+        names = [f"emf.{l}.{n}" for l in range(cfg.emformer_layers) for n in ("qkv", "out", "ffn1", "ffn2")] + ["emf.proj"]
+        names += [f"conan.align.{l}.{n}" for l in range(2) for n in ("q", "out", "ffn1", "ffn2")]
+        names += [f"conan.dec.{b_}.{s_}.pw" for b_ in range(cfg.dec_blocks) for s_ in range(2)]
+        taps = {n: 1 for n in names}
+        taps["conan.content_proj"] = cfg.content_kernel
+        taps["conan.dec.post"] = cfg.dec_post_kernel
+        taps.update({f"conan.uv.{i}": cfg.predictor_kernel for i in range(5)})
+        taps.update({f"conan.dec.{b_}.{s_}.conv": cfg.dec_kernel for b_ in range(cfg.dec_blocks) for s_ in range(2)})
+        for n, k in taps.items():
+            out[n + ".w"], out[n + ".b"] = split_linear(out[n + ".w"].float(), out[n + ".b"].float(), k)
     return {k: t.detach().contiguous() for k, t in out.items()}

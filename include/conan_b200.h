@@ -71,7 +71,9 @@ typedef struct conan_config {
   int32_t voc_precision;          /* 0: fp32 operands (FFMA);  1: fp16 operands, fp32 accumulate */
   int32_t voc_use_tensor_cores;   /* 1: tcgen05 implicit-GEMM kernels where eligible (needs voc_precision 1) */
   int32_t voc_group;              /* streams per vocoder pass (L2 blocking); 0 = all at once */
-  int32_t reserved[8];
+  int32_t lin_use_tensor_cores;   /* 1: Emformer / Conan linear + conv contractions on tcgen05 with split-fp16 operands
+                                     (x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, fp32 accumulate: fp32-grade results); 0: fp32 FFMA */
+  int32_t reserved[7];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */
@@ -198,6 +200,15 @@ typedef struct conan_conv_params {
   int32_t y2_is_half;
   int32_t act2;
   float slope2;
+  /* fp32-grade tensor-core mode (tcgen05 engine only): operands are split fp16 pairs v = hi + lo.
+   * x_split = 1: the hi plane of x is slot s, the lo plane slot s + x_lo_slot_off of the same buffer, and w is
+   * packed [cout, 3*k*cin] = [W_hi | W_lo | W_hi] (optionally pre-scaled by 1/acc_scale); the kernel accumulates
+   * x_hi*W_hi + x_hi*W_lo + x_lo*W_hi in fp32.  y2_split = 1: y2 is written as such a pair (lo at +y2_lo_off elements). */
+  int32_t x_split;
+  int64_t x_lo_slot_off;
+  float acc_scale;          /* v = (acc * acc_scale + bias) * scale ; 0 means 1 */
+  int32_t y2_split;
+  int64_t y2_lo_off;
 } conan_conv_params_t;
 
 /* engine: 0 = FFMA (fp32 accumulate on CUDA cores, fp32 or fp16 operands),

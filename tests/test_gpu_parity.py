@@ -36,7 +36,7 @@ def _engine(state_dicts, **kw):
 
 @pytest.fixture(scope="module")
 def eng_fp32(state_dicts):
-    e = _engine(state_dicts, voc_precision="fp32", voc_tensor_cores=False)
+    e = _engine(state_dicts, voc_precision="fp32", voc_tensor_cores=False, lin_tensor_cores=False)
     yield e
     e.close()
 
@@ -155,6 +155,47 @@ def test_conv_gemm_tcgen05_vs_ffma_and_torch(cin, cout, k, dil, L, S):
     assert (outs["tc"][0][untouched] == 0).all()
 
 
+SPLIT_SHAPES = [
+    # cin, cout, k, L, S     (Emformer / Conan contractions in fp32-grade tensor-core mode; dims already padded to 32)
+    (96, 256, 1, 6, 70), (96, 2048, 1, 6, 33), (2048, 96, 1, 6, 20), (96, 128, 1, 4, 50),
+    (256, 256, 3, 4, 40), (256, 512, 5, 4, 35), (512, 256, 1, 4, 64), (256, 2048, 1, 4, 10), (128, 128, 5, 4, 33),
+]
+
+
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+@pytest.mark.parametrize("cin,cout,k,L,S", SPLIT_SHAPES)
+def test_conv_gemm_tcgen05_split_fp16_is_fp32_grade(cin, cout, k, L, S):
+    """x_hi*W_hi + x_hi*W_lo + x_lo*W_hi on the tensor cores vs a float64 reference.  The operands carry ~22 bits;
+    what remains is the tensor core's fp32 accumulation (truncating adds: the error grows with the number of
+    K-steps, measured 3e-6 at K=96 .. 5e-5 at K=2048 for O(1) outputs) -- two orders below the 1e-3 mel budget
+    and below the smallest argmax margin of the golden runs (8e-4)."""
+    from conan_b200 import ops
+    from conan_b200.weights import pack_conv, split_linear
+    g = torch.Generator().manual_seed(cin + cout + k + L)
+    H = (k - 1) + 1
+    nslots = S + 3
+    x = torch.randn(nslots, H + L, cin, generator=g)
+    w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(nslots, L, cout, generator=g)
+    xh = x.half()
+    ctx = torch.stack([xh, (x - xh.float()).half()]).contiguous()
+    w3, bp = split_linear(pack_conv(w), b, k)
+    ref = F.gelu(_conv_reference(x.double(), w.double(), b.double(), k, 1, L, 1) * 0.7) + res.double()
+    y = torch.zeros(nslots, L, cout, device="cuda")
+    y2 = torch.zeros(2, nslots, L + 2, cout, device="cuda", dtype=torch.float16)
+    ops.conv_gemm(ctx.cuda(), w3.cuda(), bp.cuda(), k=k, dil=1, L=L, row0=1, n_streams=S, engine=ops.ENGINE_TC, scale=0.7, act="gelu",
+                  res=res.cuda(), y=y, y2=y2, y2_row0=2, y2_split=True, x_split=True, acc_scale=1.0 / 1024)
+    torch.cuda.synchronize()
+    err = (y.cpu()[:S].double() - ref[:S]).abs().max().item()
+    y2c = y2.cpu().float()
+    pair = (y2c[0] + y2c[1])[:S, 2:]
+    err2 = (pair.double() - ref[:S]).abs().max().item()
+    print("split-fp16 GEMM max-abs", err, "pair", err2)
+    assert err < 1e-4 and err2 < 1e-4
+    assert (y.cpu()[S:] == 0).all() and (y2c[:, S:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------
 # Emformer
 # ------------------------------------------------------------------------------------------
@@ -164,9 +205,10 @@ def _chunks(src, pos):
     return c.contiguous(), emit
 
 
-def test_emformer_step_vs_oracle_lockstep(state_dicts, eng_fp32):
+@pytest.mark.parametrize("which", ["eng_fp32", "eng_tc"])
+def test_emformer_step_vs_oracle_lockstep(state_dicts, which, request):
     from oracle.incremental import EmformerOracle
-    eng = eng_fp32
+    eng = request.getfixturevalue(which)
     B, T = 3, 72                                   # 18 chunks: left context saturates at 50 and the 56-row ring wraps
     src = torch.stack([synth.synth_mel(T, 40 + s) for s in range(B)])
     o = EmformerOracle(state_dicts[1])
@@ -184,7 +226,7 @@ def test_emformer_step_vs_oracle_lockstep(state_dicts, eng_fp32):
         worst = max(worst, (enc.cpu() - enc_ref).abs().max().item())
         worst_logit = max(worst_logit, (logits.cpu() - logit_ref).abs().max().item())
         assert (tok.cpu().long() == logit_ref.argmax(-1)).all(), f"token mismatch at pos {pos}"
-    print("emformer enc max-abs", worst, "logits max-abs", worst_logit)
+    print(which, "emformer enc max-abs", worst, "logits max-abs", worst_logit)
     assert worst < 1e-4 and worst_logit < 1e-4
     assert int(eng.debug_read("emformer_past_len", 5).view(torch.int32)[0]) == T
 
@@ -247,9 +289,10 @@ def test_session_open_vs_oracle(state_dicts, eng_fp32, t_ref):
     assert (idx.long() == dbg["vq_idx"][0]).all()
 
 
-def test_decoder_step_vs_oracle_teacher_forced(state_dicts, eng_fp32):
+@pytest.mark.parametrize("which", ["eng_fp32", "eng_tc"])
+def test_decoder_step_vs_oracle_teacher_forced(state_dicts, which, request):
     from oracle.incremental import ConanOracle
-    eng = eng_fp32
+    eng = request.getfixturevalue(which)
     B, n_chunks = 3, 14                              # 56 frames: longer than the 56-frame receptive field of the chunk path
     ref = torch.stack([synth.synth_mel(90, 21 + s) for s in range(B)])
     g = torch.Generator().manual_seed(9)
@@ -273,7 +316,7 @@ def test_decoder_step_vs_oracle_teacher_forced(state_dicts, eng_fp32):
                 uvp = eng.debug_read("uv_pred", i).cpu().view(4, 4)      # scratch is compact: index in the ready list
                 assert (uvp[:, 3].long() == dbg["pitch"][i]).all(), "f0 bucket mismatch"
                 buckets.update(dbg["pitch"][i].tolist())
-    print("decoder mel max-abs", worst, "distinct f0 buckets", len(buckets))
+    print(which, "decoder mel max-abs", worst, "distinct f0 buckets", len(buckets))
     assert worst < MEL_TOL
     assert len(buckets) > 8                          # the bucket arithmetic is genuinely exercised
 
