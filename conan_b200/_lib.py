@@ -74,7 +74,7 @@ SYMBOLS = {
     "conan_step_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "conan_engine_launch_count": (C.c_uint64, [_P]),
     "conan_engine_set_profiling": (C.c_int, [_P, C.c_int]),
-    "conan_engine_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "conan_engine_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "conan_debug_read": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),
     "conan_conv_gemm": (C.c_int, [C.POINTER(ConvParams), C.c_int, _P]),
 }

@@ -59,5 +59,6 @@ __device__ __forceinline__ float warp_max(float v) {
 int launch_conv_gemm_ffma(const conan_conv_params_t& p, cudaStream_t st);
 int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st);
 bool conv_gemm_tc_eligible(const conan_conv_params_t& p);
+bool conv_gemm_tc_uses_window(const conan_conv_params_t& p);
 
 }  // namespace conan

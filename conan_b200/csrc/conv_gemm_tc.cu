@@ -22,6 +22,7 @@
 // upsampling conv is just this kernel with a wider output row).
 #include <cuda.h>
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -48,6 +49,7 @@ struct TcArgs {
   int n_streams, L, TT, cin, k, dil, cout, row0;
   int kblocks;               // nseg * k * cin / BK
   int n_tiles;               // cout / BN
+  int num_tiles;             // m_tiles * n_tiles
   int nseg;                  // 1, or 3 for split operands: K' = [x_hi*W_hi | x_hi*W_lo | x_lo*W_hi]
   int lo_slot_off;           // slot offset of the lo plane of a split x
   TcEpi e;
@@ -61,6 +63,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -213,25 +218,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 5)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
   using SL = SmemLayout<BN, BK, STAGES>;
   constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulators: MMAs of tile i+1 overlap the epilogue of tile i
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SL::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = blockIdx.x % a.n_tiles, mt = blockIdx.x / a.n_tiles;
-  // a tile is NS = 128/TT consecutive streams x TT consecutive time steps: one rectangular TMA box
+  // a tile is NS = 128/TT consecutive streams x TT consecutive time steps: one rectangular TMA box.
+  // Persistent CTAs walk the tiles round-robin; consecutive tile ids share the A rows (nt fastest).
   const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
-  const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -248,50 +253,71 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       const int kb_per_tap = a.cin / BK;
       const int kb_per_seg = a.kblocks / a.nseg;
-      for (int kb = 0; kb < a.kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * SL::STAGE_BYTES;
-        uint8_t* sb = sa + SL::A_BYTES;
-        mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
-        const int seg = kb / kb_per_seg, kbl = kb - seg * kb_per_seg;
-        const int j = kbl / kb_per_tap, c0 = (kbl - j * kb_per_tap) * BK;
-        tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
-        tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
+      int kbg = 0;                                           // k-block counter across tiles (the smem ring never drains)
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+        const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
+        for (int kb = 0; kb < a.kblocks; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * SL::STAGE_BYTES;
+          uint8_t* sb = sa + SL::A_BYTES;
+          mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
+          const int seg = kb / kb_per_seg, kbl = kb - seg * kb_per_seg;
+          const int j = kbl / kb_per_tap, c0 = (kbl - j * kb_per_tap) * BK;
+          tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
+          tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
-      for (int kb = 0; kb < a.kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[ab], aph ^ 1);                  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
-        const uint32_t sb = sa + SL::A_BYTES;
-        const uint64_t adesc = make_smem_desc<SWZ>(sa), bdesc = make_smem_desc<SWZ>(sb);
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+        for (int kb = 0; kb < a.kblocks; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+          const uint32_t sb = sa + SL::A_BYTES;
+          const uint64_t adesc = make_smem_desc<SWZ>(sa), bdesc = make_smem_desc<SWZ>(sb);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // advance 16 halfs = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-          tc_mma_f16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 halfs = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+            tc_mma_f16(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);            // frees the smem stage when these MMAs have read it
+        tc_commit(&acc_full[ab]);            // accumulator complete
       }
-      tc_commit(tmem_full_bar);              // accumulator complete
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;       // tile row == TMEM lane
     const int q = r / a.TT, tt = r - q * a.TT;
-    const int stream = stream0 + q;
-    epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16), nt * BN, stream < a.n_streams, stream, t0 + tt,
-                      tmem_full_bar, 0);
-    tc_fence_before();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+      const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
+      epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), nt * BN, stream < a.n_streams, stream, t,
+                        &acc_full[ab], aph);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -316,10 +342,6 @@ struct WinArgs {
   TcEpi e;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // A descriptor whose start address is offset by whole rows inside a swizzle atom (tap j starts
 // j*dil rows into the window).  Measured on B200: the swizzle XOR is applied on absolute shared-memory
 // address bits, so the descriptor's base_offset field must stay 0 for such starts (setting it to
@@ -327,7 +349,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // the 128-byte and the 64-byte swizzle.
 
 template <int C, int BN, int NBUF, int NEPI>
-__global__ void __launch_bounds__(64 + 128 * NEPI)
+__global__ void __launch_bounds__(64 + 128 * NEPI, NEPI == 1 ? 4 : 1)
 conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, WinArgs a) {
   constexpr int ROWB = C * 2;                       // bytes per row = swizzle span (64 or 128)
   constexpr int TAPB = BN * ROWB;                   // one tap of the weight matrix
@@ -489,6 +511,22 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, unsigned long lo
   return 0;
 }
 
+int num_sms();
+
+// CTAs of a kernel that fit on one SM: registers, shared memory (with the carve-out preference set to
+// "max shared", which the launchers request), warps and the 512 TMEM columns.  The CUDA occupancy query is
+// not used: it answers for the *default* carve-out and returns 1 for these kernels.
+int resident_ctas(const void* func, int threads, size_t dyn_smem, int tmem_cols) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, func) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+  const int regs_per_cta = ((fa.numRegs * 32 + 255) / 256 * 256) * (threads / 32);      // allocation granularity: 256 regs per warp
+  int n = 65536 / std::max(regs_per_cta, 1);
+  n = std::min<int>(n, (int)((227 * 1024) / (dyn_smem + fa.sharedSizeBytes + 1024)));
+  n = std::min(n, 64 / (threads / 32));
+  n = std::min(n, 512 / std::max(tmem_cols, 32));
+  return std::max(n, 1);
+}
+
 int pick_tt(int L) {
   for (int tt = 128; tt >= 1; tt >>= 1)
     if (L % tt == 0) return tt;
@@ -502,15 +540,22 @@ int pick_bn(int cout) {
 }
 
 template <int BN, int BK, int STAGES>
-int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcArgs& a, long long m_tiles, cudaStream_t st) {
+int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, long long m_tiles, cudaStream_t st) {
   using SL = SmemLayout<BN, BK, STAGES>;
+  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES>;
   static bool attr_set = false;
+  static int per_sm = 1;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+    per_sm = resident_ctas((const void*)kern, NUM_THREADS, SL::TOTAL, 2 * BN);
     attr_set = true;
   }
-  conv_gemm_tc_kernel<BN, BK, STAGES><<<(unsigned)(m_tiles * a.n_tiles), NUM_THREADS, SL::TOTAL, st>>>(tmA, tmW, a);
+  a.num_tiles = (int)(m_tiles * a.n_tiles);
+  const int grid = std::min(a.num_tiles, num_sms() * per_sm);           // persistent: exactly the co-resident CTAs
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "ring<%d,%d,%d> tiles %d per_sm %d grid %d\n", BN, BK, STAGES, a.num_tiles, per_sm, grid);
+  kern<<<grid, NUM_THREADS, SL::TOTAL, st>>>(tmA, tmW, a);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -542,15 +587,23 @@ bool window_eligible(const conan_conv_params_t& p) {
   return window_smem_bytes(p) <= 200 * 1024;
 }
 
+// Persistent launch: the grid is exactly the number of CTAs that can be co-resident (queried from the
+// occupancy calculator for this kernel / block size / dynamic smem), so the static round-robin tile
+// schedule never leaves a second, partial wave.
 template <int C, int BN, int NEPI>
-int launch_window_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const WinArgs& a, int grid, size_t smem, cudaStream_t st) {
+int launch_window_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const WinArgs& a, size_t smem, cudaStream_t st) {
+  auto kern = conv_window_tc_kernel<C, BN, WIN_NBUF, NEPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_window_tc_kernel<C, BN, WIN_NBUF, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
-  conv_window_tc_kernel<C, BN, WIN_NBUF, NEPI><<<grid, 64 + 128 * NEPI, smem, st>>>(tmA, tmW, a);
+  const int per_sm = resident_ctas((const void*)kern, 64 + 128 * NEPI, smem, 2 * BN);
+  const int grid = std::min(a.num_tiles, num_sms() * per_sm);
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "window<%d,%d,%d> k %d tiles %d smem %zu per_sm %d grid %d\n", C, BN, NEPI, a.k, a.num_tiles, smem, per_sm, grid);
+  kern<<<grid, 64 + 128 * NEPI, smem, st>>>(tmA, tmW, a);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -571,19 +624,18 @@ int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
               p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0};
   const size_t smem = window_smem_bytes(p);
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm > 4) per_sm = 4;
-  if (per_sm < 1) per_sm = 1;
-  const int grid = std::min(a.num_tiles, num_sms() * per_sm);
-  if (per_sm >= 2) {
-    if (C == 32) return launch_window_variant<32, 32, 1>(tmA, tmW, a, grid, smem, st);
-    return launch_window_variant<64, 64, 1>(tmA, tmW, a, grid, smem, st);
+  // one epilogue warpgroup per CTA when several CTAs fit on an SM, two when the resident weights leave room for one
+  if ((227 * 1024) / (smem + 1024) >= 2) {
+    if (C == 32) return launch_window_variant<32, 32, 1>(tmA, tmW, a, smem, st);
+    return launch_window_variant<64, 64, 1>(tmA, tmW, a, smem, st);
   }
-  if (C == 32) return launch_window_variant<32, 32, 2>(tmA, tmW, a, grid, smem, st);
-  return launch_window_variant<64, 64, 2>(tmA, tmW, a, grid, smem, st);
+  if (C == 32) return launch_window_variant<32, 32, 2>(tmA, tmW, a, smem, st);
+  return launch_window_variant<64, 64, 2>(tmA, tmW, a, smem, st);
 }
 
 }  // namespace
+
+bool conv_gemm_tc_uses_window(const conan_conv_params_t& p) { return conv_gemm_tc_eligible(p) && window_eligible(p); }
 
 bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
   if (!p.x_is_half) return false;
@@ -626,10 +678,13 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
               p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0};
   const int NS = TILE_M / TT;
   const long long m_tiles = (long long)((p.n_streams + NS - 1) / NS) * (p.L / TT);
+  // Few CTAs and a long K loop (the Emformer / Conan GEMMs: M = 4..6 rows x streams): one CTA per SM anyway, so
+  // spend the shared memory on pipeline depth instead of co-residency.
+  const bool deep = m_tiles * a.n_tiles <= 2 * num_sms() && a.kblocks >= 12;
   if (BK == 64) {
-    if (BN == 128) return launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
-    if (BN == 64) return launch_variant<64, 64, 2>(tmA, tmW, a, m_tiles, st);
-    return launch_variant<32, 64, 2>(tmA, tmW, a, m_tiles, st);
+    if (BN == 128) return deep ? launch_variant<128, 64, 6>(tmA, tmW, a, m_tiles, st) : launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
+    if (BN == 64) return deep ? launch_variant<64, 64, 8>(tmA, tmW, a, m_tiles, st) : launch_variant<64, 64, 2>(tmA, tmW, a, m_tiles, st);
+    return deep ? launch_variant<32, 64, 8>(tmA, tmW, a, m_tiles, st) : launch_variant<32, 64, 2>(tmA, tmW, a, m_tiles, st);
   }
   if (BN == 128) return launch_variant<128, 32, 3>(tmA, tmW, a, m_tiles, st);
   if (BN == 64) return launch_variant<64, 32, 3>(tmA, tmW, a, m_tiles, st);

@@ -94,7 +94,7 @@ struct conan_engine {
   int* qSlots = nullptr;
   // ---- optional per-launch event timing of the conv engines (bench.py's roofline leg)
   bool profiling = false;
-  struct ProfRec { cudaEvent_t a, b; int cat; double flops; };
+  struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
   mutable std::vector<ProfRec> prof;
   // ---- host-call staging
   int* hIds = nullptr; float* hChunk = nullptr; float* hWav = nullptr; float* hMel = nullptr; int* hTok = nullptr; int* hIdsSmall = nullptr;
@@ -288,8 +288,19 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
   if (p.x_split && !tc) { set_error("internal: split-fp16 operand on a shape the tcgen05 engine cannot run"); return 1; }
   if (!e->profiling) return tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
   conan_engine::ProfRec r;
-  r.cat = tc ? 1 : 0;
+  // categories: 0 FFMA, 1 tcgen05 ring kernel (vocoder), 2 tcgen05 window kernel, 3 tcgen05 ring kernel with split operands
+  r.cat = !tc ? 0 : (p.x_split ? 3 : (conv_gemm_tc_uses_window(p) ? 2 : 1));
   r.flops = 2.0 * (double)p.n_streams * p.L * p.cout * p.k * p.cin;
+  {
+    // algorithmic HBM bytes of the launch: input rows once, weights once, residual / old output read, outputs written
+    const double esz = p.x_is_half ? 2.0 : 4.0, rows_out = (double)p.n_streams * p.L;
+    double b = (double)p.n_streams * (p.L + (p.k - 1) * p.dil) * p.cin * esz * (p.x_split ? 2 : 1);
+    b += (double)p.cout * p.k * p.cin * esz * (p.x_split ? 3 : 1);
+    if (p.res) b += rows_out * p.cout * 4 * (p.res_row_stride ? 1.0 : 1.0 / p.L);
+    if (p.y) b += rows_out * p.cout * 4 * (p.accumulate ? 2 : 1);
+    if (p.y2) b += rows_out * p.cout * (p.y2_is_half ? 2.0 : 4.0) * (p.y2_split ? 2 : 1);
+    r.bytes = b;
+  }
   CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
   CONAN_CUDA_OK(cudaEventRecord(r.a, st));
   int rc = tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
@@ -900,19 +911,20 @@ int conan_engine_set_profiling(conan_engine_t* e, int enabled) {
   return 0;
 }
 
-int conan_engine_profile_read(conan_engine_t* e, int category, double* ms, uint64_t* launches, double* flops) {
+int conan_engine_profile_read(conan_engine_t* e, int category, double* ms, uint64_t* launches, double* flops, double* bytes) {
   if (!e) { set_error("null engine"); return 1; }
   CONAN_CUDA_OK(cudaDeviceSynchronize());
-  double t = 0, f = 0; uint64_t n = 0;
+  double t = 0, f = 0, b = 0; uint64_t n = 0;
   for (auto& r : e->prof) {
     if (r.cat != category) continue;
     float dt = 0.f;
     CONAN_CUDA_OK(cudaEventElapsedTime(&dt, r.a, r.b));
-    t += dt; f += r.flops; ++n;
+    t += dt; f += r.flops; b += r.bytes; ++n;
   }
   if (ms) *ms = t;
   if (launches) *launches = n;
   if (flops) *flops = f;
+  if (bytes) *bytes = b;
   return 0;
 }
 

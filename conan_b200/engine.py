@@ -201,10 +201,11 @@ class Engine:
         _lib.check(self.lib.conan_engine_set_profiling(self.h, int(enabled)), "set_profiling")
 
     def profile_read(self, category: int):
-        """category 0 = FFMA conv engine, 1 = tcgen05 conv engine -> (ms, launches, algorithmic flops)."""
-        ms, n, fl = C.c_double(), C.c_uint64(), C.c_double()
-        _lib.check(self.lib.conan_engine_profile_read(self.h, category, C.byref(ms), C.byref(n), C.byref(fl)), "profile_read")
-        return ms.value, n.value, fl.value
+        """category 0 FFMA, 1 tcgen05 ring (fp16), 2 tcgen05 window, 3 tcgen05 ring (split fp16)
+        -> (ms, launches, algorithmic flops, algorithmic bytes)."""
+        ms, n, fl, by = C.c_double(), C.c_uint64(), C.c_double(), C.c_double()
+        _lib.check(self.lib.conan_engine_profile_read(self.h, category, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)), "profile_read")
+        return ms.value, n.value, fl.value, by.value
 
     # ------------------------------------------------------------------ debug
     def debug_read(self, name: str, slot: int) -> torch.Tensor:

@@ -149,12 +149,13 @@ int conan_step_host(conan_engine_t* eng, int n, const int32_t* slot_ids_host, co
 /* kernels launched by this engine since creation (bench.py's gpu_launches claim) */
 uint64_t conan_engine_launch_count(const conan_engine_t* eng);
 
-/* Per-launch CUDA-event timing of the two conv engines (measurement only: events are recorded on the
- * launching stream around every conv launch while enabled).  category 0 = FFMA, 1 = tcgen05.
- * profile_read synchronises the device and returns the summed kernel time, launch count and
- * algorithmic FLOPs (2*M*N*K) since profiling was (re-)enabled. */
+/* Per-launch CUDA-event timing of the conv engines (measurement only: events are recorded on the
+ * launching stream around every conv launch while enabled).  category 0 = FFMA, 1 = tcgen05 ring kernel
+ * (fp16 operands), 2 = tcgen05 window kernel, 3 = tcgen05 ring kernel with split-fp16 operands.
+ * profile_read synchronises the device and returns the summed kernel time, launch count, algorithmic
+ * FLOPs (2*M*N*K) and algorithmic HBM bytes since profiling was (re-)enabled. */
 int conan_engine_set_profiling(conan_engine_t* eng, int enabled);
-int conan_engine_profile_read(conan_engine_t* eng, int category, double* ms, uint64_t* launches, double* flops);
+int conan_engine_profile_read(conan_engine_t* eng, int category, double* ms, uint64_t* launches, double* flops, double* bytes);
 
 /* Debug/test access: copy a named internal per-slot tensor (fp32) of one slot to the
  * device buffer.  Returns the element count through *numel. Names: "style", "kv_cache",
