@@ -131,14 +131,17 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 
 // Fused epilogue of one accumulator row (thread = tile row = TMEM lane): waits for the accumulator,
 // then per 16-column chunk: bias, scale, activation, residual, mask, 1/3-scale (+ old output), fp32
-// store and/or activated fp16 store.  Activations on this engine are none / relu / leaky, expressed
-// branch-free as v > 0 ? v : v * slope with slope 1 (none), 0 (relu) or the leaky slope.  The residual
-// (fp32 stream) does not depend on the accumulator: its first chunk is fetched BEFORE the wait and
-// chunk c+1 while chunk c is finished, so its HBM latency overlaps the tensor work.  16 columns per
-// step keeps the kernel under 64 registers.
+// store and/or activated fp16 store.  Activations on this engine are none / relu / leaky (branch-free:
+// v > 0 ? v : v * slope with slope 1, 0 or the leaky slope) or exact-erf GELU (warp-uniform branch).
+// Latency hiding: the bias comes from shared memory (staged once per CTA); the residual (fp32 stream)
+// does not depend on the accumulator, so PF chunks of it are fetched BEFORE the accumulator wait and the
+// window is kept PF chunks ahead -- for BN <= 64 that is the whole row, i.e. every HBM load of the tile is
+// in flight at once.
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane_base, int nbase, bool valid, int slot, int t,
-                                              uint64_t* acc_full_bar, uint32_t parity) {
+__device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
+                                              bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+  constexpr int NCH = BN / 16;
+  constexpr int PF = NCH < 4 ? NCH : 4;                // chunks of residual in flight (4 x 4 float4 = 64 registers at most)
   const float rm = (e.rowmask && valid) ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
   const float* resp = (e.res && valid) ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
   float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
@@ -148,26 +151,28 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane
   const float s1 = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.slope);
   const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);
   const float f = rm * e.out_scale;
-  float4 rcur[4], rnext[4];
+  float4 rbuf[PF][4];
   auto fetch_res = [&](float4 (&dst)[4], int c0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  fetch_res(rcur, 0);
+#pragma unroll
+  for (int c = 0; c < PF; ++c) fetch_res(rbuf[c], c * 16);
   mbar_wait(acc_full_bar, parity);
   tc_fence_after();
 #pragma unroll
-  for (int c0 = 0; c0 < BN; c0 += 16) {
-    if (c0 + 16 < BN) fetch_res(rnext, c0 + 16);
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = ch * 16;
     uint32_t acc[16];
     tc_ld_32x32b_x16(tmem_lane_base + (uint32_t)c0, acc);
     float v[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + nbase + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nbase + c0 + 4 * i);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-      const float rr[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
+      const float4 r4 = rbuf[ch % PF][i];
+      const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float x = fmaf(__uint_as_float(acc[4 * i + u]), e.acc_scale, bb[u]) * e.scale;
@@ -176,6 +181,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane
         v[4 * i + u] = (x + rr[u]) * f;
       }
     }
+    if (ch + PF < NCH) fetch_res(rbuf[ch % PF], (ch + PF) * 16);
     if (yp) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -200,9 +206,12 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, uint32_t tmem_lane
         if (e.y2_lo_off) *(reinterpret_cast<uint4*>(y2p + e.y2_lo_off + c0) + i) = *reinterpret_cast<uint4*>(l);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
   }
+}
+
+// stage the bias (or zeros) of all `cout` output channels in shared memory, once per CTA
+__device__ __forceinline__ void stage_bias(float* s_bias, const float* bias, int cout) {
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = bias ? bias[i] : 0.f;
 }
 
 template <int BN, int BK, int STAGES>
@@ -210,11 +219,12 @@ struct SmemLayout {
   static constexpr int A_BYTES = TILE_M * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/;
+  static constexpr int BIAS_BYTES = 2048 * 4;           // bias of up to 2048 output channels
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/ + BIAS_BYTES;
 };
 
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 5)
+__global__ void __launch_bounds__(NUM_THREADS, BN >= 128 ? 2 : (BN >= 64 ? 3 : 4))
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
   using SL = SmemLayout<BN, BK, STAGES>;
   constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
@@ -226,6 +236,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* acc_full = empty_bar + STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * SL::STAGE_BYTES + 256);
+  stage_bias(s_bias, a.e.bias, a.cout);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // a tile is NS = 128/TT consecutive streams x TT consecutive time steps: one rectangular TMA box.
@@ -311,8 +323,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t aph = (it >> 1) & 1;
       const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
       const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
-      epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), nt * BN, stream < a.n_streams, stream, t,
-                        &acc_full[ab], aph);
+      epilogue_rows<BN>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), nt * BN, stream < a.n_streams,
+                        stream, t, &acc_full[ab], aph);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
     }
@@ -349,7 +361,7 @@ struct WinArgs {
 // the 128-byte and the 64-byte swizzle.
 
 template <int C, int BN, int NBUF, int NEPI>
-__global__ void __launch_bounds__(64 + 128 * NEPI, NEPI == 1 ? 4 : 1)
+__global__ void __launch_bounds__(64 + 128 * NEPI, (NEPI == 1 && C == 32) ? 4 : 1)
 conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, WinArgs a) {
   constexpr int ROWB = C * 2;                       // bytes per row = swizzle span (64 or 128)
   constexpr int TAPB = BN * ROWB;                   // one tap of the weight matrix
@@ -366,6 +378,8 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* acc_full = a_empty + NBUF;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);
+  stage_bias(s_bias, a.e.bias, BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -438,7 +452,7 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int si = g / a.tiles_per_stream, t0 = (g - si * a.tiles_per_stream) * TILE_M;
-      epilogue_rows<BN>(a.e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), 0, true, si, t0 + r,
+      epilogue_rows<BN>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), 0, true, si, t0 + r,
                         &acc_full[ab], aph);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
@@ -576,7 +590,7 @@ size_t window_smem_bytes(const conan_conv_params_t& p) {
   const int rowb = p.cin * 2, tapb = p.cout * rowb;
   const int win_rows = TILE_M + (p.k - 1) * p.dil;
   const size_t winb = ((size_t)win_rows * rowb + 1023) & ~(size_t)1023;
-  return (((size_t)p.k * tapb + 1023) & ~(size_t)1023) + WIN_NBUF * winb + 1024 + 256;
+  return (((size_t)p.k * tapb + 1023) & ~(size_t)1023) + WIN_NBUF * winb + 1024 + 512;      // + alignment slack, barriers, bias
 }
 
 bool window_eligible(const conan_conv_params_t& p) {
