@@ -29,7 +29,7 @@ class ConanConfig(C.Structure):
         ("voc_up_kernels", C.c_int32 * 8), ("voc_n_res", C.c_int32), ("voc_res_kernels", C.c_int32 * 8),
         ("voc_res_dilations", C.c_int32 * 8), ("voc_n_dil", C.c_int32),
         ("voc_precision", C.c_int32), ("voc_use_tensor_cores", C.c_int32), ("voc_group", C.c_int32),
-        ("lin_use_tensor_cores", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("voc_residual_from_ctx", C.c_int32), ("lin_use_tensor_cores", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -48,6 +48,7 @@ class ConvParams(C.Structure):
         ("y2_is_half", C.c_int32), ("act2", C.c_int32), ("slope2", C.c_float),
         ("x_split", C.c_int32), ("x_lo_slot_off", C.c_int64), ("acc_scale", C.c_float),
         ("y2_split", C.c_int32), ("y2_lo_off", C.c_int64),
+        ("res_is_half", C.c_int32), ("res_inv_slope", C.c_float),
     ]
 
 

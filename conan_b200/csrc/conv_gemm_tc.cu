@@ -38,11 +38,12 @@ constexpr int NUM_THREADS = 192;
 
 struct TcEpi {
   const float* bias; float scale; int act; float slope;
-  const float* res; long long res_slot_stride; int res_row_stride;
+  const void* res; long long res_slot_stride; int res_row_stride;      // fp32 stream, or fp16 activated context rows (res_is_half)
   const float* rowmask; int mask_slot_stride; float out_scale;
   float* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
   __half* y2; long long y2_slot_stride; int y2_row_stride, y2_row0; int act2; float slope2;
   float acc_scale; long long y2_lo_off;      // y2_lo_off != 0: y2 is a split fp16 pair (hi, lo = fp16(v - hi))
+  int res_is_half; float res_inv_slope;      // residual = inverse-LeakyReLU of the fp16 rows the producer wrote for the next conv
 };
 
 struct TcArgs {
@@ -137,13 +138,17 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 // does not depend on the accumulator, so PF chunks of it are fetched BEFORE the accumulator wait and the
 // window is kept PF chunks ahead -- for BN <= 64 that is the whole row, i.e. every HBM load of the tile is
 // in flight at once.
-template <int BN>
-__device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
-                                              bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+enum ResKind : int { RES_NONE = 0, RES_F32 = 1, RES_F16 = 2 };
+
+template <int BN, int RK>
+__device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
+                                                bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
   constexpr int NCH = BN / 16;
   constexpr int PF = NCH < 4 ? NCH : 4;                // chunks of residual in flight (4 x 4 float4 = 64 registers at most)
   const float rm = (e.rowmask && valid) ? e.rowmask[(long long)slot * e.mask_slot_stride + t] : 1.f;
-  const float* resp = (e.res && valid) ? e.res + (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase : nullptr;
+  const long long res_off = (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase;
+  const float* resp = (RK == RES_F32 && valid) ? reinterpret_cast<const float*>(e.res) + res_off : nullptr;
+  const __half* resh = (RK == RES_F16 && valid) ? reinterpret_cast<const __half*>(e.res) + res_off : nullptr;
   float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
   __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
   const bool acc_old = e.accumulate && yp;
@@ -151,14 +156,24 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __res
   const float s1 = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.slope);
   const float s2 = e.act2 == ACT_NONE ? 1.f : (e.act2 == ACT_RELU ? 0.f : e.slope2);
   const float f = rm * e.out_scale;
-  float4 rbuf[PF][4];
-  auto fetch_res = [&](float4 (&dst)[4], int c0) {
+  constexpr int RW = RK == RES_F32 ? 4 : (RK == RES_F16 ? 2 : 1);     // 16-byte registers per chunk of residual
+  float4 rbuf[PF][RW];
+  // 16 residual values of a chunk: four float4 (fp32 stream) or two 16-byte loads of halfs
+  auto fetch_res = [&](float4 (&dst)[RW], int c0) {
+    if (RK == RES_F16) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < RW; ++i)
+        dst[i] = resh ? *(reinterpret_cast<const float4*>(resh + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (RK == RES_F32) {
+#pragma unroll
+      for (int i = 0; i < RW; ++i)
+        dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   };
+  if (RK != RES_NONE) {
 #pragma unroll
-  for (int c = 0; c < PF; ++c) fetch_res(rbuf[c], c * 16);
+    for (int c = 0; c < PF; ++c) fetch_res(rbuf[c], c * 16);
+  }
   mbar_wait(acc_full_bar, parity);
   tc_fence_after();
 #pragma unroll
@@ -171,8 +186,18 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __res
     for (int i = 0; i < 4; ++i) {
       const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nbase + c0 + 4 * i);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-      const float4 r4 = rbuf[ch % PF][i];
-      const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+      float rr[4] = {0.f, 0.f, 0.f, 0.f};
+      if (RK == RES_F16) {                                   // halfs 4i .. 4i+3 of the chunk, LeakyReLU undone
+        const __half2* hp = reinterpret_cast<const __half2*>(&rbuf[ch % PF][(i >> 1) % RW]) + (i & 1) * 2;
+        const float2 a = __half22float2(hp[0]), b = __half22float2(hp[1]);
+        rr[0] = a.x; rr[1] = a.y; rr[2] = b.x; rr[3] = b.y;
+        const float inv = e.res_inv_slope != 0.f ? e.res_inv_slope : 1.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rr[u] = rr[u] < 0.f ? rr[u] * inv : rr[u];
+      } else if (RK == RES_F32) {
+        const float4 r4 = rbuf[ch % PF][i % RW];
+        rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float x = fmaf(__uint_as_float(acc[4 * i + u]), e.acc_scale, bb[u]) * e.scale;
@@ -181,7 +206,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __res
         v[4 * i + u] = (x + rr[u]) * f;
       }
     }
-    if (ch + PF < NCH) fetch_res(rbuf[ch % PF], (ch + PF) * 16);
+    if (RK != RES_NONE && ch + PF < NCH) fetch_res(rbuf[ch % PF], (ch + PF) * 16);
     if (yp) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -207,6 +232,15 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __res
       }
     }
   }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
+                                              bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+  // one lean instantiation per residual kind (warp-uniform dispatch)
+  if (!e.res) epilogue_rows_k<BN, RES_NONE>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
+  else if (e.res_is_half) epilogue_rows_k<BN, RES_F16>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
+  else epilogue_rows_k<BN, RES_F32>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
 }
 
 // stage the bias (or zeros) of all `cout` output channels in shared memory, once per CTA
@@ -636,7 +670,8 @@ int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
   a.tiles_per_stream = p.L / TILE_M; a.num_tiles = p.n_streams * a.tiles_per_stream;
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
-              p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0};
+              p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0,
+              p.res_is_half, p.res_inv_slope};
   const size_t smem = window_smem_bytes(p);
   // one epilogue warpgroup per CTA when several CTAs fit on an SM, two when the resident weights leave room for one
   if ((227 * 1024) / (smem + 1024) >= 2) {
@@ -661,7 +696,7 @@ bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
   if (p.act == ACT_TANH || p.act2 > ACT_LRELU) return false;          // none / relu / leaky / gelu (first), none / relu / leaky (second)
   if (p.y2_split && (!p.y2 || p.y2_lo_off % 8)) return false;
   if (p.y && (p.y_slot_stride % 4 || p.y_row_stride % 4)) return false;
-  if (p.res && (p.res_slot_stride % 4 || p.res_row_stride % 4)) return false;
+  if (p.res && (p.res_slot_stride % 8 || p.res_row_stride % 8 || ((uintptr_t)p.res) % 16)) return false;
   if (p.y2 && (p.y2_slot_stride % 8 || p.y2_row_stride % 8)) return false;
   if (((uintptr_t)p.x) % 128 || ((uintptr_t)p.w) % 128) return false;
   return true;
@@ -689,7 +724,8 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   a.kblocks = Ktot / BK; a.n_tiles = p.cout / BN; a.nseg = nseg; a.lo_slot_off = (int)p.x_lo_slot_off;
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
-              p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0};
+              p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0,
+              p.res_is_half, p.res_inv_slope};
   const int NS = TILE_M / TT;
   const long long m_tiles = (long long)((p.n_streams + NS - 1) / NS) * (p.L / TT);
   // Few CTAs and a long K loop (the Emformer / Conan GEMMs: M = 4..6 rows x streams): one CTA per SM anyway, so

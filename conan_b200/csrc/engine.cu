@@ -585,6 +585,8 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
 int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float* wav_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
   const float sl = 0.1f;
+  // from_ctx: x_j is not kept as an fp32 stream; conv c2_j reads it back from lrelu(x_j), the rows conv c1_j consumed
+  const bool from_ctx = c.voc_residual_from_ctx != 0;
   TRY(launch_hist_gather(e->histVoc, e->nHistVoc, n, ids, st));
   TRY(launch_rows_to_view(mel, e->vPRE.new_rows(), n, nullptr, c.segment, c.n_mels, st));
   {
@@ -599,7 +601,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
       // conv -> pixel shuffle folded into the weight row order: output row t holds r_up consecutive
       // output frames, i.e. [i, L_in, r*C] viewed as [i, L_in*r, C]  (hifigan_causal.py:186-188)
       auto p = conv_on_ctx(e, e->vUP[i], c.voc_up_kernels[i], 1, e->P(u + "w"), e->F(u + "b"), r_up * C, n);
-      p.y = e->vXS; p.y_slot_stride = (long long)L * C; p.y_row_stride = r_up * C; p.y_row0 = 0;
+      if (!from_ctx) { p.y = e->vXS; p.y_slot_stride = (long long)L * C; p.y_row_stride = r_up * C; p.y_row0 = 0; }
       p.y2 = e->vXA[i].at_row(e->vXA[i].H); p.y2_slot_stride = e->vXA[i].slot_stride(); p.y2_row_stride = r_up * C; p.y2_row0 = 0;
       p.y2_is_half = e->vXA[i].is_half; p.act2 = ACT_LRELU; p.slope2 = sl;
       TRY(run_conv(e, p, st, e->cfg.voc_use_tensor_cores != 0));
@@ -618,12 +620,15 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
         TRY(run_conv(e, p1, st, e->cfg.voc_use_tensor_cores != 0));
         auto p2 = conv_on_ctx(e, e->vC2[i][r][j], k, 1, e->P(q + "c2." + std::to_string(j) + ".w"),
                               e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
-        res_rows(p2, xj, L, C);
+        if (from_ctx) {
+          p2.res = (const float*)in1.at_row(in1.H); p2.res_slot_stride = in1.slot_stride(); p2.res_row_stride = C;
+          p2.res_is_half = in1.is_half ? 1 : 0; p2.res_inv_slope = 1.0f / sl;
+        } else {
+          res_rows(p2, xj, L, C);
+        }
         if (j + 1 < c.voc_n_dil) {
-          float* xn = e->vXR[j & 1];
-          out_rows(p2, xn, L, C);
+          if (!from_ctx) { float* xn = e->vXR[j & 1]; out_rows(p2, xn, L, C); xj = xn; }
           out2_ctx(p2, e->vC1[i][r][j + 1], ACT_LRELU, sl);
-          xj = xn;
         } else {
           out_rows(p2, e->vSUM, L, C);
           p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)

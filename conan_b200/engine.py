@@ -20,7 +20,8 @@ PARTS_EMFORMER, PARTS_CONAN, PARTS_VOCODER, PARTS_ALL = 1, 2, 4, 7
 
 def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max_slots: int = 64,
                 max_ref_frames: int = 512, device: int = 0, voc_precision: str = "fp16",
-                voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None) -> _lib.ConanConfig:
+                voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None,
+                voc_residual_from_ctx: Optional[bool] = None) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -59,6 +60,9 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     cfg.voc_precision = {"fp32": 0, "fp16": 1}[voc_precision]
     cfg.voc_use_tensor_cores = int(bool(voc_tensor_cores) and cfg.voc_precision == 1)
     cfg.voc_group = voc_group
+    # fp16-operand vocoder: recover the resblock residual from the activated fp16 context rows (halves the HBM traffic of
+    # every second conv; costs 1.7 dB of the 59 dB SNR).  The fp32 vocoder keeps its fp32 residual stream.
+    cfg.voc_residual_from_ctx = int(cfg.voc_precision == 1 if voc_residual_from_ctx is None else bool(voc_residual_from_ctx))
     # Emformer / Conan contractions: split-fp16 tensor-core GEMMs (fp32-grade) by default whenever the tensor-core
     # vocoder is on; lin_tensor_cores=False keeps them on the exact-fp32 FFMA engine
     cfg.lin_use_tensor_cores = int(cfg.voc_use_tensor_cores if lin_tensor_cores is None else bool(lin_tensor_cores))

@@ -23,7 +23,7 @@ def conv_gemm(ctx: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
               scale: float = 1.0, act: str = "none", slope: float = 0.0, res: Optional[torch.Tensor] = None,
               rowmask: Optional[torch.Tensor] = None, out_scale: float = 1.0, y: Optional[torch.Tensor] = None,
               accumulate: bool = False, y2: Optional[torch.Tensor] = None, y2_row0: int = 0, act2: str = "none",
-              slope2: float = 0.0, x_split: bool = False, acc_scale: float = 1.0, y2_split: bool = False):
+              slope2: float = 0.0, x_split: bool = False, acc_scale: float = 1.0, y2_split: bool = False, res_inv_slope: float = 0.0):
     """ctx [slots, rows, cin] (fp32 or fp16), w_packed [cout, k*cin] (same dtype), bias [cout] fp32.
     y [slots, L, cout] fp32 (optional), y2 [slots, rows2, cout] fp32/fp16 written at rows y2_row0.. (optional),
     res [slots, L, cout] fp32 (optional), rowmask [slots, L] fp32 (optional)."""
@@ -45,8 +45,9 @@ def conv_gemm(ctx: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
     p.slot_ids, p.n_slots = _p(slot_ids), slots
     p.scale, p.act, p.slope = scale, ACT[act], slope
     if res is not None:
-        assert res.dtype == torch.float32 and res.shape == (slots, L, cout) and res.is_contiguous()
+        assert res.dtype in (torch.float32, torch.float16) and res.shape == (slots, L, cout) and res.is_contiguous()
         p.res, p.res_slot_stride, p.res_row_stride = _p(res), L * cout, cout
+        p.res_is_half, p.res_inv_slope = int(res.dtype == torch.float16), res_inv_slope
     if rowmask is not None:
         assert rowmask.dtype == torch.float32 and rowmask.shape == (slots, L)
         p.rowmask, p.mask_slot_stride = _p(rowmask), L

@@ -71,9 +71,12 @@ typedef struct conan_config {
   int32_t voc_precision;          /* 0: fp32 operands (FFMA);  1: fp16 operands, fp32 accumulate */
   int32_t voc_use_tensor_cores;   /* 1: tcgen05 implicit-GEMM kernels where eligible (needs voc_precision 1) */
   int32_t voc_group;              /* streams per vocoder pass (L2 blocking); 0 = all at once */
+  int32_t voc_residual_from_ctx;  /* 1: the vocoder's resblock residual x_j is recovered from the activated copy lrelu(x_j) that is the
+                                     next conv's input anyway (inverse LeakyReLU), so no separate fp32 residual stream is written or
+                                     read; 0: keep an fp32 residual stream (reference-grade path) */
   int32_t lin_use_tensor_cores;   /* 1: Emformer / Conan linear + conv contractions on tcgen05 with split-fp16 operands
                                      (x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, fp32 accumulate: fp32-grade results); 0: fp32 FFMA */
-  int32_t reserved[7];
+  int32_t reserved[6];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */
@@ -210,6 +213,10 @@ typedef struct conan_conv_params {
   float acc_scale;          /* v = (acc * acc_scale + bias) * scale ; 0 means 1 */
   int32_t y2_split;
   int64_t y2_lo_off;
+  /* residual read from an activated fp16/fp32 context buffer instead of an fp32 stream: res_is_half selects the
+   * element type of `res`; res_inv_slope != 0 undoes the LeakyReLU the producer applied (r = h >= 0 ? h : h * res_inv_slope). */
+  int32_t res_is_half;
+  float res_inv_slope;
 } conan_conv_params_t;
 
 /* engine: 0 = FFMA (fp32 accumulate on CUDA cores, fp32 or fp16 operands),

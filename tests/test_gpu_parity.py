@@ -155,6 +155,31 @@ def test_conv_gemm_tcgen05_vs_ffma_and_torch(cin, cout, k, dil, L, S):
     assert (outs["tc"][0][untouched] == 0).all()
 
 
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+@pytest.mark.parametrize("cin,cout,k,dil,L,S", [(64, 64, 7, 3, 640, 2), (128, 128, 3, 1, 160, 5), (32, 32, 11, 5, 1280, 1)])
+def test_conv_gemm_residual_from_activated_fp16_rows(cin, cout, k, dil, L, S):
+    """res given as fp16 lrelu(x) rows with the inverse slope: both engines must add x back (x = h >= 0 ? h : 10 h)."""
+    from conan_b200 import ops
+    from conan_b200.weights import pack_conv
+    g = torch.Generator().manual_seed(cin + k)
+    H = (k - 1) * dil
+    ctx = (torch.randn(S, H + L, cin, generator=g) * 0.5).half()
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).half()
+    b = torch.randn(cout, generator=g)
+    xres = torch.randn(S, L, cout, generator=g)
+    act = F.leaky_relu(xres, 0.1).half()
+    x_back = torch.where(act.float() >= 0, act.float(), act.float() * 10.0)
+    ref = _conv_reference(ctx.double(), w.double(), b.double(), k, dil, L, 0) + x_back.double()
+    outs = []
+    for engine in (ops.ENGINE_FFMA, ops.ENGINE_TC):
+        y = torch.zeros(S, L, cout, device="cuda")
+        ops.conv_gemm(ctx.cuda(), pack_conv(w).cuda(), b.cuda(), k=k, dil=dil, L=L, row0=0, engine=engine, res=act.cuda(),
+                      res_inv_slope=10.0, y=y)
+        outs.append(y.cpu())
+        assert (outs[-1].double() - ref).abs().max().item() < 1e-4
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-4
+
+
 SPLIT_SHAPES = [
     # cin, cout, k, L, S     (Emformer / Conan contractions in fp32-grade tensor-core mode; dims already padded to 32)
     (96, 256, 1, 6, 70), (96, 2048, 1, 6, 33), (2048, 96, 1, 6, 20), (96, 128, 1, 4, 50),
