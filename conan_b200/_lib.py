@@ -49,6 +49,8 @@ class ConvParams(C.Structure):
         ("x_split", C.c_int32), ("x_lo_slot_off", C.c_int64), ("acc_scale", C.c_float),
         ("y2_split", C.c_int32), ("y2_lo_off", C.c_int64),
         ("res_is_half", C.c_int32), ("res_inv_slope", C.c_float),
+        ("res2", C.c_void_p), ("res2_slot_stride", C.c_int64), ("res2_row_stride", C.c_int32), ("res2_is_half", C.c_int32),
+        ("y_is_half", C.c_int32),
     ]
 
 

@@ -42,9 +42,10 @@ struct EpiArgs {
   const float* bias; float scale; int act; float slope;
   const void* res; long long res_slot_stride; int res_row_stride;
   const float* rowmask; int mask_slot_stride; float out_scale;
-  float* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
+  void* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
   void* y2; long long y2_slot_stride; int y2_row_stride, y2_row0; int y2_is_half; int act2; float slope2;
   int res_is_half; float res_inv_slope;
+  const void* res2; long long res2_slot_stride; int res2_row_stride; int res2_is_half; int y_is_half;
 };
 
 template <typename T>
@@ -204,11 +205,20 @@ conv_gemm_ffma_kernel(const T* __restrict__ X, long long x_slot_stride, int x_ro
         if (e.res_inv_slope != 0.f && r < 0.f) r *= e.res_inv_slope;        // undo the producer's LeakyReLU
         v += r;
       }
+      if (e.res2) {
+        const long long ro = (long long)slot * e.res2_slot_stride + (long long)t * e.res2_row_stride + n;
+        v += e.res2_is_half ? __half2float(reinterpret_cast<const __half*>(e.res2)[ro]) : reinterpret_cast<const float*>(e.res2)[ro];
+      }
       v *= fsc;
       if (e.y) {
-        float* yp = e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + n;
-        if (e.accumulate) v += *yp;
-        *yp = v;
+        const long long yo = (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + n;
+        if (e.y_is_half) {
+          reinterpret_cast<__half*>(e.y)[yo] = __float2half_rn(v);
+        } else {
+          float* yp = reinterpret_cast<float*>(e.y) + yo;
+          if (e.accumulate) v += *yp;
+          *yp = v;
+        }
       }
       if (e.y2) {
         float v2 = v > 0.f ? v : v * s2;
@@ -229,7 +239,8 @@ int launch_conv_gemm_ffma(const conan_conv_params_t& p, cudaStream_t st) {
   if (p.n_streams <= 0) return 0;
   EpiArgs e{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask,
             p.mask_slot_stride, p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate,
-            p.y2, p.y2_slot_stride, p.y2_row_stride, p.y2_row0, p.y2_is_half, p.act2, p.slope2, p.res_is_half, p.res_inv_slope};
+            p.y2, p.y2_slot_stride, p.y2_row_stride, p.y2_row0, p.y2_is_half, p.act2, p.slope2, p.res_is_half, p.res_inv_slope,
+            p.res2, p.res2_slot_stride, p.res2_row_stride, p.res2_is_half, p.y_is_half};
   long long M = (long long)p.n_streams * p.L;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((p.cout + BN - 1) / BN));
   if (p.x_is_half)

@@ -40,10 +40,12 @@ struct TcEpi {
   const float* bias; float scale; int act; float slope;
   const void* res; long long res_slot_stride; int res_row_stride;      // fp32 stream, or fp16 activated context rows (res_is_half)
   const float* rowmask; int mask_slot_stride; float out_scale;
-  float* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
+  void* y; long long y_slot_stride; int y_row_stride, y_row0; int accumulate;
   __half* y2; long long y2_slot_stride; int y2_row_stride, y2_row0; int act2; float slope2;
   float acc_scale; long long y2_lo_off;      // y2_lo_off != 0: y2 is a split fp16 pair (hi, lo = fp16(v - hi))
   int res_is_half; float res_inv_slope;      // residual = inverse-LeakyReLU of the fp16 rows the producer wrote for the next conv
+  const __half* res2; long long res2_slot_stride; int res2_row_stride;   // second fp16 residual (running MRF sum), RES_F16 path only
+  int y_is_half;
 };
 
 struct TcArgs {
@@ -149,7 +151,11 @@ __device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __r
   const long long res_off = (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase;
   const float* resp = (RK == RES_F32 && valid) ? reinterpret_cast<const float*>(e.res) + res_off : nullptr;
   const __half* resh = (RK == RES_F16 && valid) ? reinterpret_cast<const __half*>(e.res) + res_off : nullptr;
-  float* yp = (e.y && valid) ? e.y + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase : nullptr;
+  const long long y_off = (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase;
+  float* yp = (e.y && valid && !e.y_is_half) ? reinterpret_cast<float*>(e.y) + y_off : nullptr;
+  __half* yh = (e.y && valid && e.y_is_half) ? reinterpret_cast<__half*>(e.y) + y_off : nullptr;
+  const __half* res2p = (RK == RES_F16 && e.res2 && valid)
+                            ? e.res2 + (long long)slot * e.res2_slot_stride + (long long)t * e.res2_row_stride + nbase : nullptr;
   __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
   const bool acc_old = e.accumulate && yp;
   const bool gelu = e.act == ACT_GELU;
@@ -158,6 +164,7 @@ __device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __r
   const float f = rm * e.out_scale;
   constexpr int RW = RK == RES_F32 ? 4 : (RK == RES_F16 ? 2 : 1);     // 16-byte registers per chunk of residual
   float4 rbuf[PF][RW];
+  float4 r2buf[RK == RES_F16 ? PF : 1][2];                   // second residual (fp16 running sum), same look-ahead
   // 16 residual values of a chunk: four float4 (fp32 stream) or two 16-byte loads of halfs
   auto fetch_res = [&](float4 (&dst)[RW], int c0) {
     if (RK == RES_F16) {
@@ -170,9 +177,17 @@ __device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __r
         dst[i] = resp ? *(reinterpret_cast<const float4*>(resp + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
+  auto fetch_res2 = [&](float4 (&dst)[2], int c0) {
+    dst[0] = *(reinterpret_cast<const float4*>(res2p + c0));
+    dst[1] = *(reinterpret_cast<const float4*>(res2p + c0) + 1);
+  };
   if (RK != RES_NONE) {
 #pragma unroll
     for (int c = 0; c < PF; ++c) fetch_res(rbuf[c], c * 16);
+    if (RK == RES_F16 && res2p) {
+#pragma unroll
+      for (int c = 0; c < PF; ++c) fetch_res2(r2buf[c], c * 16);
+    }
   }
   mbar_wait(acc_full_bar, parity);
   tc_fence_after();
@@ -194,6 +209,11 @@ __device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __r
         const float inv = e.res_inv_slope != 0.f ? e.res_inv_slope : 1.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) rr[u] = rr[u] < 0.f ? rr[u] * inv : rr[u];
+        if (res2p) {
+          const __half2* sp = reinterpret_cast<const __half2*>(&r2buf[ch % PF][i >> 1]) + (i & 1) * 2;
+          const float2 c = __half22float2(sp[0]), d = __half22float2(sp[1]);
+          rr[0] += c.x; rr[1] += c.y; rr[2] += d.x; rr[3] += d.y;
+        }
       } else if (RK == RES_F32) {
         const float4 r4 = rbuf[ch % PF][i % RW];
         rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
@@ -206,7 +226,19 @@ __device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __r
         v[4 * i + u] = (x + rr[u]) * f;
       }
     }
-    if (RK != RES_NONE && ch + PF < NCH) fetch_res(rbuf[ch % PF], (ch + PF) * 16);
+    if (RK != RES_NONE && ch + PF < NCH) {
+      fetch_res(rbuf[ch % PF], (ch + PF) * 16);
+      if (RK == RES_F16 && res2p) fetch_res2(r2buf[ch % PF], (ch + PF) * 16);
+    }
+    if (yh) {                                                // fp16 primary output (running MRF sum)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __half2 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(v[8 * i + 2 * u], v[8 * i + 2 * u + 1]);
+        *(reinterpret_cast<uint4*>(yh + c0) + i) = *reinterpret_cast<uint4*>(h);
+      }
+    }
     if (yp) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -395,7 +427,7 @@ struct WinArgs {
 // the 128-byte and the 64-byte swizzle.
 
 template <int C, int BN, int NBUF, int NEPI>
-__global__ void __launch_bounds__(64 + 128 * NEPI, (NEPI == 1 && C == 32) ? 4 : 1)
+__global__ void __launch_bounds__(64 + 128 * NEPI, NEPI == 1 ? (C == 32 ? 4 : 2) : 1)
 conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, WinArgs a) {
   constexpr int ROWB = C * 2;                       // bytes per row = swizzle span (64 or 128)
   constexpr int TAPB = BN * ROWB;                   // one tap of the weight matrix
@@ -671,7 +703,7 @@ int launch_conv_window_tc(const conan_conv_params_t& p, cudaStream_t st) {
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
               p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0,
-              p.res_is_half, p.res_inv_slope};
+              p.res_is_half, p.res_inv_slope, (const __half*)p.res2, p.res2_slot_stride, p.res2_row_stride, p.y_is_half};
   const size_t smem = window_smem_bytes(p);
   // one epilogue warpgroup per CTA when several CTAs fit on an SM, two when the resident weights leave room for one
   if ((227 * 1024) / (smem + 1024) >= 2) {
@@ -695,7 +727,9 @@ bool conv_gemm_tc_eligible(const conan_conv_params_t& p) {
   if (p.row0 < 0) return false;
   if (p.act == ACT_TANH || p.act2 > ACT_LRELU) return false;          // none / relu / leaky / gelu (first), none / relu / leaky (second)
   if (p.y2_split && (!p.y2 || p.y2_lo_off % 8)) return false;
-  if (p.y && (p.y_slot_stride % 4 || p.y_row_stride % 4)) return false;
+  if (p.y && (p.y_slot_stride % 8 || p.y_row_stride % 8)) return false;
+  if (p.res2 && (!p.res || !p.res_is_half || !p.res2_is_half || p.res2_slot_stride % 8 || p.res2_row_stride % 8)) return false;
+  if (p.y_is_half && p.accumulate) return false;
   if (p.res && (p.res_slot_stride % 8 || p.res_row_stride % 8 || ((uintptr_t)p.res) % 16)) return false;
   if (p.y2 && (p.y2_slot_stride % 8 || p.y2_row_stride % 8)) return false;
   if (((uintptr_t)p.x) % 128 || ((uintptr_t)p.w) % 128) return false;
@@ -725,7 +759,7 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   a.e = TcEpi{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
               p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
               p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0,
-              p.res_is_half, p.res_inv_slope};
+              p.res_is_half, p.res_inv_slope, (const __half*)p.res2, p.res2_slot_stride, p.res2_row_stride, p.y_is_half};
   const int NS = TILE_M / TT;
   const long long m_tiles = (long long)((p.n_streams + NS - 1) / NS) * (p.L / TT);
   // Few CTAs and a long K loop (the Emformer / Conan GEMMs: M = 4..6 rows x streams): one CTA per SM anyway, so

@@ -76,6 +76,7 @@ struct conan_engine {
   // ---- vocoder
   Ctx vPRE, vUP[8], vXA[8], vC1[8][4][4], vC2[8][4][4], vPOST;
   float *vXS = nullptr, *vXR[2] = {nullptr, nullptr}, *vSUM = nullptr;
+  __half* vSUMh = nullptr;       // running MRF sum as fp16 (residual-from-context mode)
   int vL[9], vC[9];     // rows / channels entering scale i (vL[0] = segment, vC[0] = initial channel)
   // ---- history gather/scatter tables
   HistDesc* histConan = nullptr; int nHistConan = 0;
@@ -296,8 +297,9 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
     const double esz = p.x_is_half ? 2.0 : 4.0, rows_out = (double)p.n_streams * p.L;
     double b = (double)p.n_streams * (p.L + (p.k - 1) * p.dil) * p.cin * esz * (p.x_split ? 2 : 1);
     b += (double)p.cout * p.k * p.cin * esz * (p.x_split ? 3 : 1);
-    if (p.res) b += rows_out * p.cout * 4 * (p.res_row_stride ? 1.0 : 1.0 / p.L);
-    if (p.y) b += rows_out * p.cout * 4 * (p.accumulate ? 2 : 1);
+    if (p.res) b += rows_out * p.cout * (p.res_is_half ? 2 : 4) * (p.res_row_stride ? 1.0 : 1.0 / p.L);
+    if (p.res2) b += rows_out * p.cout * (p.res2_is_half ? 2 : 4);
+    if (p.y) b += rows_out * p.cout * (p.y_is_half ? 2 : 4) * (p.accumulate ? 2 : 1);
     if (p.y2) b += rows_out * p.cout * (p.y2_is_half ? 2.0 : 4.0) * (p.y2_split ? 2 : 1);
     r.bytes = b;
   }
@@ -386,6 +388,7 @@ int allocate_state(conan_engine* e) {
   TRY(alloc_ctx(e, &e->vPOST, 6, e->vL[c.voc_n_ups], 0, e->vC[c.voc_n_ups], hf));
   TRY(dalloc(e, &e->vXS, (size_t)S * maxLC)); TRY(dalloc(e, &e->vXR[0], (size_t)S * maxLC));
   TRY(dalloc(e, &e->vXR[1], (size_t)S * maxLC)); TRY(dalloc(e, &e->vSUM, (size_t)S * maxLC));
+  TRY(dalloc(e, &e->vSUMh, (size_t)S * maxLC));
 
   // ---- history / zero tables
   auto build_tables = [&](std::vector<const Ctx*> ctxs, std::vector<HistDesc> extra, HistDesc** hist, int* nhist, ZeroDesc** zeros,
@@ -629,6 +632,16 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
         if (j + 1 < c.voc_n_dil) {
           if (!from_ctx) { float* xn = e->vXR[j & 1]; out_rows(p2, xn, L, C); xj = xn; }
           out2_ctx(p2, e->vC1[i][r][j + 1], ACT_LRELU, sl);
+        } else if (from_ctx && e->vXA[i].is_half) {
+          // MRF average (hifigan_causal.py:324-329) with the running sum carried in fp16: resblock 0 writes it, 1 adds to it,
+          // the last one only reads it and emits lrelu(sum / 3) into the next layer's context
+          if (r > 0) { p2.res2 = e->vSUMh; p2.res2_slot_stride = (long long)L * C; p2.res2_row_stride = C; p2.res2_is_half = 1; }
+          if (r < c.voc_n_res - 1) {
+            p2.y = (float*)e->vSUMh; p2.y_slot_stride = (long long)L * C; p2.y_row_stride = C; p2.y_row0 = 0; p2.y_is_half = 1;
+          } else {
+            p2.out_scale = 1.0f / (float)c.voc_n_res;
+            out2_ctx(p2, next, ACT_LRELU, sl);
+          }
         } else {
           out_rows(p2, e->vSUM, L, C);
           p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)

@@ -23,7 +23,8 @@ def conv_gemm(ctx: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
               scale: float = 1.0, act: str = "none", slope: float = 0.0, res: Optional[torch.Tensor] = None,
               rowmask: Optional[torch.Tensor] = None, out_scale: float = 1.0, y: Optional[torch.Tensor] = None,
               accumulate: bool = False, y2: Optional[torch.Tensor] = None, y2_row0: int = 0, act2: str = "none",
-              slope2: float = 0.0, x_split: bool = False, acc_scale: float = 1.0, y2_split: bool = False, res_inv_slope: float = 0.0):
+              slope2: float = 0.0, x_split: bool = False, acc_scale: float = 1.0, y2_split: bool = False, res_inv_slope: float = 0.0,
+              res2: Optional[torch.Tensor] = None):
     """ctx [slots, rows, cin] (fp32 or fp16), w_packed [cout, k*cin] (same dtype), bias [cout] fp32.
     y [slots, L, cout] fp32 (optional), y2 [slots, rows2, cout] fp32/fp16 written at rows y2_row0.. (optional),
     res [slots, L, cout] fp32 (optional), rowmask [slots, L] fp32 (optional)."""
@@ -52,9 +53,13 @@ def conv_gemm(ctx: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Te
         assert rowmask.dtype == torch.float32 and rowmask.shape == (slots, L)
         p.rowmask, p.mask_slot_stride = _p(rowmask), L
     p.out_scale = out_scale
+    if res2 is not None:
+        assert res2.dtype in (torch.float32, torch.float16) and res2.shape == (slots, L, cout) and res2.is_contiguous()
+        p.res2, p.res2_slot_stride, p.res2_row_stride, p.res2_is_half = _p(res2), L * cout, cout, int(res2.dtype == torch.float16)
     if y is not None:
-        assert y.dtype == torch.float32 and y.shape == (slots, L, cout) and y.is_contiguous()
+        assert y.dtype in (torch.float32, torch.float16) and y.shape == (slots, L, cout) and y.is_contiguous()
         p.y, p.y_slot_stride, p.y_row_stride, p.y_row0 = _p(y), L * cout, cout, 0
+        p.y_is_half = int(y.dtype == torch.float16)
     p.accumulate = int(accumulate)
     if y2 is not None and y2_split:      # y2 [2, slots, rows2, cout] fp16
         assert y2.dim() == 4 and y2.shape[0] == 2 and y2.dtype == torch.float16 and y2.is_contiguous()

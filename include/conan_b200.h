@@ -217,6 +217,13 @@ typedef struct conan_conv_params {
    * element type of `res`; res_inv_slope != 0 undoes the LeakyReLU the producer applied (r = h >= 0 ? h : h * res_inv_slope). */
   int32_t res_is_half;
   float res_inv_slope;
+  /* second residual (fp16 or fp32, added as is) and an fp16 primary output: the running MRF sum of the vocoder's
+   * three resblocks is carried as an fp16 tensor -- v += res2[slot*res2_slot_stride + t*res2_row_stride + n]. */
+  const void* res2;
+  int64_t res2_slot_stride;
+  int32_t res2_row_stride;
+  int32_t res2_is_half;
+  int32_t y_is_half;        /* y is __half* (no accumulate in that case: use res2) */
 } conan_conv_params_t;
 
 /* engine: 0 = FFMA (fp32 accumulate on CUDA cores, fp32 or fp16 operands),
