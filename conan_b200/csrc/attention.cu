@@ -33,9 +33,12 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
   const int past = past_len[slot];
   const int lc_len = min(lc, past);
   const int nkeys = rc + lc_len + seg;
-  float* sK = sm;                         // [nkeys][D]
-  float* sV = sK + (size_t)(rc + lc + seg) * D;
-  float* sQ = sV + (size_t)(rc + lc + seg) * D;   // [rows][D]
+  // rows are padded to D + 1 floats: lanes own keys, so an unpadded stride of 80 words would put every
+  // lane on one of two banks (16-way conflicts on every K/V read)
+  const int DS = D + 1;
+  float* sK = sm;                         // [nkeys][DS]
+  float* sV = sK + (size_t)(rc + lc + seg) * DS;
+  float* sQ = sV + (size_t)(rc + lc + seg) * DS;   // [rows][D]
   const float* q_in = qkv + (long long)blockIdx.x * rows * ldq;      // compact scratch: index i, row stride ldq
   float* rg = ring + (long long)slot * ring_rows * 2 * D;
   const int tid = threadIdx.x;
@@ -58,7 +61,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
       int r = rc + (key - rc - lc_len);
       kval = q_in[(long long)r * ldq + D + c]; vval = q_in[(long long)r * ldq + 2 * D + c];
     }
-    sK[idx] = kval; sV[idx] = vval;
+    sK[key * DS + c] = kval; sV[key * DS + c] = vval;
   }
   __syncthreads();
   // state update: ring rows (past + t) % ring_rows <- utterance K/V.  ring_rows >= lc + seg, so the
@@ -86,7 +89,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
         if (key < nkeys) {
           s = 0.f;
 #pragma unroll
-          for (int d = 0; d < EMF_MAX_HD; ++d) if (d < hd) s = fmaf(qv[d], sK[key * D + h * hd + d], s);
+          for (int d = 0; d < EMF_MAX_HD; ++d) if (d < hd) s = fmaf(qv[d], sK[key * DS + h * hd + d], s);
         }
         sc[kk] = s; mx = fmaxf(mx, s);
       }
@@ -109,7 +112,7 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
         if (key < nkeys) {
           float p = sc[kk] * inv;
 #pragma unroll
-          for (int d = 0; d < EMF_MAX_HD; ++d) if (d < hd) o[d] = fmaf(p, sV[key * D + h * hd + d], o[d]);
+          for (int d = 0; d < EMF_MAX_HD; ++d) if (d < hd) o[d] = fmaf(p, sV[key * DS + h * hd + d], o[d]);
         }
       }
 #pragma unroll
@@ -181,7 +184,7 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
   if (n <= 0) return 0;
   if (rc + lc + seg > EMF_MAX_KEYS || D / heads > EMF_MAX_HD) { set_error("emformer_attention: key count or head_dim above compiled limits"); return 1; }
   if (ring_rows < lc + seg) { set_error("emformer_attention: ring too short"); return 1; }
-  size_t sh = ((size_t)2 * (rc + lc + seg) * D + (size_t)(seg + rc) * D) * sizeof(float);
+  size_t sh = ((size_t)2 * (rc + lc + seg) * (D + 1) + (size_t)(seg + rc) * D) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; }
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }

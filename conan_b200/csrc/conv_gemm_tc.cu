@@ -93,6 +93,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// Programmatic dependent launch: the next tensor-core kernel of the step may start its prologue (barrier
+// init, TMEM allocation, bias staging, resident-weight TMA) while this one drains; it touches activations
+// only after pdl_wait(), which returns when every prerequisite grid has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -325,6 +330,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();                                  // activations of the previous layer are complete and visible from here on
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -464,12 +471,14 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(a.k * TAPB));
+      mbar_expect_tx(w_full, (uint32_t)(a.k * TAPB));                     // weights are constants: fetched before the dependency wait
       for (int j = 0; j < a.k; ++j) tma_load_2d(sW + j * TAPB, &tmW, w_full, j * C, 0);
+      pdl_wait();
       int it = 0;
       for (int g = blockIdx.x; g < a.num_tiles; g += gridDim.x, ++it) {
         const int buf = it % NBUF;
@@ -509,6 +518,7 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else {
     // ===================================================================== epilogue warpgroups
+    pdl_wait();
     const int wg = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -593,6 +603,23 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, unsigned long lo
 
 int num_sms();
 
+// Launch with programmatic stream serialisation (PDL) when CONAN_TC_PDL=1.  Measured on B200 (S = 1024): no gain
+// (7.89 ms with, 7.83 ms without) -- the persistent grids fill every SM until their last tile, so the next kernel's
+// prologue has nowhere to overlap; kept off by default.
+template <typename K, typename A>
+int launch_pdl(K kern, int grid, int threads, size_t smem, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, const A& a) {
+  static const bool pdl = [] { const char* v = getenv("CONAN_TC_PDL"); return v && atoi(v) != 0; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmW, a);
+  if (e != cudaSuccess) { set_error(std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
 // CTAs of a kernel that fit on one SM: registers, shared memory (with the carve-out preference set to
 // "max shared", which the launchers request), warps and the 512 TMEM columns.  The CUDA occupancy query is
 // not used: it answers for the *default* carve-out and returns 1 for these kernels.
@@ -635,7 +662,7 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, lon
   a.num_tiles = (int)(m_tiles * a.n_tiles);
   const int grid = std::min(a.num_tiles, num_sms() * per_sm);           // persistent: exactly the co-resident CTAs
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "ring<%d,%d,%d> tiles %d per_sm %d grid %d\n", BN, BK, STAGES, a.num_tiles, per_sm, grid);
-  kern<<<grid, NUM_THREADS, SL::TOTAL, st>>>(tmA, tmW, a);
+  if (launch_pdl(kern, grid, NUM_THREADS, SL::TOTAL, st, tmA, tmW, a)) return 1;
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -683,7 +710,7 @@ int launch_window_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const 
   const int per_sm = resident_ctas((const void*)kern, 64 + 128 * NEPI, smem, 2 * BN);
   const int grid = std::min(a.num_tiles, num_sms() * per_sm);
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "window<%d,%d,%d> k %d tiles %d smem %zu per_sm %d grid %d\n", C, BN, NEPI, a.k, a.num_tiles, smem, per_sm, grid);
-  kern<<<grid, 64 + 128 * NEPI, smem, st>>>(tmA, tmW, a);
+  if (launch_pdl(kern, grid, 64 + 128 * NEPI, smem, st, tmA, tmW, a)) return 1;
   CONAN_CHECK_LAUNCH();
   return 0;
 }
