@@ -21,9 +21,9 @@ __device__ __forceinline__ int slot_of(const int* slot_ids, int i) { return slot
 // which removes the reference's batch-element-0 limitation (TA:392).
 // ---------------------------------------------------------------------------------------
 constexpr int EMF_MAX_KEYS = 64;   // rc + lc + seg = 56 at the reference config
-constexpr int EMF_MAX_HD = 16;
+constexpr int EMF_MAX_ROWS = 8;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ ring, const int* __restrict__ past_len,
                           RowView att, const int* __restrict__ slot_ids, int seg, int rc, int lc,
                           int ring_rows, int D, int heads, int ldq) {
@@ -43,85 +43,94 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
   float* rg = ring + (long long)slot * ring_rows * 2 * D;
   const int tid = threadIdx.x;
 
-  // stage Q, and K/V in key order
+  // stage Q, and K|V in key order.  Every key's K|V is one contiguous run of 2D floats (columns [D, 3D) of a
+  // qkv row, or a ring row), moved as float4 with all loads of a thread issued before the first store.
+  const int hd = D / heads;
+  const float scaling = rsqrtf((float)hd);           // (input_dim // num_heads) ** -0.5, applied to Q before Q.K^T
   for (int idx = tid; idx < rows * D; idx += blockDim.x) {
-    int r = idx / D, c = idx % D;
-    sQ[idx] = q_in[(long long)r * ldq + c];
+    int r = idx / D, c = idx - r * D;
+    sQ[idx] = q_in[(long long)r * ldq + c] * scaling;
   }
-  for (int idx = tid; idx < nkeys * D; idx += blockDim.x) {
-    int key = idx / D, c = idx % D;
-    float kval, vval;
-    if (key < rc) {                                   // look-ahead rows
-      kval = q_in[(long long)key * ldq + D + c]; vval = q_in[(long long)key * ldq + 2 * D + c];
-    } else if (key < rc + lc_len) {                   // cached left context, oldest first
-      int logical = past - lc_len + (key - rc);
-      int rr = logical % ring_rows;
-      kval = rg[(long long)rr * 2 * D + c]; vval = rg[(long long)rr * 2 * D + D + c];
-    } else {                                          // this chunk's utterance rows
-      int r = rc + (key - rc - lc_len);
-      kval = q_in[(long long)r * ldq + D + c]; vval = q_in[(long long)r * ldq + 2 * D + c];
+  {
+    const int v4_per_key = (2 * D) / 4;                 // 40
+    const int items = nkeys * v4_per_key;
+    constexpr int UNR = 10;                             // 56 keys * 40 / 256 threads = 8.75 items per thread
+    float4 buf[UNR];
+    int kk[UNR], qq[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int item = tid + u * blockDim.x;
+      kk[u] = -1;
+      if (item < items) {
+        const int key = item / v4_per_key, q4 = item - key * v4_per_key;
+        const float* src;
+        if (key < rc) src = q_in + (long long)key * ldq + D;                                   // look-ahead rows
+        else if (key < rc + lc_len) src = rg + (long long)((past - lc_len + (key - rc)) % ring_rows) * 2 * D;   // left context, oldest first
+        else src = q_in + (long long)(rc + (key - rc - lc_len)) * ldq + D;                     // this chunk's utterance rows
+        buf[u] = *reinterpret_cast<const float4*>(src + q4 * 4);
+        kk[u] = key; qq[u] = q4;
+      }
     }
-    sK[key * DS + c] = kval; sV[key * DS + c] = vval;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (kk[u] >= 0) {
+        const int c = qq[u] * 4;
+        float* dst = (c < D ? sK + kk[u] * DS + c : sV + kk[u] * DS + (c - D));
+        dst[0] = buf[u].x; dst[1] = buf[u].y; dst[2] = buf[u].z; dst[3] = buf[u].w;
+      }
+    }
   }
   __syncthreads();
-  // state update: ring rows (past + t) % ring_rows <- utterance K/V.  ring_rows >= lc + seg, so the
+  // state update: ring rows (past + t) % ring_rows <- utterance K|V.  ring_rows >= lc + seg, so the
   // rows overwritten are older than the left context that was just staged.
-  for (int idx = tid; idx < seg * 2 * D; idx += blockDim.x) {
-    int t = idx / (2 * D), c = idx % (2 * D);
-    int rr = (past + t) % ring_rows;
-    rg[(long long)rr * 2 * D + c] = q_in[(long long)(rc + t) * ldq + D + c];
+  for (int idx = tid; idx < seg * (2 * D) / 4; idx += blockDim.x) {
+    const int t = idx / ((2 * D) / 4), q4 = idx - t * ((2 * D) / 4);
+    const int rr = (past + t) % ring_rows;
+    *reinterpret_cast<float4*>(rg + (long long)rr * 2 * D + q4 * 4) =
+        *reinterpret_cast<const float4*>(q_in + (long long)(rc + t) * ldq + D + q4 * 4);
   }
 
-  const int hd = D / heads;
-  const float scaling = rsqrtf((float)hd);           // (input_dim // num_heads) ** -0.5
+  // One warp per head.  Lanes own keys for the scores (each K element is read once for all query rows); the
+  // probabilities then overwrite this head's K columns (private to the warp), and P.V runs with lanes over
+  // the rows x head_dim outputs.
   const int warp = tid >> 5, lane = tid & 31;
   for (int h = warp; h < heads; h += (blockDim.x >> 5)) {
-    for (int qr = 0; qr < rows; ++qr) {
-      float qv[EMF_MAX_HD];
+    const int c0 = h * hd;
+    float acc[EMF_MAX_ROWS][EMF_MAX_KEYS / 32];
 #pragma unroll
-      for (int d = 0; d < EMF_MAX_HD; ++d) qv[d] = d < hd ? sQ[qr * D + h * hd + d] * scaling : 0.f;
-      float sc[EMF_MAX_KEYS / 32];
-      float mx = -INFINITY;
+    for (int r = 0; r < EMF_MAX_ROWS; ++r)
 #pragma unroll
-      for (int kk = 0; kk < EMF_MAX_KEYS / 32; ++kk) {
-        int key = lane + kk * 32;
-        float s = -INFINITY;
-        if (key < nkeys) {
-          s = 0.f;
+      for (int kk = 0; kk < EMF_MAX_KEYS / 32; ++kk) acc[r][kk] = 0.f;
+    const int key0 = min(lane, nkeys - 1), key1 = min(lane + 32, nkeys - 1);
+    for (int d = 0; d < hd; ++d) {
+      const float k0 = sK[key0 * DS + c0 + d], k1 = sK[key1 * DS + c0 + d];
 #pragma unroll
-          for (int d = 0; d < EMF_MAX_HD; ++d) if (d < hd) s = fmaf(qv[d], sK[key * DS + h * hd + d], s);
-        }
-        sc[kk] = s; mx = fmaxf(mx, s);
-      }
-      mx = warp_max(mx);
-      float den = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < EMF_MAX_KEYS / 32; ++kk) {
-        int key = lane + kk * 32;
-        sc[kk] = key < nkeys ? expf(sc[kk] - mx) : 0.f;
-        den += sc[kk];
-      }
-      den = warp_sum(den);
-      float inv = 1.f / den;
-      float o[EMF_MAX_HD];
-#pragma unroll
-      for (int d = 0; d < EMF_MAX_HD; ++d) o[d] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < EMF_MAX_KEYS / 32; ++kk) {
-        int key = lane + kk * 32;
-        if (key < nkeys) {
-          float p = sc[kk] * inv;
-#pragma unroll
-          for (int d = 0; d < EMF_MAX_HD; ++d) if (d < hd) o[d] = fmaf(p, sV[key * DS + h * hd + d], o[d]);
+      for (int r = 0; r < EMF_MAX_ROWS; ++r) {
+        if (r < rows) {
+          const float qv = sQ[r * D + c0 + d];
+          acc[r][0] = fmaf(qv, k0, acc[r][0]);
+          acc[r][1] = fmaf(qv, k1, acc[r][1]);
         }
       }
+    }
+    __syncwarp();
 #pragma unroll
-      for (int d = 0; d < EMF_MAX_HD; ++d) {
-        if (d < hd) {
-          float v = warp_sum(o[d]);
-          if (lane == 0) store_view(att, (long long)blockIdx.x * att.slot_stride + (long long)qr * att.row_stride + h * hd + d, v);
-        }
+    for (int r = 0; r < EMF_MAX_ROWS; ++r) {
+      if (r < rows) {
+        const float s0 = lane < nkeys ? acc[r][0] : -INFINITY, s1 = lane + 32 < nkeys ? acc[r][1] : -INFINITY;
+        const float mx = warp_max(fmaxf(s0, s1));
+        const float e0 = lane < nkeys ? expf(s0 - mx) : 0.f, e1 = lane + 32 < nkeys ? expf(s1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(e0 + e1);
+        if (lane < nkeys) sK[lane * DS + c0 + r] = e0 * inv;
+        if (lane + 32 < nkeys) sK[(lane + 32) * DS + c0 + r] = e1 * inv;
       }
+    }
+    __syncwarp();
+    for (int o = lane; o < rows * hd; o += 32) {
+      const int r = o / hd, d = o - r * hd;
+      float v = 0.f;
+      for (int key = 0; key < nkeys; ++key) v = fmaf(sK[key * DS + c0 + r], sV[key * DS + c0 + d], v);
+      store_view(att, (long long)blockIdx.x * att.slot_stride + (long long)r * att.row_stride + c0 + d, v);
     }
   }
 }
@@ -129,50 +138,92 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
 // ---------------------------------------------------------------------------------------
 // Aligner cross-attention (nn.MultiheadAttention, prosody_util.py:108-127): queries are this
 // chunk's frames, keys/values are the session-cached projections of the prosody tokens.
-//   q [slot, rows, H] (unscaled), cache [slot, layer, tp_max, 2H] (K | V), kpm [slot, tp_max]
-// grid (stream, head); one warp per query row; scores staged in shared memory.
+//   q [i, rows, H] (unscaled, compact), cache [slot, layer, tp_max, 2H] (K | V), kpm [slot, tp_max]
+// One warp per (stream, head) handles all query rows: scores with lanes over keys (each K row is read once
+// for the 4 queries), fp32 softmax by warp shuffles, then P.V with lanes over the head dimension (coalesced
+// V rows).  8 warps per CTA.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int XA_MAX_ROWS = 8;
+constexpr int XA_WARPS = 8;
+
+__global__ void __launch_bounds__(XA_WARPS * 32)
 cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ cache, const float* __restrict__ kpm,
-                       const int* __restrict__ n_keys, RowView out, const int* __restrict__ slot_ids, int rows,
+                       const int* __restrict__ n_keys, RowView out, const int* __restrict__ slot_ids, int n, int rows,
                        int H, int heads, int layer, int n_layers, int tp_max) {
-  extern __shared__ float sc[];                      // [rows][tp_max]
-  const int slot = slot_of(slot_ids, blockIdx.x), h = blockIdx.y;
-  const int hd = H / heads;
-  const int Tp = n_keys[slot];
+  extern __shared__ float xsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hd = H / heads;                                          // 128
+  float* sq = xsm + (size_t)warp * (XA_MAX_ROWS * hd + XA_MAX_ROWS * tp_max);   // [rows][hd] scaled queries
+  float* sc = sq + XA_MAX_ROWS * hd;                                  // [rows][tp_max] scores -> probabilities
+  const int pair = blockIdx.x * XA_WARPS + warp;
+  if (pair >= n * heads) return;
+  const int i = pair / heads, h = pair - i * heads;
+  const int slot = slot_of(slot_ids, i);
+  const int Tp = n_keys[slot];
   const float* kv = cache + ((long long)slot * n_layers + layer) * tp_max * 2 * H;
   const float* pm = kpm + (long long)slot * tp_max;
-  const float scaling = sqrtf(1.0f / (float)hd);     // q * math.sqrt(1.0 / head_dim)
-  for (int r = warp; r < rows; r += (blockDim.x >> 5)) {
-    float* s = sc + (size_t)r * tp_max;
-    const float* qr = q + ((long long)blockIdx.x * rows + r) * H + h * hd;
-    float qv[4];                                      // hd = 128 -> 4 per lane
-    for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; qv[j] = d < hd ? qr[d] * scaling : 0.f; }
+  const float scaling = sqrtf(1.0f / (float)hd);                      // q * math.sqrt(1.0 / head_dim)
+  for (int idx = lane; idx < rows * hd; idx += 32) {
+    const int r = idx / hd, d = idx - r * hd;
+    sq[r * hd + d] = q[((long long)i * rows + r) * H + h * hd + d] * scaling;
+  }
+  __syncwarp();
+  // ---- scores: lane <- key
+  for (int key = lane; key < Tp; key += 32) {
+    const float4* kr = reinterpret_cast<const float4*>(kv + (long long)key * 2 * H + h * hd);
+    float acc[XA_MAX_ROWS];
+#pragma unroll
+    for (int r = 0; r < XA_MAX_ROWS; ++r) acc[r] = 0.f;
+    for (int d4 = 0; d4 < hd / 4; ++d4) {
+      const float4 k4 = kr[d4];
+#pragma unroll
+      for (int r = 0; r < XA_MAX_ROWS; ++r) {
+        if (r < rows) {
+          const float4 q4 = *reinterpret_cast<const float4*>(&sq[r * hd + d4 * 4]);
+          acc[r] = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, acc[r]))));
+        }
+      }
+    }
+    const bool masked = pm[key] != 0.f;                               // key_padding_mask -> -inf
+#pragma unroll
+    for (int r = 0; r < XA_MAX_ROWS; ++r)
+      if (r < rows) sc[r * tp_max + key] = masked ? -INFINITY : acc[r];
+  }
+  __syncwarp();
+  // ---- softmax per query row
+  for (int r = 0; r < rows; ++r) {
     float mx = -INFINITY;
-    for (int key = 0; key < Tp; ++key) {
-      const float* kr = kv + (long long)key * 2 * H + h * hd;
-      float a = 0.f;
-      for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) a = fmaf(qv[j], kr[d], a); }
-      a = warp_sum(a);
-      if (pm[key] != 0.f) a = -INFINITY;              // key_padding_mask -> -inf
-      if (lane == 0) s[key] = a;
-      mx = fmaxf(mx, a);
-    }
-    __syncwarp();
+    for (int key = lane; key < Tp; key += 32) mx = fmaxf(mx, sc[r * tp_max + key]);
+    mx = warp_max(mx);
     float den = 0.f;
-    for (int key = lane; key < Tp; key += 32) { float e = expf(s[key] - mx); s[key] = e; den += e; }
+    for (int key = lane; key < Tp; key += 32) { const float e = expf(sc[r * tp_max + key] - mx); sc[r * tp_max + key] = e; den += e; }
     den = warp_sum(den);
-    __syncwarp();
-    float inv = 1.f / den;
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    const float inv = 1.f / den;
+    for (int key = lane; key < Tp; key += 32) sc[r * tp_max + key] *= inv;
+  }
+  __syncwarp();
+  // ---- P.V: lane <- 4 consecutive head dims
+  for (int d0 = lane * 4; d0 < hd; d0 += 128) {
+    float4 o[XA_MAX_ROWS];
+#pragma unroll
+    for (int r = 0; r < XA_MAX_ROWS; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int key = 0; key < Tp; ++key) {
-      float p = s[key] * inv;
-      const float* vr = kv + (long long)key * 2 * H + H + h * hd;
-      for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) o[j] = fmaf(p, vr[d], o[j]); }
+      const float4 v4 = *reinterpret_cast<const float4*>(kv + (long long)key * 2 * H + H + h * hd + d0);
+#pragma unroll
+      for (int r = 0; r < XA_MAX_ROWS; ++r) {
+        if (r < rows) {
+          const float p = sc[r * tp_max + key];
+          o[r].x = fmaf(p, v4.x, o[r].x); o[r].y = fmaf(p, v4.y, o[r].y); o[r].z = fmaf(p, v4.z, o[r].z); o[r].w = fmaf(p, v4.w, o[r].w);
+        }
+      }
     }
-    const long long orow = (long long)blockIdx.x * out.slot_stride + (long long)r * out.row_stride + h * hd;
-    for (int j = 0; j < 4; ++j) { int d = lane + 32 * j; if (d < hd) store_view(out, orow + d, o[j]); }
+#pragma unroll
+    for (int r = 0; r < XA_MAX_ROWS; ++r) {
+      if (r < rows) {
+        const long long orow = (long long)i * out.slot_stride + (long long)r * out.row_stride + h * hd + d0;
+        store_view(out, orow, o[r].x); store_view(out, orow + 1, o[r].y); store_view(out, orow + 2, o[r].z); store_view(out, orow + 3, o[r].w);
+      }
+    }
   }
 }
 
@@ -182,11 +233,16 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
                               const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv,
                               cudaStream_t st) {
   if (n <= 0) return 0;
-  if (rc + lc + seg > EMF_MAX_KEYS || D / heads > EMF_MAX_HD) { set_error("emformer_attention: key count or head_dim above compiled limits"); return 1; }
+  if (rc + lc + seg > EMF_MAX_KEYS || seg + rc > EMF_MAX_ROWS || seg + rc > D / heads) { set_error("emformer_attention: key count / query rows above compiled limits (rows <= min(8, head_dim))"); return 1; }
+  if (D % 4 != 0 || ld_qkv % 4 != 0 || (rc + lc + seg) * ((2 * D) / 4) > 10 * 256) { set_error("emformer_attention: D / ld must be multiples of 4 and keys*2D/4 <= 2560"); return 1; }
   if (ring_rows < lc + seg) { set_error("emformer_attention: ring too short"); return 1; }
   size_t sh = ((size_t)2 * (rc + lc + seg) * (D + 1) + (size_t)(seg + rc) * D) * sizeof(float);
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr_set = true; }
+  if (!attr_set) {
+    cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }
   emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv);
   CONAN_CHECK_LAUNCH();
@@ -196,10 +252,18 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
 int launch_cross_attention(const float* q, const float* kv_cache, const float* kpm, const int* n_keys, RowView out, int n,
                            const int* slot_ids, int rows, int H, int heads, int layer, int n_layers, int tp_max, cudaStream_t st) {
   if (n <= 0) return 0;
-  if (H / heads > 128) { set_error("cross_attention: head_dim above 128"); return 1; }
-  size_t sh = (size_t)rows * tp_max * sizeof(float);
-  if (sh > 48 * 1024) { set_error("cross_attention: too many keys for the score buffer"); return 1; }
-  cross_attention_kernel<<<dim3(n, heads), 128, sh, st>>>(q, kv_cache, kpm, n_keys, out, slot_ids, rows, H, heads, layer, n_layers, tp_max);
+  const int hd = H / heads;
+  if (rows > XA_MAX_ROWS || hd % 4 != 0) { set_error("cross_attention: rows above 8 or head_dim not a multiple of 4"); return 1; }
+  size_t sh = (size_t)XA_WARPS * (XA_MAX_ROWS * hd + XA_MAX_ROWS * tp_max) * sizeof(float);
+  static size_t attr = 0;
+  if (sh > attr) {
+    if (sh > 200 * 1024) { set_error("cross_attention: too many keys for the score buffer"); return 1; }
+    cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    attr = sh;
+  }
+  const int pairs = n * heads;
+  cross_attention_kernel<<<(pairs + XA_WARPS - 1) / XA_WARPS, XA_WARPS * 32, sh, st>>>(q, kv_cache, kpm, n_keys, out, slot_ids, n, rows, H,
+                                                                                       heads, layer, n_layers, tp_max);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
