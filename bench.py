@@ -164,7 +164,8 @@ def run_b200(args):
 
     sds = synth.make_all_state_dicts(1234)
     cfg = make_config(max_slots=S, max_ref_frames=160, device=local, voc_precision=args.voc_precision,
-                      voc_tensor_cores=not args.no_tensor_cores, voc_group=args.voc_group)
+                      voc_tensor_cores=not args.no_tensor_cores, voc_group=args.voc_group,
+                      voc_fuse_resblocks=False if args.no_fuse else None)
     eng = Engine(*sds, cfg)
     slots = np.arange(S, dtype=np.int32)
     ids = eng.ids_tensor(slots)
@@ -236,7 +237,7 @@ def run_b200(args):
     NPROF = 2
     for i in range(NPROF):
         eng.step(ids, chunks_dev[i % n_pool], wav, mel, tok)
-    prof = {cat: eng.profile_read(cat) for cat in range(4)}
+    prof = {cat: eng.profile_read(cat) for cat in range(5)}
     eng.set_profiling(False)
 
     t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -251,7 +252,8 @@ def run_b200(args):
         names = {0: ("conv_gemm_ffma_kernel (fp32 CUDA-core engine)", "tensor"),
                  1: ("conv_gemm_tc_kernel (tcgen05 implicit-GEMM causal conv, fp16 operands: vocoder scales 0-1 + upsampling)", "tensor"),
                  2: ("conv_window_tc_kernel (tcgen05, persistent, weights resident, one input window per tile: vocoder scales 2-3)", "hbm"),
-                 3: ("conv_gemm_tc_kernel, split-fp16 operands (Emformer / Conan linear + conv contractions, 3 MMAs per product)", "tensor")}
+                 3: ("conv_gemm_tc_kernel, split-fp16 operands (Emformer / Conan linear + conv contractions, 3 MMAs per product)", "tensor"),
+                 4: ("resblock_fused_kernel (tcgen05, one HiFi-GAN residual block = six convs per launch, activations in shared memory: vocoder scales 2-3)", "tensor")}
         roofs = {}
         for cat, (ms, nl, fl, by) in prof.items():
             if nl == 0:
@@ -277,7 +279,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD.format(S=S), "streams_per_gpu": S, "chunk_ms": 80, "ref_frames": 150,
                        "weights": "synthetic seeded (conan_b200.synth, reference state_dict layout)",
                        "l2": f"per-step working set (resident state {eng.state_bytes / 2**30:.1f} GiB) is larger than L2; no flush needed",
-                       "voc_precision": args.voc_precision, "voc_tensor_cores": not args.no_tensor_cores, "voc_group": args.voc_group},
+                       "voc_precision": args.voc_precision, "voc_tensor_cores": not args.no_tensor_cores, "voc_group": args.voc_group,
+                       "voc_fuse_resblocks": bool(cfg.voc_fuse_resblocks)},
             "latency_ms": {"p50": ps[len(ps) // 2], "p99": ps[min(len(ps) - 1, int(len(ps) * 0.99))], "max": ps[-1]},
             "rtf": (total_ms / K) / (CHUNK_S * 1e3),
             "path_tflops": world * S * K * FLOP_PER_STREAM_CHUNK / (total_ms * 1e-3) / 1e12,
@@ -306,6 +309,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voc-precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-tensor-cores", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run the 32 / 64 channel residual blocks conv by conv (A/B against the fused kernel)")
     ap.add_argument("--voc-group", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="open a cudaProfiler window around one step and exit")

@@ -227,6 +227,77 @@ cross_attention_kernel(const float* __restrict__ q, const float* __restrict__ ca
   }
 }
 
+// Same operator with this (stream, head)'s K and V rows staged in shared memory by cp.async (every 16-byte copy of
+// the CTA is in flight at once, which is what the HBM-resident cache needs), used while 2 * keys * (hd + 4) floats
+// fit.  One CTA of 4 warps per (stream, head); a warp owns a query row.  K/V rows are padded by 4 floats so the
+// per-lane float4 row reads of the score loop are conflict-free.
+constexpr int XS_THREADS = 128;
+
+__global__ void __launch_bounds__(XS_THREADS)
+cross_attention_staged_kernel(const float* __restrict__ q, const float* __restrict__ cache, const float* __restrict__ kpm,
+                              const int* __restrict__ n_keys, RowView out, const int* __restrict__ slot_ids, int rows,
+                              int H, int heads, int layer, int n_layers, int tp_max) {
+  extern __shared__ __align__(16) float xs[];
+  const int hd = H / heads, HS = hd + 4;
+  float* sK = xs;                                  // [tp_max][HS]
+  float* sV = sK + (size_t)tp_max * HS;            // [tp_max][HS]
+  float* sq = sV + (size_t)tp_max * HS;            // [rows][hd]
+  float* sp = sq + (size_t)rows * hd;              // [rows][tp_max]
+  const int i = blockIdx.x / heads, h = blockIdx.x - i * heads;
+  const int slot = slot_of(slot_ids, i);
+  const int Tp = n_keys[slot];
+  const float* kv = cache + ((long long)slot * n_layers + layer) * tp_max * 2 * H;
+  const float* pm = kpm + (long long)slot * tp_max;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v4 = hd / 4;
+  for (int idx = tid; idx < Tp * 2 * v4; idx += XS_THREADS) {
+    const int key = idx / (2 * v4), rem = idx - key * 2 * v4;
+    const int isv = rem >= v4, c4 = rem - isv * v4;
+    const float* src = kv + (long long)key * 2 * H + isv * H + h * hd + c4 * 4;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared((isv ? sV : sK) + key * HS + c4 * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  }
+  const float scaling = sqrtf(1.0f / (float)hd);                      // q * math.sqrt(1.0 / head_dim)
+  for (int idx = tid; idx < rows * hd; idx += XS_THREADS) {
+    const int r = idx / hd, d = idx - r * hd;
+    sq[idx] = q[((long long)i * rows + r) * H + h * hd + d] * scaling;
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int r = warp; r < rows; r += XS_THREADS / 32) {
+    float* p = sp + (size_t)r * tp_max;
+    const float4* q4 = reinterpret_cast<const float4*>(sq + (size_t)r * hd);
+    float mx = -INFINITY;
+    for (int key = lane; key < Tp; key += 32) {
+      const float4* k4 = reinterpret_cast<const float4*>(sK + (size_t)key * HS);
+      float a = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < v4; ++d) {
+        const float4 kk = k4[d], qq = q4[d];
+        a = fmaf(qq.x, kk.x, fmaf(qq.y, kk.y, fmaf(qq.z, kk.z, fmaf(qq.w, kk.w, a))));
+      }
+      if (pm[key] != 0.f) a = -INFINITY;                              // key_padding_mask
+      p[key] = a; mx = fmaxf(mx, a);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int key = lane; key < Tp; key += 32) { const float e = expf(p[key] - mx); p[key] = e; den += e; }
+    const float inv = 1.f / warp_sum(den);
+    __syncwarp();
+    for (int d0 = lane * 4; d0 < hd; d0 += 128) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int key = 0; key < Tp; ++key) {
+        const float pk = p[key];
+        const float4 v = *reinterpret_cast<const float4*>(sV + (size_t)key * HS + d0);
+        o.x = fmaf(pk, v.x, o.x); o.y = fmaf(pk, v.y, o.y); o.z = fmaf(pk, v.z, o.z); o.w = fmaf(pk, v.w, o.w);
+      }
+      const long long orow = (long long)i * out.slot_stride + (long long)r * out.row_stride + h * hd + d0;
+      store_view(out, orow, o.x * inv); store_view(out, orow + 1, o.y * inv);
+      store_view(out, orow + 2, o.z * inv); store_view(out, orow + 3, o.w * inv);
+    }
+  }
+}
+
 }  // namespace
 
 int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, RowView att, int n,
@@ -254,6 +325,19 @@ int launch_cross_attention(const float* q, const float* kv_cache, const float* k
   if (n <= 0) return 0;
   const int hd = H / heads;
   if (rows > XA_MAX_ROWS || hd % 4 != 0) { set_error("cross_attention: rows above 8 or head_dim not a multiple of 4"); return 1; }
+  const size_t sh_staged = ((size_t)2 * tp_max * (hd + 4) + (size_t)rows * hd + (size_t)rows * tp_max) * sizeof(float);
+  if (sh_staged <= 100 * 1024 && H % 4 == 0) {
+    static size_t attr_s = 0;
+    if (sh_staged > attr_s) {
+      cudaFuncSetAttribute(cross_attention_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_staged);
+      cudaFuncSetAttribute(cross_attention_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_s = sh_staged;
+    }
+    cross_attention_staged_kernel<<<n * heads, XS_THREADS, sh_staged, st>>>(q, kv_cache, kpm, n_keys, out, slot_ids, rows, H, heads, layer,
+                                                                            n_layers, tp_max);
+    CONAN_CHECK_LAUNCH();
+    return 0;
+  }
   size_t sh = (size_t)XA_WARPS * (XA_MAX_ROWS * hd + XA_MAX_ROWS * tp_max) * sizeof(float);
   static size_t attr = 0;
   if (sh > attr) {

@@ -27,13 +27,12 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace conan {
 
 namespace {
 
-constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 192;
 
 struct TcEpi {
@@ -57,85 +56,6 @@ struct TcArgs {
   int lo_slot_off;           // slot offset of the lo plane of a split x
   TcEpi e;
 };
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// Programmatic dependent launch: the next tensor-core kernel of the step may start its prologue (barrier
-// init, TMEM allocation, bias staging, resident-weight TMA) while this one drains; it touches activations
-// only after pdl_wait(), which returns when every prerequisite grid has completed and flushed.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start address >> 4, [16,30) LBO >> 4 (= 1 for swizzled K-major), [32,46) SBO >> 4
-//   (8 rows * swizzle span), [46,48) version = 1, [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
-template <int SWIZZLE_BYTES>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2 : 4;
-  constexpr uint64_t sbo = (8 * SWIZZLE_BYTES) >> 4;
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | (sbo << 32) | ((uint64_t)1 << 46) | (layout << 61);
-}
-
-// instruction descriptor for kind::f16: fp16 A/B (K-major), fp32 accumulate, M = 128, N = BN
-template <int BN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
 
 // Fused epilogue of one accumulator row (thread = tile row = TMEM lane): waits for the accumulator,
 // then per 16-column chunk: bias, scale, activation, residual, mask, 1/3-scale (+ old output), fp32
@@ -334,8 +254,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();                                  // activations of the previous layer are complete and visible from here on
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop, one elected lane issues)
+    {
       const int kb_per_tap = a.cin / BK;
       const int kb_per_seg = a.kblocks / a.nseg;
       int kbg = 0;                                           // k-block counter across tiles (the smem ring never drains)
@@ -348,17 +268,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
-          mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
           const int seg = kb / kb_per_seg, kbl = kb - seg * kb_per_seg;
           const int j = kbl / kb_per_tap, c0 = (kbl - j * kb_per_tap) * BK;
-          tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
-          tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
+            tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
+            tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc<BN>();
       int kbg = 0, it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
@@ -378,11 +300,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             // advance 16 halfs = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-            tc_mma_f16(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+            if (elect_one_sync()) tc_mma_f16(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
+          if (elect_one_sync()) tc_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
         }
-        tc_commit(&acc_full[ab]);            // accumulator complete
+        if (elect_one_sync()) tc_commit(&acc_full[ab]);            // accumulator complete
       }
     }
   } else {
@@ -474,10 +396,12 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(a.k * TAPB));                     // weights are constants: fetched before the dependency wait
-      for (int j = 0; j < a.k; ++j) tma_load_2d(sW + j * TAPB, &tmW, w_full, j * C, 0);
+    // ===================================================================== TMA producer (warp-uniform loop, one elected lane issues)
+    {
+      if (elect_one_sync()) {
+        mbar_expect_tx(w_full, (uint32_t)(a.k * TAPB));                   // weights are constants: fetched before the dependency wait
+        for (int j = 0; j < a.k; ++j) tma_load_2d(sW + j * TAPB, &tmW, w_full, j * C, 0);
+      }
       pdl_wait();
       int it = 0;
       for (int g = blockIdx.x; g < a.num_tiles; g += gridDim.x, ++it) {
@@ -485,13 +409,15 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t ph = (it / NBUF) & 1;
         mbar_wait(&a_empty[buf], ph ^ 1);
         const int si = g / a.tiles_per_stream, t0 = (g - si * a.tiles_per_stream) * TILE_M;
-        mbar_expect_tx(&a_full[buf], (uint32_t)(a.win_rows * ROWB));
-        tma_load_3d(sA + buf * winb, &tmA, &a_full[buf], 0, a.row0 + t0, si);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&a_full[buf], (uint32_t)(a.win_rows * ROWB));
+          tma_load_3d(sA + buf * winb, &tmA, &a_full[buf], 0, a.row0 + t0, si);
+        }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc<BN>();
       mbar_wait(w_full, 0);
       tc_fence_after();
@@ -509,11 +435,11 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t brow = sW32 + (uint32_t)(j * TAPB);
 #pragma unroll
           for (int kk = 0; kk < C / 16; ++kk)
-            tc_mma_f16(tmem_base + (uint32_t)(ab * BN), make_smem_desc<ROWB>(arow + kk * 32),
-                       make_smem_desc<ROWB>(brow + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
+            if (elect_one_sync())
+              tc_mma_f16(tmem_base + (uint32_t)(ab * BN), make_smem_desc<ROWB>(arow + kk * 32),
+                         make_smem_desc<ROWB>(brow + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
         }
-        tc_commit(&a_empty[buf]);
-        tc_commit(&acc_full[ab]);
+        if (elect_one_sync()) { tc_commit(&a_empty[buf]); tc_commit(&acc_full[ab]); }
       }
     }
   } else {
@@ -577,6 +503,8 @@ struct MapKeyHash {
   }
 };
 
+}  // namespace
+
 int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, unsigned long long d0, unsigned long long d1, unsigned long long d2,
                    unsigned long long s1_bytes, unsigned long long s2_bytes, unsigned b0, unsigned b1, unsigned b2, int swz_bytes) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
@@ -601,7 +529,26 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, unsigned long lo
   return 0;
 }
 
-int num_sms();
+// CTAs of a kernel that fit on one SM: registers, shared memory (with the carve-out preference set to
+// "max shared", which the launchers request), warps and the 512 TMEM columns.  The CUDA occupancy query is
+// not used: it answers for the *default* carve-out and returns 1 for these kernels.
+int resident_ctas(const void* func, int threads, size_t dyn_smem, int tmem_cols) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, func) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+  const int regs_per_cta = ((fa.numRegs * 32 + 255) / 256 * 256) * (threads / 32);      // allocation granularity: 256 regs per warp
+  int n = 65536 / std::max(regs_per_cta, 1);
+  n = std::min<int>(n, (int)((227 * 1024) / (dyn_smem + fa.sharedSizeBytes + 1024)));
+  n = std::min(n, 64 / (threads / 32));
+  n = std::min(n, 512 / std::max(tmem_cols, 32));
+  return std::max(n, 1);
+}
+
+int num_sms() {
+  static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+  return n;
+}
+
+namespace {
 
 // Launch with programmatic stream serialisation (PDL) when CONAN_TC_PDL=1.  Measured on B200 (S = 1024): no gain
 // (7.89 ms with, 7.83 ms without) -- the persistent grids fill every SM until their last tile, so the next kernel's
@@ -618,20 +565,6 @@ int launch_pdl(K kern, int grid, int threads, size_t smem, cudaStream_t st, cons
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmW, a);
   if (e != cudaSuccess) { set_error(std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e)); return 1; }
   return 0;
-}
-
-// CTAs of a kernel that fit on one SM: registers, shared memory (with the carve-out preference set to
-// "max shared", which the launchers request), warps and the 512 TMEM columns.  The CUDA occupancy query is
-// not used: it answers for the *default* carve-out and returns 1 for these kernels.
-int resident_ctas(const void* func, int threads, size_t dyn_smem, int tmem_cols) {
-  cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, func) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
-  const int regs_per_cta = ((fa.numRegs * 32 + 255) / 256 * 256) * (threads / 32);      // allocation granularity: 256 regs per warp
-  int n = 65536 / std::max(regs_per_cta, 1);
-  n = std::min<int>(n, (int)((227 * 1024) / (dyn_smem + fa.sharedSizeBytes + 1024)));
-  n = std::min(n, 64 / (threads / 32));
-  n = std::min(n, 512 / std::max(tmem_cols, 32));
-  return std::max(n, 1);
 }
 
 int pick_tt(int L) {
@@ -671,11 +604,6 @@ int window_mode() {
   // CONAN_TC_WINDOW=0 routes every layer through the ring kernel (A/B comparisons, debugging)
   static int mode = [] { const char* v = getenv("CONAN_TC_WINDOW"); return v ? atoi(v) : 1; }();
   return mode;
-}
-
-int num_sms() {
-  static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
-  return n;
 }
 
 constexpr int WIN_NBUF = 3;

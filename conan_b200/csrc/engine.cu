@@ -12,6 +12,7 @@
 // and one scatter launch writes the last H rows back to the slots.  Gather + scatter move exactly the
 // bytes an in-place ring shift would.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <cmath>
@@ -77,6 +78,9 @@ struct conan_engine {
   Ctx vPRE, vUP[8], vXA[8], vC1[8][4][4], vC2[8][4][4], vPOST;
   float *vXS = nullptr, *vXR[2] = {nullptr, nullptr}, *vSUM = nullptr;
   __half* vSUMh = nullptr;       // running MRF sum as fp16 (residual-from-context mode)
+  // fused residual blocks (resblock_fused.cu): per (scale, block) packed weights / biases and the resident history block
+  bool vFused[8] = {false, false, false, false, false, false, false, false};
+  __half* fW[8][4] = {}; float* fB[8][4] = {}; __half* fHist[8][4] = {}; int fHistRows[8][4] = {};
   int vL[9], vC[9];     // rows / channels entering scale i (vL[0] = segment, vC[0] = initial channel)
   // ---- history gather/scatter tables
   HistDesc* histConan = nullptr; int nHistConan = 0;
@@ -248,6 +252,11 @@ int alloc_ctx(conan_engine* e, Ctx* c, int H, int L, int R, int C, int is_half) 
   return 0;
 }
 
+constexpr int kFusedWeightCopies = 16;
+inline int fused_weight_copies() {        // CONAN_FUSED_WCOPIES=1..16 (A/B of the L2 hot-spot relief)
+  static int n = [] { const char* v = getenv("CONAN_FUSED_WCOPIES"); int x = v ? atoi(v) : 8; return x < 1 ? 1 : (x > kFusedWeightCopies ? kFusedWeightCopies : x); }();
+  return n;
+}
 constexpr float kSplitWeightScale = 1024.f;      // split weights are packed as 2^10 * W (keeps W_lo out of the fp16 subnormals)
 
 // ---- conv parameter builders (all compact: stream i of the ready list, no slot indirection) -----
@@ -306,6 +315,30 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
   CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
   CONAN_CUDA_OK(cudaEventRecord(r.a, st));
   int rc = tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
+  CONAN_CUDA_OK(cudaEventRecord(r.b, st));
+  e->prof.push_back(r);
+  return rc;
+}
+
+// profiling category 4: fused residual block (six convs per launch)
+int run_fused(const conan_engine* e, const ResblockFusedParams& f, cudaStream_t st) {
+  if (!e->profiling) return launch_resblock_fused(f, st);
+  conan_engine::ProfRec r;
+  r.cat = 4;
+  r.flops = 2.0 * 6.0 * (double)f.n_streams * f.L * f.C * f.k * f.C;
+  {
+    // algorithmic HBM bytes: input rows once, weights once, running sum in / out, next-layer rows, history in + out
+    const double rows = (double)f.n_streams * f.L;
+    double b = (double)f.n_streams * (f.L + (f.k - 1) * f.dil[0]) * f.C * 2.0 + 6.0 * f.C * f.k * f.C * 2.0;
+    if (f.sum_in) b += rows * f.C * 2.0;
+    if (f.sum_out) b += rows * f.C * 2.0;
+    if (f.next) b += rows * f.C * 2.0;
+    b += 2.0 * (double)f.n_streams * f.hist_slot_stride * 2.0;
+    r.bytes = b;
+  }
+  CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
+  CONAN_CUDA_OK(cudaEventRecord(r.a, st));
+  int rc = launch_resblock_fused(f, st);
   CONAN_CUDA_OK(cudaEventRecord(r.b, st));
   e->prof.push_back(r);
   return rc;
@@ -372,12 +405,37 @@ int allocate_state(conan_engine* e) {
   for (int i = 0; i < c.voc_n_ups; ++i) { e->vL[i + 1] = e->vL[i] * c.voc_rates[i]; e->vC[i + 1] = e->vC[i] / 2; }
   TRY(alloc_ctx(e, &e->vPRE, 6, seg, 0, c.n_mels, hf));
   size_t maxLC = 0;
+  std::vector<ZeroDesc> fused_zero;
   for (int i = 0; i < c.voc_n_ups; ++i) {
     TRY(alloc_ctx(e, &e->vUP[i], c.voc_up_kernels[i] - 1, e->vL[i], 0, e->vC[i], hf));
     int L = e->vL[i + 1], C = e->vC[i + 1];
     int hmax = 0;
     for (int r = 0; r < c.voc_n_res; ++r) hmax = std::max(hmax, (c.voc_res_kernels[r] - 1) * c.voc_res_dilations[0]);
     TRY(alloc_ctx(e, &e->vXA[i], hmax, L, 0, C, hf));
+    e->vFused[i] = c.voc_fuse_resblocks && c.voc_use_tensor_cores && c.voc_residual_from_ctx && hf && c.voc_n_dil == 3;
+    for (int r = 0; r < c.voc_n_res && e->vFused[i]; ++r)
+      e->vFused[i] = resblock_fused_eligible(C, L, c.voc_res_kernels[r], c.voc_res_dilations) && c.voc_res_dilations[0] == 1;
+    maxLC = std::max(maxLC, (size_t)L * C);
+    if (e->vFused[i]) {
+      // no per-conv context buffers at this scale: the block's intermediate activations live in shared memory; only
+      // the newest halo rows of each conv window are resident per slot
+      for (int r = 0; r < c.voc_n_res; ++r) {
+        const int k = c.voc_res_kernels[r];
+        e->fHistRows[i][r] = resblock_fused_hist_rows(k, c.voc_res_dilations);
+        TRY(dalloc(e, &e->fHist[i][r], (size_t)S * e->fHistRows[i][r] * C));
+        fused_zero.push_back(ZeroDesc{e->fHist[i][r], (long long)e->fHistRows[i][r] * C * 2, (long long)e->fHistRows[i][r] * C * 2});
+        const size_t wn = (size_t)C * k * C;
+        TRY(dalloc(e, &e->fW[i][r], (size_t)kFusedWeightCopies * 6 * wn)); TRY(dalloc(e, &e->fB[i][r], (size_t)6 * C));
+        for (int j = 0; j < 3; ++j)
+          for (int h = 0; h < 2; ++h) {
+            std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + (h ? ".c2." : ".c1.") + std::to_string(j);
+            for (int cp = 0; cp < kFusedWeightCopies; ++cp)
+              CONAN_CUDA_OK(cudaMemcpy(e->fW[i][r] + ((size_t)cp * 6 + 2 * j + h) * wn, e->P(q + ".w"), wn * 2, cudaMemcpyDeviceToDevice));
+            CONAN_CUDA_OK(cudaMemcpy(e->fB[i][r] + (size_t)(2 * j + h) * C, e->F(q + ".b"), (size_t)C * 4, cudaMemcpyDeviceToDevice));
+          }
+      }
+      continue;
+    }
     for (int r = 0; r < c.voc_n_res; ++r)
       for (int j = 0; j < c.voc_n_dil; ++j) {
         if (j > 0) TRY(alloc_ctx(e, &e->vC1[i][r][j], (c.voc_res_kernels[r] - 1) * c.voc_res_dilations[j], L, 0, C, hf));
@@ -436,10 +494,11 @@ int allocate_state(conan_engine* e) {
     std::vector<const Ctx*> cs{&e->vPRE, &e->vPOST};
     for (int i = 0; i < c.voc_n_ups; ++i) {
       cs.push_back(&e->vUP[i]); cs.push_back(&e->vXA[i]);
+      if (e->vFused[i]) continue;
       for (int r = 0; r < c.voc_n_res; ++r)
         for (int j = 0; j < c.voc_n_dil; ++j) { if (j > 0) cs.push_back(&e->vC1[i][r][j]); cs.push_back(&e->vC2[i][r][j]); }
     }
-    TRY(build_tables(cs, {}, &e->histVoc, &e->nHistVoc, &e->zeroVoc, &e->nZeroVoc, {}));
+    TRY(build_tables(cs, {}, &e->histVoc, &e->nHistVoc, &e->zeroVoc, &e->nZeroVoc, fused_zero));
   }
   // ---- session scratch
   e->SB = std::min(S, 32);
@@ -611,7 +670,24 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
     }
     const bool last_scale = (i == c.voc_n_ups - 1);
     const Ctx& next = last_scale ? e->vPOST : e->vUP[i + 1];
-    for (int r = 0; r < c.voc_n_res; ++r) {
+    for (int r = 0; r < c.voc_n_res && e->vFused[i]; ++r) {
+      // MRF average with the running sum in fp16: block 0 writes it, block 1 adds to it, the last block emits
+      // lrelu(sum / n_res) into the next layer's context (hifigan_causal.py:324-329)
+      ResblockFusedParams f;
+      memset(&f, 0, sizeof(f));
+      const Ctx& in = e->vXA[i];
+      f.x = in.p; f.x_slot_stride = in.slot_stride(); f.x_rows = in.rows(); f.x_hist_rows = in.H; f.n_slots = e->S;
+      f.C = C; f.L = L; f.k = c.voc_res_kernels[r]; f.n_streams = n; f.slot_ids = ids;
+      for (int j = 0; j < 3; ++j) f.dil[j] = c.voc_res_dilations[j];
+      f.w = e->fW[i][r]; f.bias = e->fB[i][r]; f.w_copies = fused_weight_copies();
+      f.hist = e->fHist[i][r]; f.hist_slot_stride = (long long)e->fHistRows[i][r] * C;
+      f.sum_in = r > 0 ? e->vSUMh : nullptr;
+      f.sum_out = r < c.voc_n_res - 1 ? e->vSUMh : nullptr;
+      if (r == c.voc_n_res - 1) { f.next = next.at_row(next.H); f.next_slot_stride = next.slot_stride(); f.next_row0 = 0; }
+      f.out_scale = 1.0f / (float)c.voc_n_res; f.slope = sl;
+      TRY(run_fused(e, f, st));
+    }
+    for (int r = 0; r < c.voc_n_res && !e->vFused[i]; ++r) {
       const int k = c.voc_res_kernels[r];
       std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
       const float* xj = e->vXS;

@@ -77,6 +77,22 @@ int launch_rows_to_view(const float* src_slot, RowView out, int n, const int* sl
 int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, int row_stride, int row0, int L, int C, int k,
                           const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st);
 
+// fused HiFi-GAN residual block on tcgen05 (resblock_fused.cu) -------------------------------------------------
+struct ResblockFusedParams {
+  const void* x; long long x_slot_stride; int x_rows, x_hist_rows, n_slots;   // compact fp16 input context [i][x_rows][C] = lrelu(x)
+  int C, L, k; int dil[3]; int n_streams;
+  const int* slot_ids;                              // slot of stream i (history block index)
+  const void* w; const float* bias;                 // packed [w_copies][6*C][k*C] fp16 (c1.0, c2.0, c1.1, c2.1, c1.2, c2.2) and [6*C] fp32
+  int w_copies;                                     // identical copies of the packed weights (spreads the L2 load of lockstep CTAs)
+  void* hist; long long hist_slot_stride;           // resident fp16 history [slot][resblock_fused_hist_rows][C] (elements)
+  const void* sum_in; void* sum_out;                // running MRF sum, compact fp16 [i][L][C] (either may be null)
+  void* next; long long next_slot_stride; int next_row0;    // following layer's context rows <- lrelu(out_scale * (x_out + sum_in))
+  float out_scale, slope;
+};
+bool resblock_fused_eligible(int C, int L, int k, const int* dil);
+int resblock_fused_hist_rows(int k, const int* dil);
+int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st);
+
 // state maintenance --------------------------------------------------------------------------
 // Resident history of a context buffer lives per slot in `hist` [slot, hist_bytes]; the step works on a compact
 // buffer `work` [i, hist_bytes + new_bytes].  gather: hist[slot_i] -> work[i][0 : hist);  scatter: the last

@@ -76,7 +76,9 @@ typedef struct conan_config {
                                      read; 0: keep an fp32 residual stream (reference-grade path) */
   int32_t lin_use_tensor_cores;   /* 1: Emformer / Conan linear + conv contractions on tcgen05 with split-fp16 operands
                                      (x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, fp32 accumulate: fp32-grade results); 0: fp32 FFMA */
-  int32_t reserved[6];
+  int32_t voc_fuse_resblocks;     /* 1: at the scales with 32 / 64 channels a whole residual block (six convs) runs as one tcgen05 kernel
+                                     with the activations kept in shared memory (needs tensor cores + voc_residual_from_ctx) */
+  int32_t reserved[5];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */

@@ -346,6 +346,34 @@ def test_decoder_step_vs_oracle_teacher_forced(state_dicts, which, request):
     assert len(buckets) > 8                          # the bucket arithmetic is genuinely exercised
 
 
+def test_decoder_long_reference(state_dicts):
+    """A 600-frame reference (150 prosody tokens): more keys than the shared-memory-staged aligner attention
+    holds, so the general warp-per-(stream, head) kernel runs; also ragged reference lengths in one batch."""
+    from oracle.incremental import ConanOracle
+    eng = _engine(state_dicts, max_slots=4, max_ref_frames=640)
+    try:
+        lens = [600, 333]
+        g = torch.Generator().manual_seed(4)
+        tokens = torch.randint(0, 100, (2, 16), generator=g)
+        worst = 0.0
+        with torch.no_grad():
+            for b, n in enumerate(lens):                 # the oracle takes one reference length per call
+                ref = synth.synth_mel(n, 70 + b)[None]
+                o = ConanOracle(state_dicts[0])
+                o.open(ref)
+                eng.reset_slots([b + 1])
+                eng.open_sessions([b + 1], ref.cuda())
+                ids = eng.ids_tensor([b + 1])
+                for c in range(4):
+                    tk = tokens[b:b + 1, c * 4:(c + 1) * 4]
+                    mel = eng.decoder_step(ids, tk.to(torch.int32).contiguous().cuda())
+                    worst = max(worst, (mel.cpu() - o.step(tk)).abs().max().item())
+        print("long-reference decoder mel max-abs", worst)
+        assert worst < MEL_TOL
+    finally:
+        eng.close()
+
+
 # ------------------------------------------------------------------------------------------
 # vocoder
 # ------------------------------------------------------------------------------------------
@@ -394,6 +422,30 @@ def test_vocoder_tcgen05_matches_ffma_same_operands(eng_fp16_ffma, eng_tc):
     err = (a - b).abs().max().item()
     print("tcgen05 vs ffma (fp16 operands) max-abs", err, "SNR", snr_db(a.numpy(), b.numpy()))
     assert snr_db(a.numpy(), b.numpy()) > 55.0
+
+
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+def test_vocoder_fused_resblocks_match_per_conv_path(state_dicts):
+    """The fused residual-block kernel (six convs per launch, activations in shared memory, per-slot history blocks)
+    computes the same fp16-operand / fp32-accumulate arithmetic as the conv-by-conv path: over several chunks
+    (history hand-over between steps), with a permuted slot list, a stream count that does not fill the machine, and a
+    second utterance on a reset slot."""
+    g = torch.Generator().manual_seed(12)
+    mel = torch.randn(5, 24, 80, generator=g) * 0.6
+    mel2 = torch.randn(5, 8, 80, generator=g) * 0.6
+    slots = [6, 0, 3, 7, 2]
+    outs = []
+    for fuse in (False, True):
+        eng = _engine(state_dicts, voc_fuse_resblocks=fuse)
+        assert bool(eng.cfg.voc_fuse_resblocks) == fuse
+        a = _run_vocoder(eng, mel, slots)
+        b = _run_vocoder(eng, mel2, slots[::-1])           # reset + different slot <-> stream mapping
+        outs.append((a, b))
+        eng.close()
+    for x, y in zip(outs[0], outs[1]):
+        err = (x - y).abs().max().item()
+        print("fused vs per-conv vocoder max-abs", err, "SNR", snr_db(x.numpy(), y.numpy()))
+        assert snr_db(x.numpy(), y.numpy()) > 70.0
 
 
 def test_vocoder_group_blocking_is_exact(state_dicts):
