@@ -230,7 +230,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * SL::STAGE_BYTES + 256);
   stage_bias(s_bias, a.e.bias, a.cout);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: provably warp-uniform role branches
   // a tile is NS = 128/TT consecutive streams x TT consecutive time steps: one rectangular TMA box.
   // Persistent CTAs walk the tiles round-robin; consecutive tile ids share the A rows (nt fastest).
   const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
@@ -376,7 +376,7 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);
   stage_bias(s_bias, a.e.bias, BN);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: provably warp-uniform role branches
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");

@@ -41,7 +41,8 @@ struct FusedArgs {
   int H[RF_CONVS];             // halo rows of the window conv c reads ((k-1) * its dilation)
   int win_off[RF_CONVS];       // byte offset of window c in shared memory (c = 0: input buffer 0)
   int hist_off[RF_CONVS];      // first row of window c's history inside the slot's history block
-  int in_winb, wt_off, bar_off, bias_off, stages, group, w_copies;      // group: taps per weight stage
+  int in_winb, wt_off, bar_off, bias_off, stages, group, w_copies;
+  int dbg;                     // timing experiments only (CONAN_FUSED_DEBUG): 1 = weights fetched once, 2 = epilogue math skipped      // group: taps per weight stage
   const int* slot_ids;
   __half* hist; long long hist_slot_stride;                            // [slot][hist rows][C]
   const float* bias;                                                   // [6][C]
@@ -76,7 +77,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(smem + a.bias_off);
   for (int i = threadIdx.x; i < RF_CONVS * C; i += blockDim.x) s_bias[i] = a.bias[i];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: provably warp-uniform role branches
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -102,7 +103,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int i = blockIdx.x; i < a.n_streams; i += gridDim.x)
         for (int t = 0; t < a.tiles; ++t, ++it) {
           const int buf = it & 1;
-          mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+          mbar_wait_lane0(&a_empty[buf], ((it >> 1) & 1) ^ 1, 64);
           if (elect_one_sync()) {
             mbar_expect_tx(&a_full[buf], (uint32_t)(in_rows * ROWB));
             tma_load_3d(smem + buf * a.in_winb, &tmA, &a_full[buf], 0, a.in_row0 + t * TILE_M, i);
@@ -112,15 +113,16 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 2) {
     // ===================================================================== weight producer (`group` taps per stage)
     {
-      int s = 0;
+      int s = 0, cnt = 0;
       uint32_t ph = 1;                                      // parity that lets the first pass through the ring proceed
       const int wcopy = blockIdx.x % a.w_copies;
       for (int i = blockIdx.x; i < a.n_streams; i += gridDim.x)
         for (int t = 0; t < a.tiles; ++t)
           for (int c = 0; c < RF_CONVS; ++c)
-            for (int j0 = 0; j0 < a.k; j0 += a.group) {
+            for (int j0 = 0; j0 < a.k; j0 += a.group, ++cnt) {
               const int nt = min(a.group, a.k - j0);
-              mbar_wait(&w_empty[s], ph);
+              if ((a.dbg & 1) && cnt >= a.stages) continue;
+              mbar_wait_lane0(&w_empty[s], ph, 32);
               if (elect_one_sync()) {
                 mbar_expect_tx(&w_full[s], (uint32_t)(nt * TAPB));
                 uint8_t* dst = smem + a.wt_off + s * a.group * TAPB;
@@ -139,29 +141,27 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint64_t desc0 = make_smem_desc<ROWB>(s32);                  // descriptor of the (1024-aligned) buffer base
       const uint64_t wdesc0 = desc0 + (uint64_t)(a.wt_off >> 4);
       const uint32_t stage_step = (uint32_t)((a.group * TAPB) >> 4);
-      int it = 0, s = 0;
+      int it = 0, s = 0, cnt = 0;
       uint32_t n = 0, wph = 0;
       for (int i = blockIdx.x; i < a.n_streams; i += gridDim.x)
         for (int t = 0; t < a.tiles; ++t, ++it)
-          for (int c = 0; c < RF_CONVS; ++c, ++n) {
-            if (c == 0) mbar_wait(&a_full[it & 1], (it >> 1) & 1);
-            else mbar_wait(&win_ready[c], it & 1);
+#pragma unroll
+          for (int c = 0; c < RF_CONVS; ++c, ++n) {        // unrolled: window offsets / dilations become uniform constant loads
+            if (c == 0) mbar_wait_warp(&a_full[it & 1], (it >> 1) & 1);
+            else mbar_wait_warp(&win_ready[c], it & 1);
             tc_fence_after();
             const uint64_t adesc = desc0 + (uint64_t)((c == 0 ? (it & 1) * a.in_winb : a.win_off[c]) >> 4);
             const uint32_t tap_step = (uint32_t)((((c & 1) ? 1 : a.dil[c >> 1]) * ROWB) >> 4);
             const uint32_t tacc = tmem_base + (uint32_t)((n & 1) * C);
             uint64_t ad = adesc;
-            for (int j0 = 0; j0 < a.k; j0 += a.group) {
+            for (int j0 = 0; j0 < a.k; j0 += a.group, ++cnt) {
               const int nt = min(a.group, a.k - j0);
-              mbar_wait(&w_full[s], wph);
+              if (!((a.dbg & 1) && cnt >= a.stages)) mbar_wait_warp(&w_full[s], wph);
               tc_fence_after();
               uint64_t bd = wdesc0 + (uint64_t)(s * stage_step);
-              for (int j = 0; j < nt; ++j, ad += tap_step, bd += (TAPB >> 4)) {
-#pragma unroll
-                for (int kk = 0; kk < C / 16; ++kk)
-                  if (elect_one_sync()) tc_mma_f16(tacc, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (j0 | j | kk) != 0 ? 1u : 0u);
-              }
-              if (elect_one_sync()) tc_commit(&w_empty[s]);
+              for (int j = 0; j < nt; ++j, ad += tap_step, bd += (TAPB >> 4))
+                tc_mma_f16_tap<C / 16>(tacc, ad, bd, idesc, (j0 | j) == 0 ? 1u : 0u);
+              if (!(a.dbg & 1) && elect_one_sync()) tc_commit(&w_empty[s]);
               if (++s == a.stages) { s = 0; wph ^= 1; }
             }
             if (elect_one_sync()) tc_commit(&acc_full[n & 1]);
@@ -210,7 +210,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int u = 0; u < HALF / 8; ++u) rv[u] = *reinterpret_cast<const uint4*>(resw + swz<ROWB>(resrow + (uint32_t)(wg * HALF * 2 + u * 16)));
           }
-          mbar_wait(&acc_full[ab], (n >> 1) & 1);
+          mbar_wait_lane0(&acc_full[ab], (n >> 1) & 1, a.dbg & 4 ? 0 : 32);
           tc_fence_after();
           const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * C + wg * HALF);
           uint32_t acc[HALF];
@@ -218,7 +218,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int ch16 = 0; ch16 < HALF / 16; ++ch16) tc_ld_32x32b_x16_nowait(tl + (uint32_t)(ch16 * 16), &acc[ch16 * 16]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int ch16 = 0; ch16 < HALF / 16; ++ch16) {
+          for (int ch16 = 0; ch16 < ((a.dbg & 2) ? 0 : HALF / 16); ++ch16) {
             const int col0 = wg * HALF + ch16 * 16;
             float v[16];
 #pragma unroll
@@ -383,6 +383,7 @@ int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st) {
     return 1;
   const unsigned long long Ktot = (unsigned long long)p.k * C;
   a.w_copies = p.w_copies > 0 ? p.w_copies : 1;
+  { static int dbg = [] { const char* v = getenv("CONAN_FUSED_DEBUG"); return v ? atoi(v) : 0; }(); a.dbg = dbg; }
   if (get_tensor_map(&tmW, p.w, 3, Ktot, (unsigned long long)RF_CONVS * C, (unsigned long long)a.w_copies, Ktot * 2,
                      Ktot * 2 * RF_CONVS * C, C, C, 1, ROWB))
     return 1;

@@ -33,6 +33,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// Polling costs shared-memory bandwidth that the tensor core also needs for its A / B operand reads (SS-mode MMAs
+// stream 64 B/cycle from shared memory): waits that are expected to be long are done by ONE lane per warp with a
+// sleep between polls; the rest of the warp parks on __syncwarp, which also orders memory among the lanes.
+__device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if ((threadIdx.x & 31) == 0) {
+    while (!mbar_try_wait(bar, parity)) { if (ns) __nanosleep(ns); }
+  }
+  __syncwarp();
+}
+// wait executed by a whole converged warp with a warp-uniform exit condition (vote): the code after it stays provably
+// convergent, which lets ptxas keep loop-carried descriptors / counters of the issuing loops in uniform registers
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {}
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -93,6 +107,43 @@ __device__ __forceinline__ void tc_ld_32x32b_x16_nowait(uint32_t taddr, uint32_t
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+
+// NK consecutive K = 16 steps of one tap (A and B advance 32 bytes inside the swizzle atom per step) issued by one
+// elected lane from a single PTX block: one elect per tap instead of one per MMA, and a straight-line sequence for ptxas.
+// `first` != 0 makes the very first MMA overwrite the accumulator.
+template <int NK>
+__device__ __forceinline__ void tc_mma_f16_tap(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t first) {
+  static_assert(NK == 2 || NK == 4, "C = 32 or 64");
+  if (NK == 4) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b64 a1, b1, a2, b2, a3, b3;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "setp.eq.b32 q, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "add.u64 a1, %1, 2;\n add.u64 b1, %2, 2;\n"
+        "add.u64 a2, %1, 4;\n add.u64 b2, %2, 4;\n"
+        "add.u64 a3, %1, 6;\n add.u64 b3, %2, 6;\n"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(first) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b64 a1, b1;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "setp.eq.b32 q, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "add.u64 a1, %1, 2;\n add.u64 b1, %2, 2;\n"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(first) : "memory");
+  }
 }
 
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):

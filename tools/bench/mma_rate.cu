@@ -1,0 +1,86 @@
+// Micro-benchmark: issue rate of tcgen05.mma (kind::f16, M = 128, fp32 accumulate, SS mode) on one SM as a function
+// of N, of the swizzle span, and of the A start-row offset inside the swizzle atom (the "taps are row offsets" trick
+// of the conv kernels).  Build + run on the GPU box:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I conan_b200/csrc tools/bench/mma_rate.cu -o /tmp/mma_rate && /tmp/mma_rate
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "tc_common.cuh"
+using namespace conan;
+
+template <int N, int ROWB, int NACC>
+__global__ void __launch_bounds__(128) rate_kernel(int iters, int a_row_step, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  constexpr int KK = ROWB / 32, TAPS = 8;
+  if (warp == 0) {
+    constexpr uint32_t idesc = make_idesc<N>();
+    const uint32_t s32 = smem_u32(smem);
+    const uint64_t adesc0 = make_smem_desc<ROWB>(s32), bdesc0 = make_smem_desc<ROWB>(s32 + 48 * 1024);
+    const uint64_t step = (uint64_t)((a_row_step * ROWB) >> 4);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk)
+          if (elect_one_sync())
+            tc_mma_f16(tmem_base + (uint32_t)((tap % NACC) * N), adesc0 + tap * step + (uint64_t)(kk * 2), bdesc0 + (uint64_t)(tap * 64 + kk * 2), idesc, 1u);
+      }
+    }
+    if (elect_one_sync()) tc_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
+template <int N, int ROWB, int NACC = 1>
+void run(const char* name, int a_row_step, int grid) {
+  long long* d; cudaMalloc(&d, 8);
+  auto k = rate_kernel<N, ROWB, NACC>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int iters = 500, per_it = 8 * (ROWB / 32);
+  k<<<grid, 128, 100 * 1024>>>(iters, a_row_step, d);
+  k<<<grid, 128, 100 * 1024>>>(iters, a_row_step, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  printf("%-34s N=%3d span=%3dB a_row_step=%2d grid=%3d accs=%d : %7.1f cycles / MMA (floor N/2 = %d)  %s\n", name, N, ROWB, a_row_step, grid, NACC,
+         (double)h / (iters * per_it), N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+int main() {
+  for (int grid : {1, 148}) {
+    run<32, 64>("C=32 window conv", 0, grid);   run<32, 64>("C=32 window conv, taps", 1, grid);  run<32, 64>("C=32 window conv, taps dil 5", 5, grid);
+    run<64, 128>("C=64 window conv", 0, grid);  run<64, 128>("C=64 window conv, taps", 1, grid); run<64, 128>("C=64 window conv, taps dil 5", 5, grid);
+    run<64, 128>("C=64, atom-aligned taps", 8, grid);
+    run<128, 128>("ring 128x128", 0, grid);     run<128, 128>("ring 128x128, taps", 1, grid);
+    run<256, 128>("N=256", 0, grid);
+  }
+  // independent accumulators: is the minimum a dependent-accumulate latency or an operand-read throughput limit?
+  run<32, 64, 2>("C=32, 2 accumulators", 1, 148);  run<32, 64, 4>("C=32, 4 accumulators", 1, 148);
+  run<32, 128, 1>("N=32 on 128B rows", 1, 148);    run<32, 128, 2>("N=32 on 128B rows", 1, 148);
+  run<64, 128, 2>("C=64, 2 accumulators", 1, 148); run<64, 128, 4>("C=64, 4 accumulators", 1, 148);
+  run<128, 128, 2>("N=128, 2 accumulators", 1, 148);
+  run<16, 128, 1>("N=16 on 128B rows", 1, 148);
+  // two CTAs per SM, each with its own accumulator
+  run<32, 64>("C=32, 2 CTAs/SM", 1, 296); run<64, 128>("C=64, 2 CTAs/SM", 1, 296); run<128, 128>("N=128, 2 CTAs/SM", 1, 296);
+  return 0;
+}
