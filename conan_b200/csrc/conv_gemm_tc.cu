@@ -221,7 +221,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulators: MMAs of tile i+1 overlap the epilogue of tile i
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SL::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;
@@ -362,7 +362,7 @@ conv_window_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   constexpr int TAPB = BN * ROWB;                   // one tap of the weight matrix
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   const int winb = (a.win_rows * ROWB + 1023) & ~1023;
   uint8_t* sW = smem;
   uint8_t* sA = smem + ((a.k * TAPB + 1023) & ~1023);

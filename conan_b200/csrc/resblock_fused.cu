@@ -65,7 +65,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   constexpr int TMEM_COLS = 2 * C < 32 ? 32 : 2 * C;
   constexpr int HALF = C / 2;                       // columns per epilogue warpgroup
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* a_full = bars;                           // [2]
   uint64_t* a_empty = bars + 2;                      // [2]
