@@ -203,7 +203,7 @@ void declare_weights(conan_engine* e) {
   // vocoder
   const int wdt = c.voc_precision ? CONAN_DTYPE_F16 : CONAN_DTYPE_F32;
   int ch = c.voc_initial_channel;
-  need(e, "voc.pre.w", (size_t)ch * 7 * c.n_mels, wdt); need(e, "voc.pre.b", ch);
+  need(e, "voc.pre.w", (size_t)ch * 7 * (c.voc_use_tensor_cores ? pad32(c.n_mels) : c.n_mels), wdt); need(e, "voc.pre.b", ch);
   for (int i = 0; i < c.voc_n_ups; ++i) {
     int co = ch / 2;
     std::string p = "voc.up." + std::to_string(i) + ".";
@@ -403,7 +403,8 @@ int allocate_state(conan_engine* e) {
   const int hf = c.voc_precision ? 1 : 0;
   e->vL[0] = seg; e->vC[0] = c.voc_initial_channel;
   for (int i = 0; i < c.voc_n_ups; ++i) { e->vL[i + 1] = e->vL[i] * c.voc_rates[i]; e->vC[i + 1] = e->vC[i] / 2; }
-  TRY(alloc_ctx(e, &e->vPRE, 6, seg, 0, c.n_mels, hf));
+  // tensor-core mode: mel rows padded to a multiple of 32 channels (pad columns stay zero) so conv_pre is tcgen05-eligible
+  TRY(alloc_ctx(e, &e->vPRE, 6, seg, 0, c.voc_use_tensor_cores ? pad32(c.n_mels) : c.n_mels, hf));
   size_t maxLC = 0;
   std::vector<ZeroDesc> fused_zero;
   for (int i = 0; i < c.voc_n_ups; ++i) {

@@ -30,8 +30,10 @@ namespace conan {
 namespace {
 
 constexpr int RF_CONVS = 6;
-constexpr int RF_THREADS = 384;   // warp 0: input-window TMA, warp 1: MMA issuer (+TMEM alloc), warp 2: weight TMA, warps 4..11: epilogue
-constexpr int RF_EPI = 256;
+// warp 0: input-window TMA, warp 1: MMA issuer (+TMEM alloc), warp 2: weight TMA, warps 4..: epilogue warpgroups, one per
+// 16 output columns (C/16 warpgroups: every epilogue thread owns one row x 16 columns = one tcgen05.ld.x16)
+__host__ __device__ constexpr int rf_epi_threads(int C) { return 128 * (C / 16); }
+__host__ __device__ constexpr int rf_threads(int C) { return 128 + rf_epi_threads(C); }
 constexpr int RF_MAX_STAGES = 16;
 
 struct FusedArgs {
@@ -57,13 +59,14 @@ __device__ __forceinline__ uint32_t swz(uint32_t off) {      // byte offset insi
 }
 
 template <int C>
-__global__ void __launch_bounds__(RF_THREADS, C == 32 ? 2 : 1)
+__global__ void __launch_bounds__(rf_threads(C), C == 32 ? 2 : 1)
 resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, FusedArgs a) {
   constexpr int ROWB = C * 2;
   constexpr int CH = ROWB / 16;
   constexpr int TAPB = C * ROWB;
   constexpr int TMEM_COLS = 2 * C < 32 ? 32 : 2 * C;
-  constexpr int HALF = C / 2;                       // columns per epilogue warpgroup
+  constexpr int HALF = 16;                          // columns per epilogue warpgroup
+  constexpr int RF_EPI = rf_epi_threads(C);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
@@ -210,7 +213,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int u = 0; u < HALF / 8; ++u) rv[u] = *reinterpret_cast<const uint4*>(resw + swz<ROWB>(resrow + (uint32_t)(wg * HALF * 2 + u * 16)));
           }
-          mbar_wait_lane0(&acc_full[ab], (n >> 1) & 1, a.dbg & 4 ? 0 : 32);
+          mbar_wait_lane0(&acc_full[ab], (n >> 1) & 1, a.dbg & 4 ? 32 : 0);
           tc_fence_after();
           const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * C + wg * HALF);
           uint32_t acc[HALF];
@@ -222,7 +225,13 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int col0 = wg * HALF + ch16 * 16;
             float v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = __uint_as_float(acc[ch16 * 16 + u]) + s_bias[c * C + col0 + u];
+            for (int u = 0; u < 4; ++u) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c * C + col0 + 4 * u]);
+              v[4 * u] = __uint_as_float(acc[ch16 * 16 + 4 * u]) + b4.x;
+              v[4 * u + 1] = __uint_as_float(acc[ch16 * 16 + 4 * u + 1]) + b4.y;
+              v[4 * u + 2] = __uint_as_float(acc[ch16 * 16 + 4 * u + 2]) + b4.z;
+              v[4 * u + 3] = __uint_as_float(acc[ch16 * 16 + 4 * u + 3]) + b4.w;
+            }
             if (c & 1) {                                              // + x: inverse LeakyReLU of the rows conv c-1 consumed
 #pragma unroll
               for (int h8 = 0; h8 < 2; ++h8) {
@@ -326,10 +335,10 @@ int launch_fused_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const F
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
-  const int per_sm = resident_ctas((const void*)kern, RF_THREADS, smem, 2 * C < 32 ? 32 : 2 * C);
+  const int per_sm = resident_ctas((const void*)kern, rf_threads(C), smem, 2 * C < 32 ? 32 : 2 * C);
   const int grid = std::min(a.n_streams, num_sms() * per_sm);
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused<%d> k %d tiles/stream %d smem %zu per_sm %d grid %d\n", C, a.k, a.tiles, smem, per_sm, grid);
-  kern<<<grid, RF_THREADS, smem, st>>>(tmA, tmW, a);
+  kern<<<grid, rf_threads(C), smem, st>>>(tmA, tmW, a);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

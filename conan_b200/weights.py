@@ -131,7 +131,11 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
     # ---- vocoder
     v = sd_voc
     wdt = torch.float16 if cfg.voc_precision else torch.float32
-    out["voc.pre.w"], out["voc.pre.b"] = pack_conv(fold_weight_norm(v, "conv_pre.conv")).to(wdt), v["conv_pre.conv.bias"]
+    w_pre = fold_weight_norm(v, "conv_pre.conv")
+    if cfg.voc_use_tensor_cores:      # mel channels padded to a multiple of 32 (zero weights): conv_pre runs on the tcgen05 ring kernel
+        pad = (-w_pre.shape[1]) % 32
+        w_pre = torch.nn.functional.pad(w_pre, (0, 0, 0, pad))
+    out["voc.pre.w"], out["voc.pre.b"] = pack_conv(w_pre).to(wdt), v["conv_pre.conv.bias"]
     ch = cfg.voc_initial_channel
     rb = 0
     for i in range(cfg.voc_n_ups):
