@@ -33,7 +33,6 @@ namespace conan {
 
 namespace {
 
-constexpr int NUM_THREADS = 192;
 
 struct TcEpi {
   const float* bias; float scale; int act; float slope;
@@ -51,7 +50,8 @@ struct TcArgs {
   int n_streams, L, TT, cin, k, dil, cout, row0;
   int kblocks;               // nseg * k * cin / BK
   int n_tiles;               // cout / BN
-  int num_tiles;             // m_tiles * n_tiles
+  int m_tiles;               // 128-row tiles over (stream, time)
+  int num_tiles;             // CTA tiles: ceil(m_tiles / MT) * n_tiles
   int nseg;                  // 1, or 3 for split operands: K' = [x_hi*W_hi | x_hi*W_lo | x_lo*W_hi]
   int lo_slot_off;           // slot offset of the lo plane of a split x
   TcEpi e;
@@ -205,21 +205,28 @@ __device__ __forceinline__ void stage_bias(float* s_bias, const float* bias, int
   for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = bias ? bias[i] : 0.f;
 }
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int MT>
 struct SmemLayout {
-  static constexpr int A_BYTES = TILE_M * BK * 2;
+  static constexpr int A1_BYTES = TILE_M * BK * 2;      // one 128-row A tile
+  static constexpr int A_BYTES = MT * A1_BYTES;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_BYTES = 2048 * 4;           // bias of up to 2048 output channels
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/ + BIAS_BYTES;
 };
 
-template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, BN >= 128 ? 2 : (BN >= 64 ? 3 : 4))
+// MT = m-tiles per CTA tile.  The vocoder layers run at the L2 -> SM bandwidth limit (every k-block brings 16 KB of A and
+// 16 KB of B for four 128x128x16 MMAs), so MT = 2 lets two 128-row A tiles share each B tile: 48 KB per eight MMAs instead
+// of 64 KB.  Each m-tile of the pair has its own double-buffered TMEM accumulator (4 x 128 columns = all of TMEM, hence
+// one CTA per SM) and its own epilogue warpgroup.
+// ES = epilogue warpgroups per m-tile, each draining BN / ES accumulator columns (the short-K layers are bound by the
+// epilogue's latency, not by the MMAs: more warps in flight per tile).
+template <int BN, int BK, int STAGES, int MT, int ES>
+__global__ void __launch_bounds__(64 + 128 * MT * ES, MT == 2 ? 1 : (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4)))
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
-  using SL = SmemLayout<BN, BK, STAGES>;
+  using SL = SmemLayout<BN, BK, STAGES, MT>;
   constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
-  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulators: MMAs of tile i+1 overlap the epilogue of tile i
+  constexpr int TMEM_COLS = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;     // two accumulators per m-tile: MMAs of tile i+1 overlap the epilogue of tile i
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SL::STAGE_BYTES);
@@ -232,14 +239,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: provably warp-uniform role branches
   // a tile is NS = 128/TT consecutive streams x TT consecutive time steps: one rectangular TMA box.
-  // Persistent CTAs walk the tiles round-robin; consecutive tile ids share the A rows (nt fastest).
+  // Persistent CTAs walk the tiles round-robin; consecutive tile ids share the A rows (nt fastest).  With MT = 2 a CTA tile is
+  // the pair of m-tiles (2q, 2q+1); the second one may lie past the end (odd count): it is computed on stale operands and dropped.
   const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128 * MT * ES); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -260,8 +268,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int kb_per_seg = a.kblocks / a.nseg;
       int kbg = 0;                                           // k-block counter across tiles (the smem ring never drains)
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
-        const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
+        const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * MT;
         for (int kb = 0; kb < a.kblocks; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (kbg / STAGES) & 1;
@@ -271,8 +278,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int seg = kb / kb_per_seg, kbl = kb - seg * kb_per_seg;
           const int j = kbl / kb_per_tap, c0 = (kbl - j * kb_per_tap) * BK;
           if (elect_one_sync()) {
-            mbar_expect_tx(&full_bar[s], SL::STAGE_BYTES);
-            tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
+            const bool second = MT == 2 && mt + 1 < a.m_tiles;
+            mbar_expect_tx(&full_bar[s], SL::B_BYTES + (second ? 2 : 1) * SL::A1_BYTES);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              if (m == 1 && !second) break;
+              const int stream0 = ((mt + m) / TPS) * NS, t0 = ((mt + m) % TPS) * a.TT;
+              tma_load_3d(sa + m * SL::A1_BYTES, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil,
+                          stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
+            }
             tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
           }
         }
@@ -288,7 +302,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[ab], aph ^ 1);                  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * MT * BN);
         for (int kb = 0; kb < a.kblocks; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (kbg / STAGES) & 1;
@@ -296,19 +310,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
           const uint32_t sb = sa + SL::A_BYTES;
-          const uint64_t adesc = make_smem_desc<SWZ>(sa), bdesc = make_smem_desc<SWZ>(sb);
+          const uint64_t bdesc = make_smem_desc<SWZ>(sb);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            // advance 16 halfs = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-            if (elect_one_sync()) tc_mma_f16(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t adesc = make_smem_desc<SWZ>(sa + m * SL::A1_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // advance 16 halfs = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+              if (elect_one_sync())
+                tc_mma_f16(tacc + (uint32_t)(m * BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
           }
           if (elect_one_sync()) tc_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
         }
-        if (elect_one_sync()) tc_commit(&acc_full[ab]);            // accumulator complete
+        if (elect_one_sync()) tc_commit(&acc_full[ab]);            // accumulators complete
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (one warpgroup per m-tile of the CTA tile)
+    const int wgi = (warp - 2) >> 2;         // warpgroup index: m-tile of the pair (slow) x column part (fast)
+    const int wg = wgi / ES, cpart = wgi - wg * ES;
+    constexpr int BNE = BN / ES;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;       // tile row == TMEM lane
     const int q = r / a.TT, tt = r - q * a.TT;
@@ -316,10 +338,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+      const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * MT + wg;
       const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
-      epilogue_rows<BN>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN), nt * BN, stream < a.n_streams,
-                        stream, t, &acc_full[ab], aph);
+      epilogue_rows<BNE>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * MT + wg) * BN + cpart * BNE),
+                         nt * BN + cpart * BNE, mt < a.m_tiles && stream < a.n_streams, stream, t, &acc_full[ab], aph);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
     }
@@ -579,23 +601,25 @@ int pick_bn(int cout) {
   return 0;
 }
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int MT = 1, int ES = 1>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, long long m_tiles, cudaStream_t st) {
-  using SL = SmemLayout<BN, BK, STAGES>;
-  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES>;
+  using SL = SmemLayout<BN, BK, STAGES, MT>;
+  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES, MT, ES>;
+  constexpr int threads = 64 + 128 * MT * ES;
   static bool attr_set = false;
   static int per_sm = 1;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-    per_sm = resident_ctas((const void*)kern, NUM_THREADS, SL::TOTAL, 2 * BN);
+    per_sm = resident_ctas((const void*)kern, threads, SL::TOTAL, 2 * MT * BN);
     attr_set = true;
   }
-  a.num_tiles = (int)(m_tiles * a.n_tiles);
+  a.m_tiles = (int)m_tiles;
+  a.num_tiles = (int)(((m_tiles + MT - 1) / MT) * a.n_tiles);
   const int grid = std::min(a.num_tiles, num_sms() * per_sm);           // persistent: exactly the co-resident CTAs
-  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "ring<%d,%d,%d> tiles %d per_sm %d grid %d\n", BN, BK, STAGES, a.num_tiles, per_sm, grid);
-  if (launch_pdl(kern, grid, NUM_THREADS, SL::TOTAL, st, tmA, tmW, a)) return 1;
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "ring<%d,%d,%d,%d,%d> tiles %d per_sm %d grid %d\n", BN, BK, STAGES, MT, ES, a.num_tiles, per_sm, grid);
+  if (launch_pdl(kern, grid, threads, SL::TOTAL, st, tmA, tmW, a)) return 1;
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -721,7 +745,17 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   // spend the shared memory on pipeline depth instead of co-residency.
   const bool deep = m_tiles * a.n_tiles <= 2 * num_sms() && a.kblocks >= 12;
   if (BK == 64) {
-    if (BN == 128) return deep ? launch_variant<128, 64, 6>(tmA, tmW, a, m_tiles, st) : launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
+    if (BN == 128) {
+      if (deep) return launch_variant<128, 64, 6>(tmA, tmW, a, m_tiles, st);
+      // enough tiles to fill the machine with pairs: two m-tiles share every B tile (the layer is L2 -> SM bandwidth bound)
+      static const int pair_mode = [] { const char* v = getenv("CONAN_TC_PAIR"); return v ? atoi(v) : 2; }();
+      if (nseg == 1 && m_tiles * a.n_tiles >= 4LL * num_sms()) {
+        if (pair_mode == 1) return launch_variant<128, 64, 4, 2, 1>(tmA, tmW, a, m_tiles, st);
+        if (pair_mode == 2) return launch_variant<128, 64, 3, 1, 2>(tmA, tmW, a, m_tiles, st);
+        if (pair_mode == 3) return launch_variant<128, 64, 4, 2, 2>(tmA, tmW, a, m_tiles, st);
+      }
+      return launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
+    }
     if (BN == 64) return deep ? launch_variant<64, 64, 8>(tmA, tmW, a, m_tiles, st) : launch_variant<64, 64, 2>(tmA, tmW, a, m_tiles, st);
     return deep ? launch_variant<32, 64, 8>(tmA, tmW, a, m_tiles, st) : launch_variant<32, 64, 2>(tmA, tmW, a, m_tiles, st);
   }

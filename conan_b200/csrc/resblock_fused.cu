@@ -44,6 +44,8 @@ struct FusedArgs {
   int win_off[RF_CONVS];       // byte offset of window c in shared memory (c = 0: input buffer 0)
   int hist_off[RF_CONVS];      // first row of window c's history inside the slot's history block
   int in_winb, wt_off, bar_off, bias_off, stages, group, w_copies;
+  int in_single;               // 1: one input-window buffer (C = 64: the shared memory goes to a deeper weight ring instead)
+  long long* ts;               // optional timeline buffer (CONAN_FUSED_TIMELINE): CTA 0 stamps clock64 at each hand-over
   int dbg;                     // timing experiments only (CONAN_FUSED_DEBUG): 1 = weights fetched once, 2 = epilogue math skipped      // group: taps per weight stage
   const int* slot_ids;
   __half* hist; long long hist_slot_stride;                            // [slot][hist rows][C]
@@ -58,7 +60,9 @@ __device__ __forceinline__ uint32_t swz(uint32_t off) {      // byte offset insi
   return off ^ (((off >> 7) & (ROWB == 128 ? 7u : 3u)) << 4);
 }
 
-template <int C>
+// KT: kernel size known at compile time (3 / 7 / 11: the MMA issue loop is then fully unrolled, which matters -- the issuing
+// warp, not the tensor pipe, paces a conv of k x C/16 short MMAs), or 0 for any k.
+template <int C, int KT>
 __global__ void __launch_bounds__(rf_threads(C), C == 32 ? 2 : 1)
 resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, FusedArgs a) {
   constexpr int ROWB = C * 2;
@@ -105,8 +109,8 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int it = 0;
       for (int i = blockIdx.x; i < a.n_streams; i += gridDim.x)
         for (int t = 0; t < a.tiles; ++t, ++it) {
-          const int buf = it & 1;
-          mbar_wait_lane0(&a_empty[buf], ((it >> 1) & 1) ^ 1, 64);
+          const int buf = a.in_single ? 0 : (it & 1);
+          mbar_wait_lane0(&a_empty[buf], ((a.in_single ? it : (it >> 1)) & 1) ^ 1, 64);
           if (elect_one_sync()) {
             mbar_expect_tx(&a_full[buf], (uint32_t)(in_rows * ROWB));
             tma_load_3d(smem + buf * a.in_winb, &tmA, &a_full[buf], 0, a.in_row0 + t * TILE_M, i);
@@ -150,24 +154,38 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int t = 0; t < a.tiles; ++t, ++it)
 #pragma unroll
           for (int c = 0; c < RF_CONVS; ++c, ++n) {        // unrolled: window offsets / dilations become uniform constant loads
-            if (c == 0) mbar_wait_warp(&a_full[it & 1], (it >> 1) & 1);
+            const int ibuf = a.in_single ? 0 : (it & 1);
+            if (c == 0) mbar_wait_warp(&a_full[ibuf], (a.in_single ? it : (it >> 1)) & 1);
             else mbar_wait_warp(&win_ready[c], it & 1);
             tc_fence_after();
-            const uint64_t adesc = desc0 + (uint64_t)((c == 0 ? (it & 1) * a.in_winb : a.win_off[c]) >> 4);
+            if (a.ts && blockIdx.x == 0 && n < 64 && elect_one_sync()) a.ts[n * 8 + 0] = clock64();      // window ready seen by the MMA warp
+            const uint64_t adesc = desc0 + (uint64_t)((c == 0 ? ibuf * a.in_winb : a.win_off[c]) >> 4);
             const uint32_t tap_step = (uint32_t)((((c & 1) ? 1 : a.dil[c >> 1]) * ROWB) >> 4);
             const uint32_t tacc = tmem_base + (uint32_t)((n & 1) * C);
             uint64_t ad = adesc;
-            for (int j0 = 0; j0 < a.k; j0 += a.group, ++cnt) {
-              const int nt = min(a.group, a.k - j0);
+            constexpr int GROUP = C == 64 ? 2 : 4;            // taps per weight stage (the host sets a.group to the same value)
+            const int kk_taps = KT > 0 ? KT : a.k;
+#pragma unroll
+            for (int j0 = 0; j0 < (KT > 0 ? KT : 64); j0 += GROUP) {
+              if (KT == 0 && j0 >= kk_taps) break;
               if (!((a.dbg & 1) && cnt >= a.stages)) mbar_wait_warp(&w_full[s], wph);
               tc_fence_after();
+              if (a.ts && blockIdx.x == 0 && n < 64 && j0 == 0 && elect_one_sync()) a.ts[n * 8 + 6] = clock64();   // first weight group landed
               uint64_t bd = wdesc0 + (uint64_t)(s * stage_step);
-              for (int j = 0; j < nt; ++j, ad += tap_step, bd += (TAPB >> 4))
-                tc_mma_f16_tap<C / 16>(tacc, ad, bd, idesc, (j0 | j) == 0 ? 1u : 0u);
+#pragma unroll
+              for (int j = 0; j < GROUP; ++j) {
+                if (j0 + j < kk_taps) {
+                  tc_mma_f16_tap<C / 16>(tacc, ad, bd, idesc, (j0 | j) == 0 ? 1u : 0u);
+                  ad += tap_step; bd += (TAPB >> 4);
+                }
+              }
               if (!(a.dbg & 1) && elect_one_sync()) tc_commit(&w_empty[s]);
+              if (a.ts && blockIdx.x == 0 && n < 64 && j0 == 0 && elect_one_sync()) a.ts[n * 8 + 7] = clock64();   // first group issued
               if (++s == a.stages) { s = 0; wph ^= 1; }
+              ++cnt;
             }
             if (elect_one_sync()) tc_commit(&acc_full[n & 1]);
+            if (a.ts && blockIdx.x == 0 && n < 64 && elect_one_sync()) a.ts[n * 8 + 1] = clock64();      // last MMA + commit issued
           }
     }
   } else if (warp >= 4) {
@@ -202,7 +220,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int u = 0; u < HALF / 8; ++u) sprev[u] = *(reinterpret_cast<const uint4*>(sp) + u);
           }
-          const uint8_t* resw = smem + (c == 1 ? (it & 1) * a.in_winb : a.win_off[c > 0 ? c - 1 : 0]);
+          const uint8_t* resw = smem + (c == 1 ? (a.in_single ? 0 : (it & 1)) * a.in_winb : a.win_off[c > 0 ? c - 1 : 0]);
           const uint32_t resrow = (uint32_t)((a.H[c > 0 ? c - 1 : 0] + r) * ROWB);
           uint8_t* dstw = smem + a.win_off[c < RF_CONVS - 1 ? c + 1 : 0];
           const uint32_t dstrow = (uint32_t)((a.H[c < RF_CONVS - 1 ? c + 1 : 0] + r) * ROWB);
@@ -215,11 +233,14 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           mbar_wait_lane0(&acc_full[ab], (n >> 1) & 1, a.dbg & 4 ? 32 : 0);
           tc_fence_after();
+          const bool stamp = a.ts && blockIdx.x == 0 && n < 64 && etid == 0;
+          if (a.ts) { if (stamp) a.ts[n * 8 + 2] = clock64(); __syncwarp(); }                                                   // accumulator complete seen by the epilogue
           const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * C + wg * HALF);
           uint32_t acc[HALF];
 #pragma unroll
           for (int ch16 = 0; ch16 < HALF / 16; ++ch16) tc_ld_32x32b_x16_nowait(tl + (uint32_t)(ch16 * 16), &acc[ch16 * 16]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (a.ts) { if (stamp) a.ts[n * 8 + 3] = clock64(); __syncwarp(); }                                                   // TMEM read done
 #pragma unroll
           for (int ch16 = 0; ch16 < ((a.dbg & 2) ? 0 : HALF / 16); ++ch16) {
             const int col0 = wg * HALF + ch16 * 16;
@@ -294,12 +315,14 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               }
             }
           }
-          if (c == 1) mbar_arrive(&a_empty[it & 1]);                 // the input window (A operand of conv 0, residual of conv 1) is free
+          if (c == 1) mbar_arrive(&a_empty[a.in_single ? 0 : (it & 1)]);                 // the input window (A operand of conv 0, residual of conv 1) is free
           tc_fence_before();
+          if (a.ts) { if (stamp) a.ts[n * 8 + 4] = clock64(); __syncwarp(); }                                                   // math + stores done
           if (c < RF_CONVS - 1) {
             fence_proxy_async_smem();                                 // rows written above are read by tcgen05.mma
             mbar_arrive(&win_ready[c + 1]);
           }
+          if (a.ts) { if (stamp) a.ts[n * 8 + 5] = clock64(); __syncwarp(); }                                                   // hand-over signalled
           if (c >= 1) {
             // window c has been consumed (its accumulator is complete): its newest H rows are the next tile's history, or the
             // slot's after the last tile.  Off the critical path: the next reader of these rows is conv c of the NEXT tile,
@@ -325,9 +348,9 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 inline int align1k(int x) { return (x + 1023) & ~1023; }
 
-template <int C>
+template <int C, int KT>
 int launch_fused_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const FusedArgs& a, size_t smem, cudaStream_t st) {
-  auto kern = resblock_fused_kernel<C>;
+  auto kern = resblock_fused_kernel<C, KT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
@@ -337,12 +360,24 @@ int launch_fused_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const F
   }
   const int per_sm = resident_ctas((const void*)kern, rf_threads(C), smem, 2 * C < 32 ? 32 : 2 * C);
   const int grid = std::min(a.n_streams, num_sms() * per_sm);
-  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused<%d> k %d tiles/stream %d smem %zu per_sm %d grid %d\n", C, a.k, a.tiles, smem, per_sm, grid);
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused<%d,%d> k %d tiles/stream %d smem %zu per_sm %d grid %d\n", C, KT, a.k, a.tiles, smem, per_sm, grid);
   kern<<<grid, rf_threads(C), smem, st>>>(tmA, tmW, a);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
 
+}  // namespace
+
+namespace {
+template <int C>
+int launch_fused_k(const CUtensorMap& tmA, const CUtensorMap& tmW, const FusedArgs& a, size_t smem, cudaStream_t st) {
+  switch (a.k) {
+    case 3: return launch_fused_variant<C, 3>(tmA, tmW, a, smem, st);
+    case 7: return launch_fused_variant<C, 7>(tmA, tmW, a, smem, st);
+    case 11: return launch_fused_variant<C, 11>(tmA, tmW, a, smem, st);
+    default: return launch_fused_variant<C, 0>(tmA, tmW, a, smem, st);
+  }
+}
 }  // namespace
 
 int resblock_fused_hist_rows(int k, const int* dil) {
@@ -368,7 +403,11 @@ int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st) {
   if (p.x_hist_rows < a.H[0]) { set_error("resblock_fused: input context keeps too little history"); return 1; }
   a.in_row0 = p.x_hist_rows - a.H[0];
   a.in_winb = align1k((TILE_M + a.H[0]) * ROWB);
-  int off = 2 * a.in_winb, hrow = 0;
+  // TMA round trips are ~1 us under load and a weight stage is only recycled when its MMAs have completed, so weight streaming
+  // is bound by the bytes in flight: at C = 64 (8 KB per tap, consumed in ~200 cycles) the ring gets the second input buffer's
+  // space -- the next tile's input is not needed before four more convs have run
+  { static int single = [] { const char* v = getenv("CONAN_FUSED_SINGLE"); return v ? atoi(v) : 1; }(); a.in_single = (C == 64 && single) ? 1 : 0; }
+  int off = (a.in_single ? 1 : 2) * a.in_winb, hrow = 0;
   a.win_off[0] = 0; a.hist_off[0] = 0;
   for (int c = 1; c < RF_CONVS; ++c) {
     a.win_off[c] = off; off += align1k((TILE_M + a.H[c]) * ROWB);
@@ -376,7 +415,7 @@ int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st) {
   }
   a.wt_off = off;
   a.group = C == 64 ? 2 : 4;                 // 16 KB / 8 KB weight stages
-  a.stages = 4;
+  a.stages = a.in_single ? 6 : 4;
   off += a.stages * a.group * TAPB;
   a.bar_off = off; off += 512;
   a.bias_off = off; off += RF_CONVS * C * 4;
@@ -393,11 +432,29 @@ int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st) {
   const unsigned long long Ktot = (unsigned long long)p.k * C;
   a.w_copies = p.w_copies > 0 ? p.w_copies : 1;
   { static int dbg = [] { const char* v = getenv("CONAN_FUSED_DEBUG"); return v ? atoi(v) : 0; }(); a.dbg = dbg; }
+
   if (get_tensor_map(&tmW, p.w, 3, Ktot, (unsigned long long)RF_CONVS * C, (unsigned long long)a.w_copies, Ktot * 2,
                      Ktot * 2 * RF_CONVS * C, C, C, 1, ROWB))
     return 1;
-  if (C == 32) return launch_fused_variant<32>(tmA, tmW, a, smem, st);
-  return launch_fused_variant<64>(tmA, tmW, a, smem, st);
+  if (getenv("CONAN_FUSED_TIMELINE")) {
+    // developer aid: CTA 0 stamps the first 64 conv steps; printed after the launch (synchronises the stream)
+    static long long* ts = nullptr;
+    if (!ts) cudaMalloc(&ts, 64 * 8 * sizeof(long long));
+    cudaMemsetAsync(ts, 0, 64 * 8 * sizeof(long long), st);
+    a.ts = ts;
+    int rc = C == 32 ? launch_fused_k<32>(tmA, tmW, a, smem, st) : launch_fused_k<64>(tmA, tmW, a, smem, st);
+    long long h[64 * 8];
+    cudaMemcpyAsync(h, ts, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "timeline C=%d k=%d: step: mma_start  [w0_wait g0_issue rest] mma_issue_span  issue_end->acc_seen  tmem_ld  math  signal  | epilogue_signal->next_mma_start\n", C, p.k);
+    for (int n = 6; n < 30; ++n)
+      fprintf(stderr, "  %2d c=%d: %6lld [%5lld %5lld %5lld] %6lld %6lld %6lld %6lld %6lld | %6lld\n", n, n % 6, h[n * 8] - h[6 * 8], h[n * 8 + 6] - h[n * 8], h[n * 8 + 7] - h[n * 8 + 6],
+              h[n * 8 + 1] - h[n * 8 + 7], h[n * 8 + 1] - h[n * 8], h[n * 8 + 2] - h[n * 8 + 1],
+              h[n * 8 + 3] - h[n * 8 + 2], h[n * 8 + 4] - h[n * 8 + 3], h[n * 8 + 5] - h[n * 8 + 4], h[(n + 1) * 8] - h[n * 8 + 5]);
+    return rc;
+  }
+  if (C == 32) return launch_fused_k<32>(tmA, tmW, a, smem, st);
+  return launch_fused_k<64>(tmA, tmW, a, smem, st);
 }
 
 }  // namespace conan
