@@ -264,31 +264,33 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================================================================== TMA producer (warp-uniform loop, one elected lane issues)
     {
-      const int kb_per_tap = a.cin / BK;
-      const int kb_per_seg = a.kblocks / a.nseg;
-      int kbg = 0;                                           // k-block counter across tiles (the smem ring never drains)
+      int s = 0;                                             // smem ring position / phase carried across tiles (the ring never drains)
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * MT;
-        for (int kb = 0; kb < a.kblocks; ++kb, ++kbg) {
-          const int s = kbg % STAGES;
-          const uint32_t ph = (kbg / STAGES) & 1;
+        int stream0m[MT], t0m[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { stream0m[m] = ((mt + m) / TPS) * NS; t0m[m] = ((mt + m) % TPS) * a.TT; }
+        // k-blocks in order: segment (split operands) -> tap -> channel block; counters instead of divisions (this loop paces the TMA issue)
+        int seg = 0, j = 0, c0 = 0;
+        for (int kb = 0; kb < a.kblocks; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
-          const int seg = kb / kb_per_seg, kbl = kb - seg * kb_per_seg;
-          const int j = kbl / kb_per_tap, c0 = (kbl - j * kb_per_tap) * BK;
           if (elect_one_sync()) {
             const bool second = MT == 2 && mt + 1 < a.m_tiles;
             mbar_expect_tx(&full_bar[s], SL::B_BYTES + (second ? 2 : 1) * SL::A1_BYTES);
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
               if (m == 1 && !second) break;
-              const int stream0 = ((mt + m) / TPS) * NS, t0 = ((mt + m) % TPS) * a.TT;
-              tma_load_3d(sa + m * SL::A1_BYTES, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil,
-                          stream0 + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
+              tma_load_3d(sa + m * SL::A1_BYTES, &tmA, &full_bar[s], c0, a.row0 + t0m[m] + j * a.dil,
+                          stream0m[m] + (seg == 2 ? a.lo_slot_off : 0));   // box {BK, TT, NS}
             }
             tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+          c0 += BK;
+          if (c0 == a.cin) { c0 = 0; if (++j == a.k) { j = 0; ++seg; } }
         }
       }
     }
@@ -296,16 +298,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
     {
       constexpr uint32_t idesc = make_idesc<BN>();
-      int kbg = 0, it = 0;
+      int it = 0, s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[ab], aph ^ 1);                  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * MT * BN);
-        for (int kb = 0; kb < a.kblocks; ++kb, ++kbg) {
-          const int s = kbg % STAGES;
-          const uint32_t ph = (kbg / STAGES) & 1;
+        for (int kb = 0; kb < a.kblocks; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
@@ -322,6 +323,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (elect_one_sync()) tc_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (elect_one_sync()) tc_commit(&acc_full[ab]);            // accumulators complete
       }
