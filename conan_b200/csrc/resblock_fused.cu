@@ -260,8 +260,8 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const float2 f = __half22float2(hp[u]);
-                  v[h8 * 8 + 2 * u] += f.x < 0.f ? f.x * inv_slope : f.x;
-                  v[h8 * 8 + 2 * u + 1] += f.y < 0.f ? f.y * inv_slope : f.y;
+                  v[h8 * 8 + 2 * u] += fminf(f.x, f.x * inv_slope);          // inverse LeakyReLU (slope < 1): min(h, h / slope)
+                  v[h8 * 8 + 2 * u + 1] += fminf(f.y, f.y * inv_slope);
                 }
               }
             }
@@ -272,7 +272,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   float x0 = v[h8 * 8 + 2 * u], x1 = v[h8 * 8 + 2 * u + 1];
-                  x0 = x0 > 0.f ? x0 : x0 * a.slope; x1 = x1 > 0.f ? x1 : x1 * a.slope;
+                  x0 = fmaxf(x0, x0 * a.slope); x1 = fmaxf(x1, x1 * a.slope);      // LeakyReLU (slope < 1): max(x, slope x)
                   h[u] = __floats2half2_rn(x0, x1);
                 }
                 *reinterpret_cast<uint4*>(dstw + swz<ROWB>(dstrow + (uint32_t)(col0 * 2 + h8 * 16))) = *reinterpret_cast<uint4*>(h);
@@ -307,7 +307,7 @@ resblock_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
                     float x0 = v[h8 * 8 + 2 * u] * a.out_scale, x1 = v[h8 * 8 + 2 * u + 1] * a.out_scale;
-                    x0 = x0 > 0.f ? x0 : x0 * a.slope; x1 = x1 > 0.f ? x1 : x1 * a.slope;
+                    x0 = fmaxf(x0, x0 * a.slope); x1 = fmaxf(x1, x1 * a.slope);      // LeakyReLU (slope < 1): max(x, slope x)
                     h[u] = __floats2half2_rn(x0, x1);
                   }
                   *(reinterpret_cast<uint4*>(nx) + h8) = *reinterpret_cast<uint4*>(h);
@@ -393,6 +393,7 @@ bool resblock_fused_eligible(int C, int L, int k, const int* dil) {
 
 int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st) {
   if (!resblock_fused_eligible(p.C, p.L, p.k, p.dil)) { set_error("resblock_fused: shape not eligible"); return 1; }
+  if (!(p.slope > 0.f && p.slope < 1.f)) { set_error("resblock_fused: LeakyReLU slope must be in (0, 1)"); return 1; }
   if (p.n_streams <= 0) return 0;
   const int C = p.C, ROWB = C * 2, TAPB = C * ROWB;
   FusedArgs a;

@@ -546,3 +546,88 @@ def test_causality_future_input_does_not_change_past_output(eng_tc):
     b, _, _ = _run_e2e(eng_tc, ref, src2, [1])
     assert torch.equal(a[:, :12 * 320], b[:, :12 * 320])
     assert not torch.equal(a[:, 12 * 320:], b[:, 12 * 320:])
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs 1-3 at their stated stream counts (parity cases, not bench lines)
+# ------------------------------------------------------------------------------------------
+def test_config1_emformer_only_64_streams_vs_oracle(state_dicts):
+    """configs[1]: Emformer content extractor only, 64 concurrent streams, chunkwise: every stream's encoder rows within
+    1e-4 of the oracle and every token exact, over enough chunks for the left-context ring to wrap."""
+    from oracle.incremental import EmformerOracle
+    S, T = 64, 64
+    eng = _engine(state_dicts, max_slots=S, max_ref_frames=64)
+    try:
+        src = torch.stack([synth.synth_mel(T, 300 + s) for s in range(S)])
+        o = EmformerOracle(state_dicts[1])
+        o.reset(S)
+        slots = torch.randperm(S, generator=torch.Generator().manual_seed(5)).tolist()
+        eng.reset_slots(slots)
+        ids = eng.ids_tensor(slots)
+        worst = 0.0
+        for pos in range(0, T, 4):
+            chunk, _ = _chunks(src, pos)
+            with torch.no_grad():
+                enc_ref = o.step(chunk)
+                tok_ref = o.logits(enc_ref).argmax(-1)
+            tok, enc, _ = eng.emformer_step(ids, chunk.cuda(), want_enc=True)
+            worst = max(worst, (enc.cpu() - enc_ref).abs().max().item())
+            assert (tok.cpu().long() == tok_ref).all(), f"token mismatch at pos {pos}"
+        print("config 1 (Emformer, 64 streams) enc max-abs", worst)
+        assert worst < 1e-4
+    finally:
+        eng.close()
+
+
+def test_config2_vocoder_only_256_streams(state_dicts, golden_dir):
+    """configs[2]: vocoder only, 256 concurrent streams.  8 distinct mel streams (checked against the oracle: SNR >= 40 dB),
+    each replicated 32 times over permuted slots: all replicas bit-identical (the fused residual-block kernel gives every
+    CTA several streams; nothing may leak between them)."""
+    from oracle.incremental import HifiGanOracle
+    S, D, T = 256, 8, 12
+    eng = _engine(state_dicts, max_slots=S, max_ref_frames=64)
+    try:
+        g = torch.Generator().manual_seed(21)
+        base = torch.stack([synth.synth_mel(T, 500 + s) for s in range(D)])
+        mel = base.repeat(S // D, 1, 1)                       # stream i carries base[i % D]
+        slots = torch.randperm(S, generator=g).tolist()
+        wav = _run_vocoder(eng, mel, slots)
+        for d in range(D):
+            assert (wav[d::D] == wav[d:d + 1]).all(), f"replicas of stream {d} differ"
+        o = HifiGanOracle(state_dicts[2])
+        o.reset(D)
+        with torch.no_grad():
+            ref = torch.cat([o.step(base[:, i:i + 4]) for i in range(0, T, 4)], 1)
+        worst = min(snr_ac_db(ref[d].numpy(), wav[d].numpy()) for d in range(D))
+        print("config 2 (vocoder, 256 streams) worst SNR_ac", worst)
+        assert worst >= SNR_MIN_DB
+    finally:
+        eng.close()
+
+
+def test_config3_full_pipeline_1024_streams_properties(state_dicts):
+    """configs[3] at full size: 1024 streams (16 distinct sessions/inputs x 64 replicas) through session setup and three
+    chunk steps.  Size-independent checks: replicas bit-identical; a stream's output equals the same stream run alone."""
+    S, D = 1024, 16
+    eng = _engine(state_dicts, max_slots=S, max_ref_frames=64)
+    try:
+        ref = torch.stack([synth.synth_mel(40, 700 + s) for s in range(D)]).repeat(S // D, 1, 1)
+        src = torch.stack([synth.synth_mel(12, 800 + s) for s in range(D)]).repeat(S // D, 1, 1)
+        slots = torch.randperm(S, generator=torch.Generator().manual_seed(8)).tolist()
+        eng.reset_slots(slots)
+        for b in range(0, S, 32):                             # session batches of 32, as the scheduler does
+            eng.open_sessions(slots[b:b + 32], ref[b:b + 32].cuda())
+        ids = eng.ids_tensor(slots)
+        wavs, mels, toks = [], [], []
+        for pos in range(0, 12, 4):
+            chunk, emit = _chunks(src, pos)
+            wav, mel, tok = eng.step(ids, chunk.cuda())
+            wavs.append(wav.cpu()), mels.append(mel.cpu()), toks.append(tok.cpu())
+        wav, mel, tok = torch.cat(wavs, 1), torch.cat(mels, 1), torch.cat(toks, 1)
+        for d in range(D):
+            assert (wav[d::D] == wav[d:d + 1]).all() and (mel[d::D] == mel[d:d + 1]).all() and (tok[d::D] == tok[d:d + 1]).all()
+        single, mel1, tok1 = _run_e2e(eng, ref[3:4], src[3:4], [slots[0]])
+        assert torch.equal(tok1[0], tok[3]) and torch.equal(mel1[0], mel[3, :mel1.shape[1]])
+        assert torch.equal(single[0], wav[3, :single.shape[1]])
+    finally:
+        eng.close()
