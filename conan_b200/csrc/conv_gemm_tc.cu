@@ -626,6 +626,11 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, lon
   return 0;
 }
 
+int es_min_tiles() {
+  static int v = [] { const char* e = getenv("CONAN_TC_ES_MIN"); return e ? atoi(e) : 2; }();
+  return v;
+}
+
 int window_mode() {
   // CONAN_TC_WINDOW=0 routes every layer through the ring kernel (A/B comparisons, debugging)
   static int mode = [] { const char* v = getenv("CONAN_TC_WINDOW"); return v ? atoi(v) : 1; }();
@@ -751,7 +756,7 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
       if (deep) return launch_variant<128, 64, 6>(tmA, tmW, a, m_tiles, st);
       // enough tiles to fill the machine with pairs: two m-tiles share every B tile (the layer is L2 -> SM bandwidth bound)
       static const int pair_mode = [] { const char* v = getenv("CONAN_TC_PAIR"); return v ? atoi(v) : 2; }();
-      if (nseg == 1 && m_tiles * a.n_tiles >= 4LL * num_sms()) {
+      if (nseg == 1 && m_tiles * a.n_tiles >= (long long)es_min_tiles() * num_sms()) {
         if (pair_mode == 1) return launch_variant<128, 64, 4, 2, 1>(tmA, tmW, a, m_tiles, st);
         if (pair_mode == 2) return launch_variant<128, 64, 3, 1, 2>(tmA, tmW, a, m_tiles, st);
         if (pair_mode == 3) return launch_variant<128, 64, 4, 2, 2>(tmA, tmW, a, m_tiles, st);
