@@ -80,6 +80,8 @@ SYMBOLS = {
     "conan_engine_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "conan_debug_read": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),
     "conan_conv_gemm": (C.c_int, [C.POINTER(ConvParams), C.c_int, _P]),
+    "conan_logmel": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_float,
+                               C.c_float, C.c_float, _P, _P, _P]),
 }
 
 _lib = None

@@ -254,6 +254,29 @@ conv_post_tanh_tiled_kernel(const __half* __restrict__ x, long long slot_stride,
   wav[(long long)i * L + t0 + threadIdx.x] = tanhf(acc);
 }
 
+// ------------------------------------------------------------------ log-mel front-end
+// spec [n*frames, ld] = windowed DFT of each frame: columns [0, bins) real parts, [bins, 2*bins) imaginary parts (produced by
+// the conv-GEMM engine: a frame is 4 taps over 320-sample rows of the centre-padded signal).  One CTA per frame:
+// magnitude -> Slaney mel (basis transposed [bins][n_mels]: coalesced over mel channels) -> log10(max(., eps)) -> clip.
+// utils/audio/__init__.py:62-72, inference/Conan.py:58-70.
+__global__ void __launch_bounds__(128)
+logmel_kernel(const float* __restrict__ spec, int ld, int bins, const float* __restrict__ basis_t, int n_mels, float eps,
+              float vmin, float vmax, float* __restrict__ mel) {
+  extern __shared__ float mag[];
+  const float* sp = spec + (long long)blockIdx.x * ld;
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+    const float re = sp[b], im = sp[bins + b];
+    mag[b] = sqrtf(re * re + im * im);
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < bins; ++b) acc = fmaf(basis_t[(long long)b * n_mels + m], mag[b], acc);
+    const float v = log10f(fmaxf(acc, eps));
+    mel[(long long)blockIdx.x * n_mels + m] = fminf(fmaxf(v, vmin), vmax);
+  }
+}
+
 // ------------------------------------------------------------------ ring maintenance
 __global__ void hist_move_kernel(const HistDesc* __restrict__ descs, const int* slot_ids, int scatter) {
   HistDesc d = descs[blockIdx.x];
@@ -498,6 +521,14 @@ int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, i
     conv_post_tanh_kernel<__half><<<grid, 256, sh, st>>>((const __half*)x, slot_stride, row_stride, row0, L, C, k, w, bias, wav_out, n, slot_ids);
   else
     conv_post_tanh_kernel<float><<<grid, 256, sh, st>>>((const float*)x, slot_stride, row_stride, row0, L, C, k, w, bias, wav_out, n, slot_ids);
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_logmel(const float* spec, int ld, int bins, const float* basis_t, int n_mels, float eps, float vmin, float vmax,
+                  float* mel, long long n_frames, cudaStream_t st) {
+  if (n_frames <= 0) return 0;
+  logmel_kernel<<<(unsigned)n_frames, 128, (size_t)bins * sizeof(float), st>>>(spec, ld, bins, basis_t, n_mels, eps, vmin, vmax, mel);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

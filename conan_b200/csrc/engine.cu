@@ -1044,6 +1044,25 @@ int conan_debug_read(conan_engine_t* e, const char* name, int slot, float* out_d
   return 0;
 }
 
+int conan_logmel(const float* wav_rows, int n_streams, int rows_per_stream, int hop, int taps, int row0, int n_frames,
+                 const float* dft_w, int bins, const float* mel_basis_t, int n_mels, float eps, float vmin, float vmax,
+                 float* spec_scratch, float* mel_out, void* stream) {
+  if (!wav_rows || !dft_w || !mel_basis_t || !spec_scratch || !mel_out) { set_error("null argument"); return 1; }
+  if (n_streams <= 0 || n_frames <= 0) return 0;
+  if (row0 < 0 || row0 + n_frames + taps - 1 > rows_per_stream) { set_error("logmel: frames outside the padded signal"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  // frame f = taps consecutive hop-sample rows starting at row f of the centre-padded signal: an implicit conv with the
+  // windowed DFT basis [2*bins, taps*hop] as weights (fp32 FFMA engine: the spectrum feeds a log)
+  conan_conv_params_t p;
+  memset(&p, 0, sizeof(p));
+  p.x = wav_rows; p.x_slot_stride = (long long)rows_per_stream * hop; p.x_row_stride = hop; p.x_rows = rows_per_stream;
+  p.row0 = row0; p.L = n_frames; p.cin = hop; p.k = taps; p.dil = 1; p.cout = 2 * bins; p.w = dft_w;
+  p.n_streams = n_streams; p.n_slots = n_streams; p.scale = 1.f; p.out_scale = 1.f;
+  p.y = spec_scratch; p.y_slot_stride = (long long)n_frames * 2 * bins; p.y_row_stride = 2 * bins;
+  if (launch_conv_gemm_ffma(p, st)) return 1;
+  return launch_logmel(spec_scratch, 2 * bins, bins, mel_basis_t, n_mels, eps, vmin, vmax, mel_out, (long long)n_streams * n_frames, st);
+}
+
 int conan_conv_gemm(const conan_conv_params_t* p, int engine, void* stream) {
   if (!p) { set_error("null params"); return 1; }
   if (engine == 1) {

@@ -93,6 +93,10 @@ bool resblock_fused_eligible(int C, int L, int k, const int* dil);
 int resblock_fused_hist_rows(int k, const int* dil);
 int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st);
 
+// log-mel front-end: |DFT| -> Slaney mel -> log10 -> clip, one CTA per frame (spec from the conv-GEMM engine)
+int launch_logmel(const float* spec, int ld, int bins, const float* basis_t, int n_mels, float eps, float vmin, float vmax,
+                  float* mel, long long n_frames, cudaStream_t st);
+
 // state maintenance --------------------------------------------------------------------------
 // Resident history of a context buffer lives per slot in `hist` [slot, hist_bytes]; the step works on a compact
 // buffer `work` [i, hist_bytes + new_bytes].  gather: hist[slot_i] -> work[i][0 : hist);  scatter: the last

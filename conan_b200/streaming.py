@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import audio, ckpt, synth
+from .frontend import GpuLogMel
 from .engine import Engine, PARTS_ALL, PARTS_CONAN, PARTS_EMFORMER, PARTS_VOCODER, make_config
 from .hparams import hparams, set_hparams
 from .scheduler import ChunkScheduler
@@ -170,18 +171,16 @@ class StreamingVoiceConversion:
         self.emformer = EmformerView(self.engine, view_slots[1:2])
         HifiGAN._engine_factory = lambda: (self.engine, view_slots[2])
         self.vocoder = get_vocoder_cls(hp["vocoder"])()
+        self.frontend = GpuLogMel(hp)
         self._vocoder_warm_zero()
 
     def _vocoder_warm_zero(self):
         _ = self.vocoder.spec2wav(np.zeros((4, 80), dtype=np.float32))
 
     def _wav_to_mel(self, path: str) -> np.ndarray:
-        hp = self.hparams
-        wav = audio.load_wav(path, hp["audio_sample_rate"])
-        mel = audio.wav2mel(wav, fft_size=hp["fft_size"], hop_size=hp["hop_size"], win_length=hp["win_size"],
-                            num_mels=hp["audio_num_mel_bins"], fmin=hp["fmin"], fmax=hp["fmax"],
-                            sample_rate=hp["audio_sample_rate"])
-        return np.clip(mel, hp["mel_vmin"], hp["mel_vmax"])
+        """inference/Conan.py:58-70: wav file -> clipped log-mel [T, 80], computed on the device (`conan_logmel`)."""
+        wav = audio.load_wav(path, self.hparams["audio_sample_rate"])
+        return self.frontend.offline(wav)[0].cpu().numpy()
 
     def infer_mels(self, ref_mel: np.ndarray, src_mel: np.ndarray):
         """The loop of infer_once on precomputed mels: (wav float32 [T*hop], mel float32 [T, 80])."""

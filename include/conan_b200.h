@@ -228,6 +228,17 @@ typedef struct conan_conv_params {
   int32_t y_is_half;        /* y is __half* (no accumulate in that case: use res2) */
 } conan_conv_params_t;
 
+/* Log-mel front-end on the device (replaces the host librosa path of inference/Conan.py:58-70 and
+ * utils/audio/__init__.py:36-80 for streamed PCM).  wav_rows: the centre-padded signal of every stream as rows of `hop`
+ * samples, [n_streams][rows_per_stream][hop] fp32 (fft_size/2 zeros in front, zeros behind); frame f covers rows
+ * row0 + f .. row0 + f + taps - 1 (taps = ceil(fft_size / hop); the basis is zero beyond fft_size).  dft_w: window-weighted
+ * DFT basis [2*bins][taps*hop] fp32 (rows 0..bins-1 cos, bins..2*bins-1 -sin); mel_basis_t: [bins][n_mels] fp32.
+ * mel_out [n_streams][n_frames][n_mels] = clip(log10(max(mel_basis . |DFT|, eps)), vmin, vmax).
+ * spec_scratch: n_streams*n_frames*2*bins floats. */
+int conan_logmel(const float* wav_rows, int n_streams, int rows_per_stream, int hop, int taps, int row0, int n_frames,
+                 const float* dft_w, int bins, const float* mel_basis_t, int n_mels, float eps, float vmin, float vmax,
+                 float* spec_scratch, float* mel_out, void* stream);
+
 /* engine: 0 = FFMA (fp32 accumulate on CUDA cores, fp32 or fp16 operands),
  *         1 = tcgen05 tensor cores (fp16 operands, fp32 accumulate in TMEM). */
 int conan_conv_gemm(const conan_conv_params_t* p, int engine, void* stream);

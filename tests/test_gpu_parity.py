@@ -631,3 +631,34 @@ def test_config3_full_pipeline_1024_streams_properties(state_dicts):
         assert torch.equal(single[0], wav[3, :single.shape[1]])
     finally:
         eng.close()
+
+
+def test_fast_system_right_context_zero(state_dicts):
+    """the released "*_fast" system runs the same graphs with right_context = 0 (4-row chunks, no look-ahead
+    keys).  Emformer rows and tokens against the oracle configured the same way, then the whole step end to end against
+    the streaming oracle driven with 4-frame chunks."""
+    from oracle.incremental import EmformerOracle, assemble_chunk
+    hp = dict(synth.DEFAULT_HP, right_context=0)
+    eng = _engine(state_dicts, hp=hp)
+    try:
+        assert eng.rows_in == 4
+        B, T = 2, 64
+        src = torch.stack([synth.synth_mel(T, 900 + s) for s in range(B)])
+        o = EmformerOracle(state_dicts[1], right_context=0)
+        o.reset(B)
+        slots = [3, 1]
+        eng.reset_slots(slots)
+        ids = eng.ids_tensor(slots)
+        worst = 0.0
+        for pos in range(0, T, 4):
+            chunk, _ = assemble_chunk(src, pos, rc=0)
+            with torch.no_grad():
+                enc_ref = o.step(chunk.contiguous())
+                tok_ref = o.logits(enc_ref).argmax(-1)
+            tok, enc, _ = eng.emformer_step(ids, chunk.contiguous().cuda(), want_enc=True)
+            worst = max(worst, (enc.cpu() - enc_ref).abs().max().item())
+            assert (tok.cpu().long() == tok_ref).all()
+        print("rc=0 emformer enc max-abs", worst)
+        assert worst < 1e-4
+    finally:
+        eng.close()
