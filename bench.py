@@ -237,7 +237,7 @@ def run_b200(args):
     NPROF = 2
     for i in range(NPROF):
         eng.step(ids, chunks_dev[i % n_pool], wav, mel, tok)
-    prof = {cat: eng.profile_read(cat) for cat in range(5)}
+    prof = {cat: eng.profile_read(cat) for cat in range(6)}
     eng.set_profiling(False)
 
     t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -253,7 +253,8 @@ def run_b200(args):
                  1: ("conv_gemm_tc_kernel (tcgen05 implicit-GEMM causal conv, fp16 operands: vocoder scales 0-1 + upsampling)", "tensor"),
                  2: ("conv_window_tc_kernel (tcgen05, persistent, weights resident, one input window per tile: vocoder scales 2-3)", "hbm"),
                  3: ("conv_gemm_tc_kernel, split-fp16 operands (Emformer / Conan linear + conv contractions, 3 MMAs per product)", "tensor"),
-                 4: ("resblock_fused_kernel (tcgen05, one HiFi-GAN residual block = six convs per launch, activations in shared memory: vocoder scales 2-3)", "tensor")}
+                 4: ("resblock_fused_kernel (tcgen05, one HiFi-GAN residual block = six convs per launch, activations in shared memory: vocoder scales 2-3)", "tensor"),
+                 5: ("ffn_fused_kernel (tcgen05, Emformer 80 -> 2048 -> 80 feed-forward in one launch, split-fp16 operands, hidden activation in shared memory)", "tensor")}
         roofs = {}
         for cat, (ms, nl, fl, by) in prof.items():
             if nl == 0:

@@ -20,9 +20,24 @@ __global__ void layernorm_kernel(LnArgs a) {
   int slot = slot_of(a.slot_ids, i);
   const float* x = reinterpret_cast<const float*>(a.in.base) + (long long)slot * a.in.slot_stride +
                    (long long)(a.in.row0 + t) * a.in.row_stride;
+  float xs[4];                                    // partial-sum mode: the row (C <= 128) is assembled once, in registers
+  if (a.part) {
+    const long long row = (long long)i * a.L + t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      float v = 0.f;
+      if (c < a.C) {
+        for (int p = 0; p < a.n_part; ++p) v += a.part[p * a.part_stride + row * a.part_ld + c];
+        v += a.part_bias[c] + a.part_res[row * a.part_res_ld + c];
+      }
+      xs[q] = v;
+    }
+  }
+  auto val = [&](int c) { return a.part ? xs[c >> 5] : x[c]; };
   float pm = a.premask ? a.premask[(long long)slot * a.premask_slot_stride + t] : 1.f;
   float s = 0.f, sabs = 0.f;
-  for (int c = lane; c < a.C; c += 32) { float v = x[c]; sabs += fabsf(v); s += v * pm; }
+  for (int c = lane; c < a.C; c += 32) { float v = val(c); sabs += fabsf(v); s += v * pm; }
   s = warp_sum(s);
   if (a.write_mask) {
     sabs = warp_sum(sabs);
@@ -34,14 +49,14 @@ __global__ void layernorm_kernel(LnArgs a) {
   }
   float mean = s / a.C;
   float q = 0.f;
-  for (int c = lane; c < a.C; c += 32) { float d = x[c] * pm - mean; q += d * d; }
+  for (int c = lane; c < a.C; c += 32) { float d = val(c) * pm - mean; q += d * d; }
   q = warp_sum(q);
   float rstd = 1.f / sqrtf(q / a.C + a.eps);
   float post = a.postmask ? a.postmask[(long long)slot * a.postmask_slot_stride + t] : 1.f;
   long long o = (long long)slot * a.out.slot_stride + (long long)(a.out.row0 + t) * a.out.row_stride;
   long long o2 = (long long)slot * a.out2.slot_stride + (long long)(a.out2.row0 + t) * a.out2.row_stride;
   for (int c = lane; c < a.C; c += 32) {
-    float y = ((x[c] * pm - mean) * rstd * a.gamma[c] + a.beta[c]) * post;
+    float y = ((val(c) * pm - mean) * rstd * a.gamma[c] + a.beta[c]) * post;
     store_view(a.out, o + c, y);
     if (a.out2.base) store_view(a.out2, o2 + c, y);
   }

@@ -63,6 +63,7 @@ struct conan_engine {
   int ring_rows = 0;
   float *eX = nullptr, *eQKV = nullptr, *eR1 = nullptr, *eR2 = nullptr, *eLOG = nullptr;
   Ctx eXN, eATT, eFN, eHF;   // GEMM operands (fp32 or split fp16)
+  bool ffnFused = false; float* eFFP = nullptr;    // fused FFN: partial outputs [split][rows][DP]
   std::vector<float*> eRing;
   int* ePast = nullptr;
   int* TOK = nullptr;
@@ -344,6 +345,21 @@ int run_fused(const conan_engine* e, const ResblockFusedParams& f, cudaStream_t 
   return rc;
 }
 
+// profiling category 5: fused position-wise FFN
+int run_ffn(const conan_engine* e, const FfnFusedParams& f, cudaStream_t st) {
+  if (!e->profiling) return launch_ffn_fused(f, st);
+  conan_engine::ProfRec r;
+  r.cat = 5;
+  r.flops = 2.0 * (double)f.M * f.hidden * (f.K + f.N);
+  r.bytes = (double)f.M * f.K * 4.0 + (double)f.hidden * (f.K + f.N) * 6.0 + (double)f.FS * f.M * f.N * 4.0;
+  CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
+  CONAN_CUDA_OK(cudaEventRecord(r.a, st));
+  int rc = launch_ffn_fused(f, st);
+  CONAN_CUDA_OK(cudaEventRecord(r.b, st));
+  e->prof.push_back(r);
+  return rc;
+}
+
 int ln_rows(const float* in, int in_rows, int in_ld, int in_row0, RowView out, const float* g, const float* b, int C, int L, int n,
             cudaStream_t st, const float* premask = nullptr, const float* postmask = nullptr, int mask_stride = 0,
             float* write_mask = nullptr, float* write_mask2 = nullptr, RowView out2 = RowView{}) {
@@ -374,6 +390,8 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->eLOG, (size_t)S * seg * e->LP));
   TRY(alloc_ctx(e, &e->eXN, 0, rows, 0, DP, lt)); TRY(alloc_ctx(e, &e->eATT, 0, rows, 0, DP, lt));
   TRY(alloc_ctx(e, &e->eFN, 0, rows, 0, DP, lt)); TRY(alloc_ctx(e, &e->eHF, 0, rows, 0, c.emformer_ffn, lt));
+  e->ffnFused = e->lin_tc && c.lin_fuse_ffn && ffn_fused_eligible(DP, c.emformer_ffn, DP);
+  if (e->ffnFused) TRY(dalloc(e, &e->eFFP, (size_t)4 * S * rows * DP));
   e->eRing.resize(c.emformer_layers);
   for (int l = 0; l < c.emformer_layers; ++l) TRY(dalloc(e, &e->eRing[l], (size_t)S * e->ring_rows * 2 * D));
   TRY(dalloc(e, &e->ePast, (size_t)S)); TRY(dalloc(e, &e->TOK, (size_t)S * seg));
@@ -546,16 +564,35 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
     out_rows(o, e->eR1, rows, DP); res_rows(o, e->eX, rows, DP);
     TRY(run_conv(e, o, st, tc));
     TRY(ln_rows(e->eR1, rows, DP, 0, e->eFN.new_rows(), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
-    auto f1 = conv_on_ctx(e, e->eFN, 1, 1, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
-    out2_ctx(f1, e->eHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
-    TRY(run_conv(e, f1, st, tc));
-    auto f2 = conv_on_ctx(e, e->eHF, 1, 1, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), DP, n);
-    out_rows(f2, e->eR2, rows, DP); res_rows(f2, e->eR1, rows, DP);
-    TRY(run_conv(e, f2, st, tc));
     // the last layer's output is also the operand of the projection GEMM
     const bool last = (l == c.emformer_layers - 1);
-    TRY(ln_rows(e->eR2, rows, DP, 0, view_f32(e->eX, (long long)rows * DP, DP), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st,
-                nullptr, nullptr, 0, nullptr, nullptr, last ? e->eXN.new_rows() : RowView{}));
+    if (e->ffnFused) {
+      // one kernel for 80 -> 2048 -> 80: partial outputs per hidden slice; the LayerNorm sums them with b2 and the residual
+      FfnFusedParams f;
+      memset(&f, 0, sizeof(f));
+      f.x = e->eFN.p; f.x_lo_off = e->eFN.plane; f.x_rows = e->S * rows; f.M = n * rows; f.K = DP; f.hidden = F; f.N = DP;
+      f.w1 = e->P(p + "ffn1.w"); f.b1 = e->F(p + "ffn1.b"); f.w2 = e->P(p + "ffn2.w");
+      f.partials = e->eFFP; f.FS = ffn_fused_split(f.M); f.acc_scale = 1.f / kSplitWeightScale;
+      TRY(run_ffn(e, f, st));
+      LnArgs a;
+      a.in = RowView{(void*)e->eR1, (long long)rows * DP, DP, 0, 0, 0};
+      a.out = view_f32(e->eX, (long long)rows * DP, DP); a.out2 = last ? e->eXN.new_rows() : RowView{};
+      a.gamma = e->F(p + "ln_out.g"); a.beta = e->F(p + "ln_out.b"); a.eps = 1e-5f; a.C = D; a.L = rows; a.n = n; a.slot_ids = nullptr;
+      a.premask = nullptr; a.premask_slot_stride = 0; a.postmask = nullptr; a.postmask_slot_stride = 0;
+      a.write_mask = nullptr; a.write_mask_slot_stride = 0; a.write_mask2 = nullptr;
+      a.part = e->eFFP; a.n_part = f.FS; a.part_stride = (long long)f.M * DP; a.part_ld = DP;
+      a.part_bias = e->F(p + "ffn2.b"); a.part_res = e->eR1; a.part_res_ld = DP;
+      TRY(launch_layernorm(a, st));
+    } else {
+      auto f1 = conv_on_ctx(e, e->eFN, 1, 1, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
+      out2_ctx(f1, e->eHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
+      TRY(run_conv(e, f1, st, tc));
+      auto f2 = conv_on_ctx(e, e->eHF, 1, 1, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), DP, n);
+      out_rows(f2, e->eR2, rows, DP); res_rows(f2, e->eR1, rows, DP);
+      TRY(run_conv(e, f2, st, tc));
+      TRY(ln_rows(e->eR2, rows, DP, 0, view_f32(e->eX, (long long)rows * DP, DP), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st,
+                  nullptr, nullptr, 0, nullptr, nullptr, last ? e->eXN.new_rows() : RowView{}));
+    }
   }
   TRY(launch_advance_past_len(e->ePast, n, ids, seg, st));
   auto pj = conv_on_ctx(e, e->eXN, 1, 1, e->P("emf.proj.w"), e->F("emf.proj.b"), LP, n, true, rc, seg);   // utterance rows only

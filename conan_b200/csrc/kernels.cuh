@@ -38,6 +38,10 @@ struct LnArgs {
   const float* postmask; int postmask_slot_stride;  // y *= postmask[slot, t]
   float* write_mask; int write_mask_slot_stride;     // mask[slot, t] = (sum_c |x| > 0) of the raw input
   float* write_mask2;                                // optional second copy (same stride)
+  // optional: the input row is  sum_p part[p][row][c] + part_bias[c] + part_res[row][c]  instead of `in` (the fused FFN kernel
+  // leaves one partial per hidden-dimension slice; compact rows, C <= 128)
+  const float* part = nullptr; int n_part = 0; long long part_stride = 0; int part_ld = 0;
+  const float* part_bias = nullptr; const float* part_res = nullptr; int part_res_ld = 0;
 };
 int launch_layernorm(const LnArgs& a, cudaStream_t st);
 
@@ -92,6 +96,19 @@ struct ResblockFusedParams {
 bool resblock_fused_eligible(int C, int L, int k, const int* dil);
 int resblock_fused_hist_rows(int k, const int* dil);
 int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st);
+
+// fused position-wise FFN (ffn_fused.cu): y partials = W2 . relu(W1 . x + b1), split-fp16 operands
+struct FfnFusedParams {
+  const void* x; long long x_lo_off; int x_rows;     // split fp16 planes [x_rows][96]: hi at x, lo at x + x_lo_off (elements)
+  int M, K, hidden, N;                               // valid rows, padded model dim (96), hidden width, padded output dim (96)
+  const void* w1; const float* b1;                   // [hidden][3*K] fp16 (W_hi | W_lo | W_hi, x 2^10), [hidden] fp32
+  const void* w2;                                    // [N][3*hidden] fp16
+  float* partials; int FS;                           // [FS][M][N] fp32
+  float acc_scale;
+};
+bool ffn_fused_eligible(int K, int hidden, int N);
+int ffn_fused_split(int M);
+int launch_ffn_fused(const FfnFusedParams& p, cudaStream_t st);
 
 // log-mel front-end: |DFT| -> Slaney mel -> log10 -> clip, one CTA per frame (spec from the conv-GEMM engine)
 int launch_logmel(const float* spec, int ld, int bins, const float* basis_t, int n_mels, float eps, float vmin, float vmax,

@@ -21,7 +21,8 @@ PARTS_EMFORMER, PARTS_CONAN, PARTS_VOCODER, PARTS_ALL = 1, 2, 4, 7
 def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max_slots: int = 64,
                 max_ref_frames: int = 512, device: int = 0, voc_precision: str = "fp16",
                 voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None,
-                voc_residual_from_ctx: Optional[bool] = None, voc_fuse_resblocks: Optional[bool] = None) -> _lib.ConanConfig:
+                voc_residual_from_ctx: Optional[bool] = None, voc_fuse_resblocks: Optional[bool] = None,
+                lin_fuse_ffn: Optional[bool] = None) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -69,6 +70,7 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     # whole residual blocks as one kernel at the 32 / 64 channel scales (activations stay in shared memory)
     can_fuse = bool(cfg.voc_use_tensor_cores and cfg.voc_residual_from_ctx)
     cfg.voc_fuse_resblocks = int(can_fuse if voc_fuse_resblocks is None else (bool(voc_fuse_resblocks) and can_fuse))
+    cfg.lin_fuse_ffn = int(bool(cfg.lin_use_tensor_cores) if lin_fuse_ffn is None else (bool(lin_fuse_ffn) and bool(cfg.lin_use_tensor_cores)))
     return cfg
 
 

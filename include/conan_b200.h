@@ -78,7 +78,9 @@ typedef struct conan_config {
                                      (x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, fp32 accumulate: fp32-grade results); 0: fp32 FFMA */
   int32_t voc_fuse_resblocks;     /* 1: at the scales with 32 / 64 channels a whole residual block (six convs) runs as one tcgen05 kernel
                                      with the activations kept in shared memory (needs tensor cores + voc_residual_from_ctx) */
-  int32_t reserved[5];
+  int32_t lin_fuse_ffn;           /* 1: the Emformer position-wise FFN (80 -> 2048 -> 80) runs as one tcgen05 kernel, the hidden
+                                     activation stays in shared memory (needs lin_use_tensor_cores) */
+  int32_t reserved[4];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */

@@ -662,3 +662,33 @@ def test_fast_system_right_context_zero(state_dicts):
         assert worst < 1e-4
     finally:
         eng.close()
+
+
+def test_emformer_fused_ffn_matches_two_gemm_path(state_dicts):
+    """The fused feed-forward kernel (hidden activation kept in shared memory, partial sums reduced by the LayerNorm) against
+    the two-GEMM path on the same split-fp16 operands, for a stream count that leaves a partial row tile."""
+    from oracle.incremental import EmformerOracle
+    B, T = 37, 24                                   # 37 * 6 = 222 rows: one full and one partial 128-row tile
+    src = torch.stack([synth.synth_mel(T, 600 + s) for s in range(B)])
+    outs = []
+    for fuse in (False, True):
+        eng = _engine(state_dicts, max_slots=40, lin_fuse_ffn=fuse)
+        assert bool(eng.cfg.lin_fuse_ffn) == fuse
+        slots = list(range(B))[::-1]
+        eng.reset_slots(slots)
+        ids = eng.ids_tensor(slots)
+        encs, toks = [], []
+        for pos in range(0, T, 4):
+            chunk, _ = _chunks(src, pos)
+            tok, enc, _ = eng.emformer_step(ids, chunk.cuda(), want_enc=True)
+            encs.append(enc.cpu()), toks.append(tok.cpu())
+        outs.append((torch.cat(encs, 1), torch.cat(toks, 1)))
+        eng.close()
+    err = (outs[0][0] - outs[1][0]).abs().max().item()
+    print("fused FFN vs two-GEMM enc max-abs", err)
+    assert err < 5e-5 and torch.equal(outs[0][1], outs[1][1])
+    o = EmformerOracle(state_dicts[1])
+    o.reset(B)
+    with torch.no_grad():
+        ref = torch.cat([o.step(_chunks(src, pos)[0]) for pos in range(0, T, 4)], 1)
+    assert (outs[1][0] - ref).abs().max().item() < 1e-4
