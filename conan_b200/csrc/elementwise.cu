@@ -55,10 +55,28 @@ __global__ void layernorm_kernel(LnArgs a) {
   float post = a.postmask ? a.postmask[(long long)slot * a.postmask_slot_stride + t] : 1.f;
   long long o = (long long)slot * a.out.slot_stride + (long long)(a.out.row0 + t) * a.out.row_stride;
   long long o2 = (long long)slot * a.out2.slot_stride + (long long)(a.out2.row0 + t) * a.out2.row_stride;
+  float ys[4] = {0.f, 0.f, 0.f, 0.f};
   for (int c = lane; c < a.C; c += 32) {
     float y = ((val(c) * pm - mean) * rstd * a.gamma[c] + a.beta[c]) * post;
     store_view(a.out, o + c, y);
     if (a.out2.base) store_view(a.out2, o2 + c, y);
+    if (a.gamma2) ys[(c >> 5) & 3] = y;
+  }
+  if (a.gamma2) {                                 // chained LayerNorm on y (same eps), C <= 128
+    float s2 = 0.f;
+#pragma unroll
+    for (int q2 = 0; q2 < 4; ++q2) if (lane + 32 * q2 < a.C) s2 += ys[q2];
+    const float mean2 = warp_sum(s2) / a.C;
+    float v2 = 0.f;
+#pragma unroll
+    for (int q2 = 0; q2 < 4; ++q2) if (lane + 32 * q2 < a.C) { const float d = ys[q2] - mean2; v2 += d * d; }
+    const float rstd2 = 1.f / sqrtf(warp_sum(v2) / a.C + a.eps);
+    const long long o3 = (long long)slot * a.out3.slot_stride + (long long)(a.out3.row0 + t) * a.out3.row_stride;
+#pragma unroll
+    for (int q2 = 0; q2 < 4; ++q2) {
+      const int c = lane + 32 * q2;
+      if (c < a.C) store_view(a.out3, o3 + c, (ys[q2] - mean2) * rstd2 * a.gamma2[c] + a.beta2[c]);
+    }
   }
 }
 

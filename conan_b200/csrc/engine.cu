@@ -554,7 +554,8 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
   TRY(launch_emformer_assemble(chunk, e->eX, DP, n, nullptr, seg, rc, D, st));
   for (int l = 0; l < c.emformer_layers; ++l) {
     std::string p = "emf." + std::to_string(l) + ".";
-    TRY(ln_rows(e->eX, rows, DP, 0, e->eXN.new_rows(), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, st));
+    // layers > 0: the input norm was applied by the previous layer's output-norm launch (chained LayerNorm)
+    if (l == 0) TRY(ln_rows(e->eX, rows, DP, 0, e->eXN.new_rows(), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, st));
     auto q = conv_on_ctx(e, e->eXN, 1, 1, e->P(p + "qkv.w"), e->F(p + "qkv.b"), QP, n);
     out_rows(q, e->eQKV, rows, QP);
     TRY(run_conv(e, q, st, tc));
@@ -582,6 +583,10 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
       a.write_mask = nullptr; a.write_mask_slot_stride = 0; a.write_mask2 = nullptr;
       a.part = e->eFFP; a.n_part = f.FS; a.part_stride = (long long)f.M * DP; a.part_ld = DP;
       a.part_bias = e->F(p + "ffn2.b"); a.part_res = e->eR1; a.part_res_ld = DP;
+      if (!last) {
+        std::string pn = "emf." + std::to_string(l + 1) + ".";
+        a.gamma2 = e->F(pn + "ln_in.g"); a.beta2 = e->F(pn + "ln_in.b"); a.out3 = e->eXN.new_rows();
+      }
       TRY(launch_layernorm(a, st));
     } else {
       auto f1 = conv_on_ctx(e, e->eFN, 1, 1, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
@@ -590,8 +595,17 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
       auto f2 = conv_on_ctx(e, e->eHF, 1, 1, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), DP, n);
       out_rows(f2, e->eR2, rows, DP); res_rows(f2, e->eR1, rows, DP);
       TRY(run_conv(e, f2, st, tc));
-      TRY(ln_rows(e->eR2, rows, DP, 0, view_f32(e->eX, (long long)rows * DP, DP), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st,
-                  nullptr, nullptr, 0, nullptr, nullptr, last ? e->eXN.new_rows() : RowView{}));
+      LnArgs a;
+      a.in = RowView{(void*)e->eR2, (long long)rows * DP, DP, 0, 0, 0};
+      a.out = view_f32(e->eX, (long long)rows * DP, DP); a.out2 = last ? e->eXN.new_rows() : RowView{};
+      a.gamma = e->F(p + "ln_out.g"); a.beta = e->F(p + "ln_out.b"); a.eps = 1e-5f; a.C = D; a.L = rows; a.n = n; a.slot_ids = nullptr;
+      a.premask = nullptr; a.premask_slot_stride = 0; a.postmask = nullptr; a.postmask_slot_stride = 0;
+      a.write_mask = nullptr; a.write_mask_slot_stride = 0; a.write_mask2 = nullptr;
+      if (!last) {
+        std::string pn = "emf." + std::to_string(l + 1) + ".";
+        a.gamma2 = e->F(pn + "ln_in.g"); a.beta2 = e->F(pn + "ln_in.b"); a.out3 = e->eXN.new_rows();
+      }
+      TRY(launch_layernorm(a, st));
     }
   }
   TRY(launch_advance_past_len(e->ePast, n, ids, seg, st));

@@ -42,6 +42,9 @@ struct LnArgs {
   // leaves one partial per hidden-dimension slice; compact rows, C <= 128)
   const float* part = nullptr; int n_part = 0; long long part_stride = 0; int part_ld = 0;
   const float* part_bias = nullptr; const float* part_res = nullptr; int part_res_ld = 0;
+  // optional chained second LayerNorm over the first one's output y (C <= 128): out3 = LN2(y) -- the next Emformer layer's
+  // input norm applied in the same pass as this layer's output norm
+  const float* gamma2 = nullptr; const float* beta2 = nullptr; RowView out3;
 };
 int launch_layernorm(const LnArgs& a, cudaStream_t st);
 
