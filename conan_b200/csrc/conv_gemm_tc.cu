@@ -191,9 +191,117 @@ __device__ __forceinline__ void epilogue_rows_k(const TcEpi& e, const float* __r
   }
 }
 
+// Lean epilogue for the vocoder layers (fp16 context rows in and out, no scale / mask / fp32 stream):
+//   v = acc + bias [+ inverse-LeakyReLU(res)] [+ res2];  v *= out_scale;  y = fp16(v) and/or y2 = fp16(LeakyReLU(v))
+// with the (inverse) LeakyReLU as min / max (slopes in (0, 1)).  The short-K layers are bound by the SM's instruction issue
+// (a 128 x 128 tile is ~16 K elements per 1.5 K cycles of MMA), so this path spends ~4-8 instructions per element instead of
+// the general path's 10-14.
+template <int BN, int RK>
+__device__ __forceinline__ void epilogue_rows_lean(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
+                                                   bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+  constexpr int NCH = BN / 16;
+  constexpr int PF = NCH < 4 ? NCH : 4;
+  const long long res_off = (long long)slot * e.res_slot_stride + (long long)t * e.res_row_stride + nbase;
+  const __half* resh = (RK == RES_F16 && valid) ? reinterpret_cast<const __half*>(e.res) + res_off : nullptr;
+  const __half* res2p = (RK == RES_F16 && e.res2 && valid)
+                            ? e.res2 + (long long)slot * e.res2_slot_stride + (long long)t * e.res2_row_stride + nbase : nullptr;
+  __half* yh = (e.y && valid) ? reinterpret_cast<__half*>(e.y) + (long long)slot * e.y_slot_stride + (long long)(e.y_row0 + t) * e.y_row_stride + nbase
+                              : nullptr;
+  __half* y2p = (e.y2 && valid) ? e.y2 + (long long)slot * e.y2_slot_stride + (long long)(e.y2_row0 + t) * e.y2_row_stride + nbase : nullptr;
+  const float inv = e.res_inv_slope != 0.f ? e.res_inv_slope : 1.f;
+  const float s2 = e.act2 == ACT_NONE ? 1.f : e.slope2;
+  const bool scaled = e.out_scale != 1.f;
+  uint4 rbuf[RK == RES_F16 ? PF : 1][2], r2buf[RK == RES_F16 ? PF : 1][2];
+  if (RK == RES_F16) {
+#pragma unroll
+    for (int c = 0; c < PF; ++c) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        rbuf[c][i] = resh ? *(reinterpret_cast<const uint4*>(resh + c * 16) + i) : make_uint4(0, 0, 0, 0);
+        r2buf[c][i] = res2p ? *(reinterpret_cast<const uint4*>(res2p + c * 16) + i) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  mbar_wait(acc_full_bar, parity);
+  tc_fence_after();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = ch * 16;
+    uint32_t acc[16];
+    tc_ld_32x32b_x16(tmem_lane_base + (uint32_t)c0, acc);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nbase + c0 + 4 * i);
+      v[4 * i] = __uint_as_float(acc[4 * i]) + b4.x;
+      v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4.y;
+      v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z;
+      v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
+    }
+    if (RK == RES_F16) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&rbuf[ch % PF][i]);
+        const __half2* sp = reinterpret_cast<const __half2*>(&r2buf[ch % PF][i]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 a = __half22float2(hp[u]);
+          v[8 * i + 2 * u] += fminf(a.x, a.x * inv);
+          v[8 * i + 2 * u + 1] += fminf(a.y, a.y * inv);
+          if (res2p) {                                          // warp-uniform
+            const float2 c = __half22float2(sp[u]);
+            v[8 * i + 2 * u] += c.x; v[8 * i + 2 * u + 1] += c.y;
+          }
+        }
+      }
+      if (ch + PF < NCH) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          rbuf[ch % PF][i] = resh ? *(reinterpret_cast<const uint4*>(resh + (ch + PF) * 16) + i) : make_uint4(0, 0, 0, 0);
+          if (res2p) r2buf[ch % PF][i] = *(reinterpret_cast<const uint4*>(res2p + (ch + PF) * 16) + i);
+        }
+      }
+    }
+    if (scaled) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] *= e.out_scale;
+    }
+    if (yh) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __half2 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(v[8 * i + 2 * u], v[8 * i + 2 * u + 1]);
+        *(reinterpret_cast<uint4*>(yh + c0) + i) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+    if (y2p) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __half2 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float x0 = v[8 * i + 2 * u], x1 = v[8 * i + 2 * u + 1];
+          h[u] = __floats2half2_rn(fmaxf(x0, x0 * s2), fmaxf(x1, x1 * s2));
+        }
+        *(reinterpret_cast<uint4*>(y2p + c0) + i) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
                                               bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+  // vocoder layers: fp16 rows in and out, no scale / mask / activation before the residual, slopes in (0, 1)
+  const bool lean = e.scale == 1.f && e.acc_scale == 1.f && !e.rowmask && e.act == ACT_NONE && !e.accumulate && !e.y2_lo_off &&
+                    (!e.y || e.y_is_half) && (!e.res || e.res_is_half) && (e.act2 == ACT_NONE || (e.act2 == ACT_LRELU && e.slope2 > 0.f && e.slope2 < 1.f)) &&
+                    (e.res_inv_slope == 0.f || e.res_inv_slope > 1.f);
+  if (lean) {
+    if (!e.res) epilogue_rows_lean<BN, RES_NONE>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
+    else epilogue_rows_lean<BN, RES_F16>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
+    return;
+  }
   // one lean instantiation per residual kind (warp-uniform dispatch)
   if (!e.res) epilogue_rows_k<BN, RES_NONE>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
   else if (e.res_is_half) epilogue_rows_k<BN, RES_F16>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
@@ -753,6 +861,14 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   const bool deep = m_tiles * a.n_tiles <= 2 * num_sms() && a.kblocks >= 12;
   if (BK == 64) {
     if (BN == 128) {
+      // fewer than half the SMs would get a 128-wide tile: halve the tile width instead (twice the CTAs, each with the same K loop)
+      static const int narrow = [] { const char* v = getenv("CONAN_TC_NARROW"); return v ? atoi(v) : 1; }();
+      if (deep && narrow && m_tiles * a.n_tiles * 2 <= num_sms()) {
+        a.n_tiles = p.cout / 64;
+        if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, 64, 1, BK * 2))
+          return 1;
+        return launch_variant<64, 64, 8>(tmA, tmW, a, m_tiles, st);
+      }
       if (deep) return launch_variant<128, 64, 6>(tmA, tmW, a, m_tiles, st);
       // enough tiles to fill the machine with pairs: two m-tiles share every B tile (the layer is L2 -> SM bandwidth bound)
       static const int pair_mode = [] { const char* v = getenv("CONAN_TC_PAIR"); return v ? atoi(v) : 2; }();
