@@ -861,13 +861,14 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   const bool deep = m_tiles * a.n_tiles <= 2 * num_sms() && a.kblocks >= 12;
   if (BK == 64) {
     if (BN == 128) {
-      // fewer than half the SMs would get a 128-wide tile: halve the tile width instead (twice the CTAs, each with the same K loop)
+      // too few 128-wide tiles to fill the SMs: narrow the tile (more CTAs, each with the same K loop) until ~3/4 of them have one
       static const int narrow = [] { const char* v = getenv("CONAN_TC_NARROW"); return v ? atoi(v) : 1; }();
       if (deep && narrow && m_tiles * a.n_tiles * 2 <= num_sms()) {
-        a.n_tiles = p.cout / 64;
-        if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, 64, 1, BK * 2))
+        const int bn = (m_tiles * (p.cout / 64) * 4 >= 3LL * num_sms() || p.cout % 32 != 0) ? 64 : 32;
+        a.n_tiles = p.cout / bn;
+        if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, bn, 1, BK * 2))
           return 1;
-        return launch_variant<64, 64, 8>(tmA, tmW, a, m_tiles, st);
+        return bn == 64 ? launch_variant<64, 64, 8>(tmA, tmW, a, m_tiles, st) : launch_variant<32, 64, 8>(tmA, tmW, a, m_tiles, st);
       }
       if (deep) return launch_variant<128, 64, 6>(tmA, tmW, a, m_tiles, st);
       // enough tiles to fill the machine with pairs: two m-tiles share every B tile (the layer is L2 -> SM bandwidth bound)
