@@ -263,7 +263,7 @@ def run_b200(args):
             tf, gb = fl / (ms * 1e-3) / 1e12, by / (ms * 1e-3) / 1e9
             r = {"kernel": kname, "bound": bound, "launches_per_step": int(nl // NPROF), "ms_per_step": ms / NPROF,
                  "algorithmic_gflop_per_step": fl / NPROF / 1e9, "algorithmic_gbyte_per_step": by / NPROF / 1e9,
-                 "tflops": tf, "gbs": gb, "traffic": None, "peak_source": peak_src}
+                 "tflops": tf, "gbs": gb, "traffic": _measured_traffic(kname), "peak_source": peak_src}
             if bound == "tensor":
                 r.update(achieved=tf, peak=tf_peak, unit="TFLOP/s", frac=tf / tf_peak)
             else:
@@ -299,6 +299,23 @@ def run_b200(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _measured_traffic(kernel_name: str):
+    """DRAM bytes per launch of a kernel family, measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum) on the same
+    command and committed under profiles/ (tools/summarize_profiles.py traffic); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1]))
+    except Exception:
+        return None
+    for fam, v in d.items():
+        if not fam.startswith("_") and kernel_name.startswith(fam):
+            return v["dram_bytes_per_launch"]
+    return None
 
 
 def main():

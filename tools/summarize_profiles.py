@@ -95,5 +95,36 @@ def full(src, dst):
     print("wrote", dst)
 
 
+def traffic(src, dst):
+    """ncu launch list (gpu__time_duration + dram__bytes_read/write per launch) -> JSON {kernel family: measured DRAM bytes per
+    launch}, read by bench.py for the `roofline.traffic` field."""
+    import json
+    lines = [l for l in open(src) if not l.startswith("==")]
+    byid = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = byid.setdefault(r["ID"], {"name": r["Kernel Name"]})
+        v, u = float(r["Metric Value"].replace(",", "")), r["Metric Unit"]
+        if r["Metric Name"] != "gpu__time_duration.sum":
+            d[r["Metric Name"]] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    fam = collections.OrderedDict()
+    for d in byid.values():
+        n = d["name"]
+        key = ("resblock_fused_kernel" if "resblock_fused" in n else "ffn_fused_kernel" if "ffn_fused" in n else
+               "conv_window_tc_kernel" if "conv_window_tc" in n else
+               # the vocoder layers run the <128, 64, 3, ...> variants; every other variant is a split-fp16 Emformer / Conan GEMM
+               ("conv_gemm_tc_kernel (" if re.search(r"<\(?i?n?t?\)?128, \(?i?n?t?\)?64, \(?i?n?t?\)?3,", n) else "conv_gemm_tc_kernel, split")
+               if "conv_gemm_tc" in n else
+               "conv_gemm_ffma_kernel" if "conv_gemm_ffma" in n else None)
+        if key is None:
+            continue
+        a = fam.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+    out = {k: {"launches": v[0], "dram_bytes_per_launch": v[1] / v[0]} for k, v in fam.items()}
+    out["_source"] = src
+    json.dump(out, open(dst, "w"), indent=1)
+    print("wrote", dst)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
