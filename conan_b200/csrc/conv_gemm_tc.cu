@@ -290,9 +290,23 @@ __device__ __forceinline__ void epilogue_rows_lean(const TcEpi& e, const float* 
   }
 }
 
-template <int BN>
+// host-side mirror of the condition under which the lean epilogue applies
+inline bool epilogue_is_lean(const TcEpi& e) {
+  return e.scale == 1.f && e.acc_scale == 1.f && !e.rowmask && e.act == ACT_NONE && !e.accumulate && !e.y2_lo_off &&
+         (!e.y || e.y_is_half) && (!e.res || e.res_is_half) && (e.act2 == ACT_NONE || (e.act2 == ACT_LRELU && e.slope2 > 0.f && e.slope2 < 1.f)) &&
+         (e.res_inv_slope == 0.f || e.res_inv_slope > 1.f);
+}
+
+// LEAN_ONLY: the launcher has checked epilogue_is_lean(); the general path is not even compiled into that kernel variant
+// (half the SASS: these kernels were stalling on instruction fetch)
+template <int BN, bool LEAN_ONLY = false>
 __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __restrict__ s_bias, uint32_t tmem_lane_base, int nbase,
                                               bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+  if (LEAN_ONLY) {
+    if (!e.res) epilogue_rows_lean<BN, RES_NONE>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
+    else epilogue_rows_lean<BN, RES_F16>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
+    return;
+  }
   // vocoder layers: fp16 rows in and out, no scale / mask / activation before the residual, slopes in (0, 1)
   const bool lean = e.scale == 1.f && e.acc_scale == 1.f && !e.rowmask && e.act == ACT_NONE && !e.accumulate && !e.y2_lo_off &&
                     (!e.y || e.y_is_half) && (!e.res || e.res_is_half) && (e.act2 == ACT_NONE || (e.act2 == ACT_LRELU && e.slope2 > 0.f && e.slope2 < 1.f)) &&
@@ -329,7 +343,7 @@ struct SmemLayout {
 // one CTA per SM) and its own epilogue warpgroup.
 // ES = epilogue warpgroups per m-tile, each draining BN / ES accumulator columns (the short-K layers are bound by the
 // epilogue's latency, not by the MMAs: more warps in flight per tile).
-template <int BN, int BK, int STAGES, int MT, int ES>
+template <int BN, int BK, int STAGES, int MT, int ES, bool LEAN>
 __global__ void __launch_bounds__(64 + 128 * MT * ES, MT == 2 ? 1 : (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4)))
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
   using SL = SmemLayout<BN, BK, STAGES, MT>;
@@ -450,7 +464,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t aph = (it >> 1) & 1;
       const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * MT + wg;
       const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
-      epilogue_rows<BNE>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * MT + wg) * BN + cpart * BNE),
+      epilogue_rows<BNE, LEAN>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * MT + wg) * BN + cpart * BNE),
                          nt * BN + cpart * BNE, mt < a.m_tiles && stream < a.n_streams, stream, t, &acc_full[ab], aph);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
@@ -711,10 +725,10 @@ int pick_bn(int cout) {
   return 0;
 }
 
-template <int BN, int BK, int STAGES, int MT = 1, int ES = 1>
+template <int BN, int BK, int STAGES, int MT = 1, int ES = 1, bool LEAN = false>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, long long m_tiles, cudaStream_t st) {
   using SL = SmemLayout<BN, BK, STAGES, MT>;
-  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES, MT, ES>;
+  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES, MT, ES, LEAN>;
   constexpr int threads = 64 + 128 * MT * ES;
   static bool attr_set = false;
   static int per_sm = 1;
@@ -875,7 +889,8 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
       static const int pair_mode = [] { const char* v = getenv("CONAN_TC_PAIR"); return v ? atoi(v) : 2; }();
       if (nseg == 1 && m_tiles * a.n_tiles >= (long long)es_min_tiles() * num_sms()) {
         if (pair_mode == 1) return launch_variant<128, 64, 4, 2, 1>(tmA, tmW, a, m_tiles, st);
-        if (pair_mode == 2) return launch_variant<128, 64, 3, 1, 2>(tmA, tmW, a, m_tiles, st);
+        if (pair_mode == 2) return epilogue_is_lean(a.e) ? launch_variant<128, 64, 3, 1, 2, true>(tmA, tmW, a, m_tiles, st)
+                                                         : launch_variant<128, 64, 3, 1, 2>(tmA, tmW, a, m_tiles, st);
         if (pair_mode == 3) return launch_variant<128, 64, 4, 2, 2>(tmA, tmW, a, m_tiles, st);
       }
       return launch_variant<128, 64, 3>(tmA, tmW, a, m_tiles, st);
