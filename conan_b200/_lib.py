@@ -75,6 +75,8 @@ SYMBOLS = {
     "conan_vocoder_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "conan_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "conan_step_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "conan_step_host_submit": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int)]),
+    "conan_step_host_wait": (C.c_int, [_P, C.c_int]),
     "conan_engine_launch_count": (C.c_uint64, [_P]),
     "conan_engine_set_profiling": (C.c_int, [_P, C.c_int]),
     "conan_engine_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

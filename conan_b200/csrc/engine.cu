@@ -104,6 +104,10 @@ struct conan_engine {
   mutable std::vector<ProfRec> prof;
   // ---- host-call staging
   int* hIds = nullptr; float* hChunk = nullptr; float* hWav = nullptr; float* hMel = nullptr; int* hTok = nullptr; int* hIdsSmall = nullptr;
+  // pipelined host stepping (conan_step_host_submit / _wait): second set of device outputs, a copy stream, per-ticket events
+  float* hWav2 = nullptr; float* hMel2 = nullptr; int* hTok2 = nullptr;
+  cudaStream_t copyStream = nullptr; cudaEvent_t evCompute[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
+  unsigned long long submitCount = 0; bool ticketPending[2] = {false, false};
 
   const WeightSlot* W(const std::string& name) const {
     auto it = windex.find(name);
@@ -541,6 +545,13 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->hChunk, (size_t)S * rows * D));
   TRY(dalloc(e, &e->hWav, (size_t)S * e->vL[c.voc_n_ups])); TRY(dalloc(e, &e->hMel, (size_t)S * seg * c.n_mels));
   TRY(dalloc(e, &e->hTok, (size_t)S * seg));
+  TRY(dalloc(e, &e->hWav2, (size_t)S * e->vL[c.voc_n_ups])); TRY(dalloc(e, &e->hMel2, (size_t)S * seg * c.n_mels));
+  TRY(dalloc(e, &e->hTok2, (size_t)S * seg));
+  CONAN_CUDA_OK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CONAN_CUDA_OK(cudaEventCreateWithFlags(&e->evCompute[i], cudaEventDisableTiming));
+    CONAN_CUDA_OK(cudaEventCreateWithFlags(&e->evCopy[i], cudaEventDisableTiming));
+  }
   return 0;
 }
 
@@ -930,6 +941,8 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
 
 void conan_engine_destroy(conan_engine_t* e) {
   if (!e) return;
+  if (e->copyStream) { cudaStreamSynchronize(e->copyStream); cudaStreamDestroy(e->copyStream); }
+  for (int i = 0; i < 2; ++i) { if (e->evCompute[i]) cudaEventDestroy(e->evCompute[i]); if (e->evCopy[i]) cudaEventDestroy(e->evCopy[i]); }
   for (void* p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -1046,6 +1059,41 @@ int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, cons
   if (mel_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out_host, e->hMel, (size_t)n * c.segment * c.n_mels * 4, cudaMemcpyDeviceToHost, st));
   if (tokens_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(tokens_out_host, e->hTok, (size_t)n * c.segment * 4, cudaMemcpyDeviceToHost, st));
   CONAN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int conan_step_host_submit(conan_engine_t* e, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
+                           float* mel_out_host, int32_t* tokens_out_host, void* stream, int* ticket) {
+  if (check_ready(e)) return 1;
+  if (n < 0 || n > e->S || !slot_ids_host || !chunk_host || !wav_out_host || !ticket) { set_error("bad arguments to conan_step_host_submit"); return 1; }
+  const conan_config_t& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int b = (int)(e->submitCount & 1);
+  if (e->ticketPending[b]) { set_error("conan_step_host_submit: two steps already in flight; call conan_step_host_wait first"); return 1; }
+  const size_t rows = c.segment + c.right_context, Lw = e->vL[c.voc_n_ups];
+  float* dWav = b ? e->hWav2 : e->hWav; float* dMel = b ? e->hMel2 : e->hMel; int* dTok = b ? e->hTok2 : e->hTok;
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->hIds, slot_ids_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->hChunk, chunk_host, (size_t)n * rows * c.emformer_dim * 4, cudaMemcpyHostToDevice, st));
+  // output set b was last read by the copy of ticket b two submits ago: that copy has been waited for by the caller
+  // (ticketPending[b] is clear), so the step may overwrite it
+  TRY(conan_step(e, n, e->hIds, e->hChunk, dWav, mel_out_host ? dMel : nullptr, tokens_out_host ? dTok : nullptr, stream));
+  CONAN_CUDA_OK(cudaEventRecord(e->evCompute[b], st));
+  CONAN_CUDA_OK(cudaStreamWaitEvent(e->copyStream, e->evCompute[b], 0));
+  CONAN_CUDA_OK(cudaMemcpyAsync(wav_out_host, dWav, (size_t)n * Lw * 4, cudaMemcpyDeviceToHost, e->copyStream));
+  if (mel_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out_host, dMel, (size_t)n * c.segment * c.n_mels * 4, cudaMemcpyDeviceToHost, e->copyStream));
+  if (tokens_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(tokens_out_host, dTok, (size_t)n * c.segment * 4, cudaMemcpyDeviceToHost, e->copyStream));
+  CONAN_CUDA_OK(cudaEventRecord(e->evCopy[b], e->copyStream));
+  e->ticketPending[b] = true;
+  ++e->submitCount;
+  *ticket = b;
+  return 0;
+}
+
+int conan_step_host_wait(conan_engine_t* e, int ticket) {
+  if (check_ready(e)) return 1;
+  if (ticket < 0 || ticket > 1 || !e->ticketPending[ticket]) { set_error("conan_step_host_wait: no such step in flight"); return 1; }
+  CONAN_CUDA_OK(cudaEventSynchronize(e->evCopy[ticket]));
+  e->ticketPending[ticket] = false;
   return 0;
 }
 

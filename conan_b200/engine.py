@@ -205,6 +205,22 @@ class Engine:
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         _lib.check(self.lib.conan_step_host(self.h, n, vp(slots), vp(chunk), vp(wav_out), vp(mel_out), vp(tokens_out), self._stream()), "step_host")
 
+    def step_host_submit(self, slots: np.ndarray, chunk: np.ndarray, wav_out: np.ndarray, mel_out: Optional[np.ndarray] = None,
+                         tokens_out: Optional[np.ndarray] = None) -> int:
+        """Pipelined step_host: returns a ticket at once; the result copies of this step overlap the next step's compute.
+        At most two steps in flight; every array passed must stay alive and untouched until step_host_wait(ticket)."""
+        n = len(slots)
+        assert slots.dtype == np.int32 and chunk.dtype == np.float32 and chunk.shape == (n, self.rows_in, self.cfg.emformer_dim)
+        assert wav_out.dtype == np.float32 and wav_out.shape == (n, self.hop_out)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        t = C.c_int(-1)
+        _lib.check(self.lib.conan_step_host_submit(self.h, n, vp(slots), vp(chunk), vp(wav_out), vp(mel_out), vp(tokens_out), self._stream(),
+                                                   C.byref(t)), "step_host_submit")
+        return t.value
+
+    def step_host_wait(self, ticket: int):
+        _lib.check(self.lib.conan_step_host_wait(self.h, ticket), "step_host_wait")
+
     # ------------------------------------------------------------------ measurement
     def set_profiling(self, enabled: bool):
         _lib.check(self.lib.conan_engine_set_profiling(self.h, int(enabled)), "set_profiling")

@@ -153,6 +153,14 @@ int conan_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const fl
 int conan_step_host(conan_engine_t* eng, int n, const int32_t* slot_ids_host, const float* chunk_host,
                     float* wav_out_host, float* mel_out_host, int32_t* tokens_out_host, void* stream);
 
+/* Pipelined variant for a serving loop: submit enqueues the input copies and the step on `stream`, the result copies on an
+ * engine-owned copy stream, and returns a ticket; the result copies of step i overlap the compute of step i+1.  At most two
+ * steps may be in flight.  Every host buffer passed to a submit (pinned memory) must stay valid and untouched until its ticket
+ * has been waited for: use two sets of chunk / result buffers, alternating. */
+int conan_step_host_submit(conan_engine_t* eng, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
+                           float* mel_out_host, int32_t* tokens_out_host, void* stream, int* ticket);
+int conan_step_host_wait(conan_engine_t* eng, int ticket);
+
 /* kernels launched by this engine since creation (bench.py's gpu_launches claim) */
 uint64_t conan_engine_launch_count(const conan_engine_t* eng);
 

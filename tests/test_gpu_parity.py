@@ -692,3 +692,38 @@ def test_emformer_fused_ffn_matches_two_gemm_path(state_dicts):
     with torch.no_grad():
         ref = torch.cat([o.step(_chunks(src, pos)[0]) for pos in range(0, T, 4)], 1)
     assert (outs[1][0] - ref).abs().max().item() < 1e-4
+
+
+def test_step_host_pipelined_equals_synchronous(eng_tc):
+    """conan_step_host_submit / _wait (two steps in flight, result copies on the engine's copy stream) returns exactly what the
+    synchronous conan_step_host returns, step by step."""
+    eng = eng_tc
+    ref = torch.stack([synth.synth_mel(40, 5), synth.synth_mel(40, 6)])
+    src = torch.stack([synth.synth_mel(24, 7), synth.synth_mel(24, 8)])
+    slots = np.array([2, 3], dtype=np.int32)
+
+    def run(pipelined):
+        eng.reset_slots(slots)
+        eng.open_sessions(slots, ref.cuda())
+        chunks = [np.ascontiguousarray(_chunks(src, pos)[0].numpy()) for pos in range(0, 24, 4)]
+        wavs = [np.empty((2, 1280), dtype=np.float32) for _ in chunks]
+        mels = [np.empty((2, 4, 80), dtype=np.float32) for _ in chunks]
+        toks = [np.empty((2, 4), dtype=np.int32) for _ in chunks]
+        if not pipelined:
+            for c, w, m, t in zip(chunks, wavs, mels, toks):
+                eng.step_host(slots, c, w, m, t)
+        else:
+            prev = None
+            for c, w, m, t in zip(chunks, wavs, mels, toks):
+                tk = eng.step_host_submit(slots, c, w, m, t)
+                if prev is not None:
+                    eng.step_host_wait(prev)
+                prev = tk
+            eng.step_host_wait(prev)
+            with pytest.raises(RuntimeError):
+                eng.step_host_wait(prev)                     # nothing in flight any more
+        return np.concatenate(wavs, 1), np.concatenate(mels, 1), np.concatenate(toks, 1)
+
+    a, b = run(False), run(True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
