@@ -889,7 +889,8 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
       static const int pair_mode = [] { const char* v = getenv("CONAN_TC_PAIR"); return v ? atoi(v) : 2; }();
       if (nseg == 1 && m_tiles * a.n_tiles >= (long long)es_min_tiles() * num_sms()) {
         if (pair_mode == 1) return launch_variant<128, 64, 4, 2, 1>(tmA, tmW, a, m_tiles, st);
-        if (pair_mode == 2) return epilogue_is_lean(a.e) ? launch_variant<128, 64, 3, 1, 2, true>(tmA, tmW, a, m_tiles, st)
+        static const int lean_only = [] { const char* v = getenv("CONAN_TC_LEANONLY"); return v ? atoi(v) : 0; }();   // measured: 1.99 vs 1.91 ms with the shared variant
+        if (pair_mode == 2) return (lean_only && epilogue_is_lean(a.e)) ? launch_variant<128, 64, 3, 1, 2, true>(tmA, tmW, a, m_tiles, st)
                                                          : launch_variant<128, 64, 3, 1, 2>(tmA, tmW, a, m_tiles, st);
         if (pair_mode == 3) return launch_variant<128, 64, 4, 2, 2>(tmA, tmW, a, m_tiles, st);
       }
