@@ -304,6 +304,7 @@ logmel_kernel(const float* __restrict__ spec, int ld, int bins, const float* __r
   __syncthreads();
   for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
     float acc = 0.f;
+#pragma unroll 1                                   // (an unrolled version issued shared loads past `bins`: compute-sanitizer)
     for (int b = 0; b < bins; ++b) acc = fmaf(basis_t[(long long)b * n_mels + m], mag[b], acc);
     const float v = log10f(fmaxf(acc, eps));
     mel[(long long)blockIdx.x * n_mels + m] = fminf(fmaxf(v, vmin), vmax);
@@ -561,7 +562,7 @@ int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, i
 int launch_logmel(const float* spec, int ld, int bins, const float* basis_t, int n_mels, float eps, float vmin, float vmax,
                   float* mel, long long n_frames, cudaStream_t st) {
   if (n_frames <= 0) return 0;
-  logmel_kernel<<<(unsigned)n_frames, 128, (size_t)bins * sizeof(float), st>>>(spec, ld, bins, basis_t, n_mels, eps, vmin, vmax, mel);
+  logmel_kernel<<<(unsigned)n_frames, 128, ((size_t)bins + 64) * sizeof(float), st>>>(spec, ld, bins, basis_t, n_mels, eps, vmin, vmax, mel);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
