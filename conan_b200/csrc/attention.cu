@@ -26,7 +26,7 @@ constexpr int EMF_MAX_ROWS = 8;
 __global__ void __launch_bounds__(256, 4)
 emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ ring, const int* __restrict__ past_len,
                           RowView att, const int* __restrict__ slot_ids, int seg, int rc, int lc,
-                          int ring_rows, int D, int heads, int ldq) {
+                          int ring_rows, int D, int heads, int ldq, EmfAttnEpilogue ep, int fused) {
   extern __shared__ float sm[];
   const int rows = seg + rc;
   const int slot = slot_of(slot_ids, blockIdx.x);
@@ -130,8 +130,33 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
       const int r = o / hd, d = o - r * hd;
       float v = 0.f;
       for (int key = 0; key < nkeys; ++key) v = fmaf(sK[key * DS + c0 + r], sV[key * DS + c0 + d], v);
-      store_view(att, (long long)blockIdx.x * att.slot_stride + (long long)r * att.row_stride + c0 + d, v);
+      if (fused) sQ[r * D + c0 + d] = v;          // this head's query columns are dead: the attention output takes their place
+      else store_view(att, (long long)blockIdx.x * att.slot_stride + (long long)r * att.row_stride + c0 + d, v);
     }
+  }
+  if (!fused) return;
+  // ---- fused tail: out_proj (fp32) + bias + residual -> r1; LayerNorm(r1) -> fn  (rows <= 8 warps)
+  __syncthreads();
+  float* sR = sK;                                  // K is dead: [rows][D] outputs of out_proj + residual
+  const long long row0 = (long long)blockIdx.x * rows;
+  for (int o = tid; o < rows * D; o += blockDim.x) {
+    const int r = o / D, c = o - r * D;
+    float acc = ep.bias[c];
+    for (int k = 0; k < D; ++k) acc = fmaf(sQ[r * D + k], ep.wt[k * D + c], acc);      // wt[k][c]: coalesced over c
+    acc += ep.x_res[(row0 + r) * ep.ld + c];
+    ep.r1[(row0 + r) * ep.ld + c] = acc;
+    sR[r * D + c] = acc;
+  }
+  __syncthreads();
+  for (int r = warp; r < rows; r += (blockDim.x >> 5)) {
+    float s1 = 0.f;
+    for (int c = lane; c < D; c += 32) s1 += sR[r * D + c];
+    const float mean = warp_sum(s1) / D;
+    float s2 = 0.f;
+    for (int c = lane; c < D; c += 32) { const float d = sR[r * D + c] - mean; s2 += d * d; }
+    const float rstd = 1.f / sqrtf(warp_sum(s2) / D + ep.eps);
+    const long long o = (long long)blockIdx.x * ep.fn.slot_stride + (long long)(ep.fn.row0 + r) * ep.fn.row_stride;
+    for (int c = lane; c < D; c += 32) store_view(ep.fn, o + c, (sR[r * D + c] - mean) * rstd * ep.ln_g[c] + ep.ln_b[c]);
   }
 }
 
@@ -302,7 +327,7 @@ cross_attention_staged_kernel(const float* __restrict__ q, const float* __restri
 
 int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, RowView att, int n,
                               const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv,
-                              cudaStream_t st) {
+                              cudaStream_t st, const EmfAttnEpilogue* ep) {
   if (n <= 0) return 0;
   if (rc + lc + seg > EMF_MAX_KEYS || seg + rc > EMF_MAX_ROWS || seg + rc > D / heads) { set_error("emformer_attention: key count / query rows above compiled limits (rows <= min(8, head_dim))"); return 1; }
   if (D % 4 != 0 || ld_qkv % 4 != 0 || (rc + lc + seg) * ((2 * D) / 4) > 10 * 256) { set_error("emformer_attention: D / ld must be multiples of 4 and keys*2D/4 <= 2560"); return 1; }
@@ -315,7 +340,8 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
     attr_set = true;
   }
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }
-  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv);
+  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv,
+                                                ep ? *ep : EmfAttnEpilogue{}, ep ? 1 : 0);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

@@ -146,6 +146,7 @@ void declare_weights(conan_engine* e) {
     need(e, p + "ln_in.g", D); need(e, p + "ln_in.b", D);
     need_linear(e, p + "qkv", 3 * D, D);
     need_linear(e, p + "out", D, D);
+    if (e->lin_tc && c.lin_fuse_ffn) { need(e, p + "out.wt", (size_t)D * D); need(e, p + "out.bf", D); }   // fp32 out_proj^T for the fused attention epilogue
     need(e, p + "ffn_ln.g", D); need(e, p + "ffn_ln.b", D);
     need_linear(e, p + "ffn1", F, D);
     need_linear(e, p + "ffn2", D, F);
@@ -570,12 +571,21 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
     auto q = conv_on_ctx(e, e->eXN, 1, 1, e->P(p + "qkv.w"), e->F(p + "qkv.b"), QP, n);
     out_rows(q, e->eQKV, rows, QP);
     TRY(run_conv(e, q, st, tc));
-    TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT.new_rows(), n, ids, seg, rc, c.left_context, e->ring_rows, D,
-                                  c.emformer_heads, QP, st));
-    auto o = conv_on_ctx(e, e->eATT, 1, 1, e->P(p + "out.w"), e->F(p + "out.b"), DP, n);
-    out_rows(o, e->eR1, rows, DP); res_rows(o, e->eX, rows, DP);
-    TRY(run_conv(e, o, st, tc));
-    TRY(ln_rows(e->eR1, rows, DP, 0, e->eFN.new_rows(), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
+    if (e->ffnFused) {
+      // attention + out_proj (fp32) + residual + the FFN's LayerNorm in one kernel: writes eR1 (fp32) and eFN (split fp16)
+      EmfAttnEpilogue ep;
+      ep.wt = e->F(p + "out.wt"); ep.bias = e->F(p + "out.bf"); ep.x_res = e->eX; ep.ld = DP; ep.r1 = e->eR1;
+      ep.ln_g = e->F(p + "ffn_ln.g"); ep.ln_b = e->F(p + "ffn_ln.b"); ep.eps = 1e-5f; ep.fn = e->eFN.new_rows();
+      TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT.new_rows(), n, ids, seg, rc, c.left_context, e->ring_rows, D,
+                                    c.emformer_heads, QP, st, &ep));
+    } else {
+      TRY(launch_emformer_attention(e->eQKV, e->eRing[l], e->ePast, e->eATT.new_rows(), n, ids, seg, rc, c.left_context, e->ring_rows, D,
+                                    c.emformer_heads, QP, st));
+      auto o = conv_on_ctx(e, e->eATT, 1, 1, e->P(p + "out.w"), e->F(p + "out.b"), DP, n);
+      out_rows(o, e->eR1, rows, DP); res_rows(o, e->eX, rows, DP);
+      TRY(run_conv(e, o, st, tc));
+      TRY(ln_rows(e->eR1, rows, DP, 0, e->eFN.new_rows(), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
+    }
     // the last layer's output is also the operand of the projection GEMM
     const bool last = (l == c.emformer_layers - 1);
     if (e->ffnFused) {

@@ -53,9 +53,16 @@ int launch_layernorm(const LnArgs& a, cudaStream_t st);
 int launch_emformer_assemble(const float* chunk, float* X, int ldx, int n, const int* slot_ids, int seg, int rc, int D, cudaStream_t st);
 // per stream: append utterance K/V rows to the ring, softmax(QK^T) V over [rc | left ctx | utt].
 // qkv / att are compact (index i, row stride ld); kv_ring / past_len are resident state indexed by slot_ids[i].
+// optional fused tail of the attention kernel: r1 = att . Wout^T + b + x_res (fp32, TA:416-425), fn = LayerNorm(r1) (the FFN's
+// input norm) written as a GEMM operand; compact rows [i*rows + t], row stride ld
+struct EmfAttnEpilogue {
+  const float* wt; const float* bias;        // out_proj weight transposed [D(k)][D(c)] and bias [D], fp32
+  const float* x_res; int ld; float* r1;     // residual in / out
+  const float* ln_g; const float* ln_b; float eps; RowView fn;
+};
 int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_len, RowView att, int n,
                               const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv,
-                              cudaStream_t st);
+                              cudaStream_t st, const EmfAttnEpilogue* ep = nullptr);
 int launch_advance_past_len(int* past_len, int n, const int* slot_ids, int seg, cudaStream_t st);
 int launch_argmax_rows(const float* logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C, cudaStream_t st);
 int launch_copy_rows_out(const float* src_slot, long long slot_stride, int row_stride, int row0, float* dst, int n,

@@ -156,6 +156,11 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
     out["voc.post.w"] = wpost[0].t().contiguous().reshape(-1)                    # [7, ch]
     out["voc.post.b"] = v["conv_post.conv.bias"]
     # ---- fp32-grade tensor-core mode: the per-chunk linear / conv contractions take split-fp16 weights
+    if cfg.lin_use_tensor_cores and cfg.lin_fuse_ffn:
+        # fused Emformer path: the attention kernel applies out_proj itself (fp32, 80 x 80): transposed weight [k][c] + bias
+        for l in range(cfg.emformer_layers):
+            out[f"emf.{l}.out.wt"] = out[f"emf.{l}.out.w"].float().t().contiguous()
+            out[f"emf.{l}.out.bf"] = out[f"emf.{l}.out.b"].float().contiguous()
     if cfg.lin_use_tensor_cores:
         names = [f"emf.{l}.{n}" for l in range(cfg.emformer_layers) for n in ("qkv", "out", "ffn1", "ffn2")] + ["emf.proj"]
         names += [f"conan.align.{l}.{n}" for l in range(2) for n in ("q", "out", "ffn1", "ffn2")]
