@@ -142,7 +142,8 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
   for (int o = tid; o < rows * D; o += blockDim.x) {
     const int r = o / D, c = o - r * D;
     float acc = ep.bias[c];
-    for (int k = 0; k < D; ++k) acc = fmaf(sQ[r * D + k], ep.wt[k * D + c], acc);      // wt[k][c]: coalesced over c
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) acc = fmaf(sQ[r * D + k], __ldg(ep.wt + k * D + c), acc);      // wt[k][c]: coalesced over c, 8 loads in flight
     acc += ep.x_res[(row0 + r) * ep.ld + c];
     ep.r1[(row0 + r) * ep.ld + c] = acc;
     sR[r * D + c] = acc;
