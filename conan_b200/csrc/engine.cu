@@ -327,8 +327,15 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
 }
 
 // profiling category 4: fused residual block (six convs per launch)
+// CONAN_FUSED_LANES: bit 0 -> two-lane kernel at C = 64, bit 1 -> at C = 32 (default 3: both; 0 = one stream per CTA)
+int fused_launch(const ResblockFusedParams& f, cudaStream_t st) {
+  static const int lanes = [] { const char* v = getenv("CONAN_FUSED_LANES"); return v ? atoi(v) : 3; }();
+  const bool two = ((f.C == 64 && (lanes & 1)) || (f.C == 32 && (lanes & 2))) && resblock_fused2_smem(f.C, f.k, f.dil) != 0;
+  return two ? launch_resblock_fused2(f, st) : launch_resblock_fused(f, st);
+}
+
 int run_fused(const conan_engine* e, const ResblockFusedParams& f, cudaStream_t st) {
-  if (!e->profiling) return launch_resblock_fused(f, st);
+  if (!e->profiling) return fused_launch(f, st);
   conan_engine::ProfRec r;
   r.cat = 4;
   r.flops = 2.0 * 6.0 * (double)f.n_streams * f.L * f.C * f.k * f.C;
@@ -344,7 +351,7 @@ int run_fused(const conan_engine* e, const ResblockFusedParams& f, cudaStream_t 
   }
   CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
   CONAN_CUDA_OK(cudaEventRecord(r.a, st));
-  int rc = launch_resblock_fused(f, st);
+  int rc = fused_launch(f, st);
   CONAN_CUDA_OK(cudaEventRecord(r.b, st));
   e->prof.push_back(r);
   return rc;

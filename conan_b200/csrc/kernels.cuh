@@ -106,6 +106,9 @@ struct ResblockFusedParams {
 bool resblock_fused_eligible(int C, int L, int k, const int* dil);
 int resblock_fused_hist_rows(int k, const int* dil);
 int launch_resblock_fused(const ResblockFusedParams& p, cudaStream_t st);
+// two streams in flight per CTA (resblock_fused2.cu): same parameters, same resident history format
+size_t resblock_fused2_smem(int C, int k, const int* dil);       // 0: does not fit
+int launch_resblock_fused2(const ResblockFusedParams& p, cudaStream_t st);
 
 // fused position-wise FFN (ffn_fused.cu): y partials = W2 . relu(W1 . x + b1), split-fp16 operands
 struct FfnFusedParams {

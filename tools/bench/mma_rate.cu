@@ -88,6 +88,66 @@ void run(const char* name, int a_row_step, int grid) {
   cudaFree(d);
 }
 
+// Does a tcgen05.commit fire when ITS batch of MMAs is complete, or only once later-issued MMAs have drained too?
+// warp 0: batch A (NA MMAs -> accumulator 0), commit(barA), wait `gap` cycles, batch B (NB MMAs -> accumulator 1), commit(barB).
+// warp 1 polls barA then barB and records when it saw them.
+template <int N, int ROWB>
+__global__ void __launch_bounds__(64) commit_kernel(int NA, int NB, int gap, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t barA, barB;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ long long t_issueA, t_issueB;
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&barA, 1); mbar_init(&barB, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  constexpr uint32_t idesc = make_idesc<N>();
+  const uint32_t s32 = smem_u32(smem);
+  const uint64_t ad = make_smem_desc<ROWB>(s32), bd = make_smem_desc<ROWB>(s32 + 32 * 1024);
+  if (warp == 0) {
+    for (int i = 0; i < NA; ++i) if (elect_one_sync()) tc_mma_f16(tmem_base, ad + (uint64_t)((i & 3) * 2), bd + (uint64_t)((i & 3) * 2), idesc, 1u);
+    if (elect_one_sync()) tc_commit(&barA);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) t_issueA = t1;
+    while (clock64() - t1 < gap) {}
+    for (int i = 0; i < NB; ++i) if (elect_one_sync()) tc_mma_f16(tmem_base + N, ad + (uint64_t)((i & 3) * 2), bd + (uint64_t)((i & 3) * 2), idesc, 1u);
+    if (elect_one_sync()) tc_commit(&barB);
+    if (threadIdx.x == 0) t_issueB = clock64();
+  } else {
+    mbar_wait(&barA, 0);
+    const long long ta = clock64();
+    mbar_wait(&barB, 0);
+    const long long tb = clock64();
+    __syncwarp();
+    if (threadIdx.x == 32) { out[0] = ta; out[1] = tb; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) { out[2] = t_issueA; out[3] = t_issueB; }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
+void run_commit(int NA, int NB, int gap) {
+  long long* d; cudaMalloc(&d, 32);
+  auto k = commit_kernel<64, 128>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+  for (int rep = 0; rep < 2; ++rep) k<<<1, 64, 80 * 1024>>>(NA, NB, gap, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[4]; cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+  printf("commit test N=64: A=%2d MMAs, gap %4d cycles, B=%2d MMAs : barA seen %5lld cycles after A's commit was issued; barB seen %5lld after B's commit issued %s\n",
+         NA, gap, NB, h[0] - h[2], h[1] - h[3], e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d);
+}
+
 int main() {
   for (int grid : {1, 148}) {
     run<32, 64>("C=32 window conv", 0, grid);   run<32, 64>("C=32 window conv, taps", 1, grid);  run<32, 64>("C=32 window conv, taps dil 5", 5, grid);
@@ -109,5 +169,6 @@ int main() {
   run<64, 128, 1, 2, 8>("C=64", 1, 148); run<32, 64, 1, 4, 2>("C=32", 1, 148); run<32, 64, 1, 4, 8>("C=32", 1, 148); run<128, 128, 1, 1, 8>("N=128", 0, 148);
   // two CTAs per SM, each with its own accumulator
   run<32, 64>("C=32, 2 CTAs/SM", 1, 296); run<64, 128>("C=64, 2 CTAs/SM", 1, 296); run<128, 128>("N=128, 2 CTAs/SM", 1, 296);
+  run_commit(12, 0, 0); run_commit(12, 12, 0); run_commit(12, 12, 700); run_commit(12, 44, 700); run_commit(44, 0, 0); run_commit(44, 44, 0);
   return 0;
 }
