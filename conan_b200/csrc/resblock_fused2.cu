@@ -81,7 +81,8 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* win_ready = bars + 8;                    // [lane][6]
   uint64_t* w_full = bars + 20;                      // [stages]
   uint64_t* w_empty = w_full + R2_MAX_STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + R2_MAX_STAGES);
+  uint64_t* tile_done = w_empty + R2_MAX_STAGES;     // [lane]  every epilogue thread has finished the lane's previous tile
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tile_done + 2);
   float* s_bias = reinterpret_cast<float*>(smem + a.bias_off);
   for (int i = threadIdx.x; i < R2_CONVS * C; i += blockDim.x) s_bias[i] = a.bias[i];
 
@@ -90,7 +91,7 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     for (int l = 0; l < 2; ++l) {
-      mbar_init(&a_full[l], 1); mbar_init(&in_free[l], EPI);
+      mbar_init(&a_full[l], 1); mbar_init(&in_free[l], EPI); mbar_init(&tile_done[l], EPI);
       mbar_init(&acc_full[l * 2], 1); mbar_init(&acc_full[l * 2 + 1], 1);
       for (int c = 0; c < R2_CONVS; ++c) mbar_init(&win_ready[l * R2_CONVS + c], EPI);
     }
@@ -214,6 +215,10 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const bool last = t == a.tiles - 1;
         uint8_t* lbase = smem + l * a.lane_bytes;
         uint8_t* hs = lbase + a.hs_off;
+        // conv 0 of a tile depends only on the TMA box, so a fast thread could get here while a slow one still reads window 4
+        // (residual of conv 5 of the previous tile) from the buffer that window 1 is about to be written into: wait until every
+        // epilogue thread has finished that tile (found with compute-sanitizer's timing, invisible at full speed)
+        if (c == 0) mbar_wait_lane0(&tile_done[l], (it[l].tiles_done & 1) ^ 1, 0);
         if (t == 0 && c == 0) hist_l[l] = a.hist + (long long)(a.slot_ids ? a.slot_ids[i] : i) * a.hist_slot_stride;
         __half* hist = hist_l[l];
         if (t == 0 && c == 0) {
@@ -340,6 +345,7 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
         if (c == 3) mbar_arrive(&in_free[l]);       // buffer 0 (input window, then window 3) is free for the next tile's input box
+        if (c == R2_CONVS - 1) mbar_arrive(&tile_done[l]);
         it[l].advance();
       }
     }
