@@ -727,3 +727,26 @@ def test_step_host_pipelined_equals_synchronous(eng_tc):
     a, b = run(False), run(True)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_vocoder_other_kernel_sizes_and_dilations():
+    """A vocoder config other than the reference's (resblock kernels 5 / 9, dilations 1, 2, 4): the fused residual-block kernels
+    take their generic-kernel-size path; fp16-operand result against the oracle, and the fused path against the conv-by-conv path."""
+    from conan_b200.engine import Engine, make_config
+    from oracle.incremental import HifiGanOracle
+    voc_hp = dict(synth.DEFAULT_VOC_HP, resblock_kernel_sizes=[5, 9], resblock_dilation_sizes=[[1, 2, 4], [1, 2, 4]])
+    sds = synth.make_all_state_dicts(77, voc_hp=voc_hp)
+    mel = torch.randn(3, 12, 80, generator=torch.Generator().manual_seed(6)) * 0.6
+    o = HifiGanOracle(sds[2], resblock_kernel_sizes=(5, 9), resblock_dilation_sizes=((1, 2, 4), (1, 2, 4)))
+    o.reset(3)
+    with torch.no_grad():
+        ref = torch.cat([o.step(mel[:, i:i + 4]) for i in range(0, 12, 4)], 1)
+    outs = []
+    for fuse in (True, False):
+        eng = Engine(*sds, make_config(voc_hp=voc_hp, max_slots=8, max_ref_frames=64, voc_fuse_resblocks=fuse))
+        outs.append(_run_vocoder(eng, mel, [5, 1, 2]))
+        eng.close()
+    s = min(snr_ac_db(ref[b].numpy(), outs[0][b].numpy()) for b in range(3))
+    print("k = 5 / 9, dilations 1 2 4: worst SNR_ac", s, "fused vs per-conv SNR", snr_db(outs[1].numpy(), outs[0].numpy()))
+    assert s >= SNR_MIN_DB
+    assert snr_db(outs[1].numpy(), outs[0].numpy()) > 70.0
