@@ -137,13 +137,18 @@ emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ rin
   if (!fused) return;
   // ---- fused tail: out_proj (fp32) + bias + residual -> r1; LayerNorm(r1) -> fn  (rows <= 8 warps)
   __syncthreads();
-  float* sR = sK;                                  // K is dead: [rows][D] outputs of out_proj + residual
+  // K / V are dead: their space takes the transposed out_proj weight [D][D] (one coalesced pass) and the rows of r1
+  float* sW = sK;
+  float* sR = sK + D * D;
+  for (int idx = tid * 4; idx < D * D; idx += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sW + idx) = __ldg(reinterpret_cast<const float4*>(ep.wt + idx));
+  __syncthreads();
   const long long row0 = (long long)blockIdx.x * rows;
   for (int o = tid; o < rows * D; o += blockDim.x) {
     const int r = o / D, c = o - r * D;
     float acc = ep.bias[c];
 #pragma unroll 8
-    for (int k = 0; k < D; ++k) acc = fmaf(sQ[r * D + k], __ldg(ep.wt + k * D + c), acc);      // wt[k][c]: coalesced over c, 8 loads in flight
+    for (int k = 0; k < D; ++k) acc = fmaf(sQ[r * D + k], sW[k * D + c], acc);      // sQ broadcast, sW consecutive over c
     acc += ep.x_res[(row0 + r) * ep.ld + c];
     ep.r1[(row0 + r) * ep.ld + c] = acc;
     sR[r * D + c] = acc;
@@ -333,6 +338,7 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
   if (rc + lc + seg > EMF_MAX_KEYS || seg + rc > EMF_MAX_ROWS || seg + rc > D / heads) { set_error("emformer_attention: key count / query rows above compiled limits (rows <= min(8, head_dim))"); return 1; }
   if (D % 4 != 0 || ld_qkv % 4 != 0 || (rc + lc + seg) * ((2 * D) / 4) > 10 * 256) { set_error("emformer_attention: D / ld must be multiples of 4 and keys*2D/4 <= 2560"); return 1; }
   if (ring_rows < lc + seg) { set_error("emformer_attention: ring too short"); return 1; }
+  if (ep && (size_t)D * D + (size_t)(seg + rc) * D > (size_t)2 * (rc + lc + seg) * (D + 1)) { set_error("emformer_attention: fused tail does not fit in the K/V staging area"); return 1; }
   size_t sh = ((size_t)2 * (rc + lc + seg) * (D + 1) + (size_t)(seg + rc) * D) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
