@@ -1,6 +1,8 @@
 // Norm / gather / ring / small-reduction kernels of the path.  One warp per row wherever a
 // row (<= 512 channels) is the unit of work, so every reduction is a warp shuffle and every
 // global access is a coalesced 128-byte line.
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace conan {
@@ -252,24 +254,27 @@ __global__ void conv_post_tanh_kernel(const T* __restrict__ x, long long slot_st
 
 // fp16 fast path: a CTA stages the (TB + k - 1) x C input rows of TB consecutive output samples in shared memory with
 // coalesced 16-byte loads (rows padded by 16 bytes: conflict-free per-thread row reads), then one thread per sample.
+// The K*C filter taps travel as a kernel parameter: every FFMA takes its weight straight from the constant bank (the index is
+// compile-time after unrolling), instead of one shared-memory load per multiply.
+template <int C, int K>
+struct PostTaps { float w[K * C]; float bias; };
+
 template <int C, int K, int TB>
 __global__ void __launch_bounds__(TB)
-conv_post_tanh_tiled_kernel(const __half* __restrict__ x, long long slot_stride, int row0, int L, const float* __restrict__ w,
-                            const float* __restrict__ bias, float* __restrict__ wav, const int* slot_ids) {
+conv_post_tanh_tiled_kernel(const __half* __restrict__ x, long long slot_stride, int row0, int L, const __grid_constant__ PostTaps<C, K> taps,
+                            float* __restrict__ wav, const int* slot_ids) {
   constexpr int ROWH = C + 8;                    // padded row, in halfs
   constexpr int V = C / 8;                       // 16-byte vectors per row
   __shared__ __align__(16) __half sx[(TB + K - 1) * ROWH];
-  __shared__ float sw[K * C];
   const int tiles = L / TB;
   const int i = blockIdx.x / tiles, t0 = (blockIdx.x - i * tiles) * TB;
   const __half* xp = x + (long long)slot_of(slot_ids, i) * slot_stride + (long long)(row0 + t0) * C;
-  for (int q = threadIdx.x; q < K * C; q += TB) sw[q] = w[q];
   for (int q = threadIdx.x; q < (TB + K - 1) * V; q += TB) {
     const int r = q / V, v = q - r * V;
     *reinterpret_cast<uint4*>(&sx[r * ROWH + v * 8]) = *(reinterpret_cast<const uint4*>(xp + (long long)r * C) + v);
   }
   __syncthreads();
-  float acc = bias[0];
+  float acc = taps.bias;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
 #pragma unroll
@@ -279,8 +284,8 @@ conv_post_tanh_tiled_kernel(const __half* __restrict__ x, long long slot_stride,
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 f = __half22float2(h[q]);
-        acc = fmaf(f.x, sw[j * C + v * 8 + 2 * q], acc);
-        acc = fmaf(f.y, sw[j * C + v * 8 + 2 * q + 1], acc);
+        acc = fmaf(f.x, taps.w[j * C + v * 8 + 2 * q], acc);
+        acc = fmaf(f.y, taps.w[j * C + v * 8 + 2 * q + 1], acc);
       }
     }
   }
@@ -541,13 +546,16 @@ int launch_pitch(const float* h, const float* ln_g, const float* ln_b, const flo
 }
 
 int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, int row_stride, int row0, int L, int C, int k,
-                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st) {
+                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st, const float* taps_host) {
   if (n <= 0) return 0;
   unsigned grid = grid_for((long long)n * L, 256, 148u * 32u);
   size_t sh = (size_t)k * C * sizeof(float);
-  if (x_is_half && C == 32 && k == 7 && row_stride == C && L % 256 == 0 && slot_stride % 8 == 0 && ((uintptr_t)x) % 16 == 0) {
-    conv_post_tanh_tiled_kernel<32, 7, 256><<<(unsigned)(n * (L / 256)), 256, 0, st>>>((const __half*)x, slot_stride, row0, L, w, bias,
-                                                                                      wav_out, slot_ids);
+  if (taps_host && x_is_half && C == 32 && k == 7 && row_stride == C && L % 256 == 0 && slot_stride % 8 == 0 && ((uintptr_t)x) % 16 == 0) {
+    PostTaps<32, 7> taps;
+    memcpy(taps.w, taps_host, sizeof(taps.w));
+    taps.bias = taps_host[7 * 32];
+    conv_post_tanh_tiled_kernel<32, 7, 256><<<(unsigned)(n * (L / 256)), 256, 0, st>>>((const __half*)x, slot_stride, row0, L, taps, wav_out,
+                                                                                      slot_ids);
     CONAN_CHECK_LAUNCH();
     return 0;
   }

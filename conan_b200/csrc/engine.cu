@@ -63,6 +63,7 @@ struct conan_engine {
   int ring_rows = 0;
   float *eX = nullptr, *eQKV = nullptr, *eR1 = nullptr, *eR2 = nullptr, *eLOG = nullptr;
   Ctx eXN, eATT, eFN, eHF;   // GEMM operands (fp32 or split fp16)
+  std::vector<float> postTapsHost;                 // host copy of conv_post's taps + bias (kernel-parameter fast path)
   bool ffnFused = false; float* eFFP = nullptr;    // fused FFN: partial outputs [split][rows][DP]
   std::vector<float*> eRing;
   int* ePast = nullptr;
@@ -809,7 +810,8 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
   }
   const int Lw = e->vL[c.voc_n_ups];
   TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
-                            e->F("voc.post.w"), e->F("voc.post.b"), wav_out, n, nullptr, st));
+                            e->F("voc.post.w"), e->F("voc.post.b"), wav_out, n, nullptr, st,
+                            e->postTapsHost.empty() ? nullptr : e->postTapsHost.data()));
   TRY(launch_hist_scatter(e->histVoc, e->nHistVoc, n, ids, st));
   return 0;
 }
@@ -996,6 +998,12 @@ int conan_engine_finalize(conan_engine_t* e) {
     if (!w.ptr) { set_error("weight '" + w.name + "' was never bound"); return 1; }
   CONAN_CUDA_OK(cudaSetDevice(e->cfg.device));
   if (allocate_state(e)) return 1;
+  {
+    const size_t nt = (size_t)7 * e->vC[e->cfg.voc_n_ups];
+    e->postTapsHost.resize(nt + 1);
+    CONAN_CUDA_OK(cudaMemcpy(e->postTapsHost.data(), e->F("voc.post.w"), nt * sizeof(float), cudaMemcpyDeviceToHost));
+    CONAN_CUDA_OK(cudaMemcpy(e->postTapsHost.data() + nt, e->F("voc.post.b"), sizeof(float), cudaMemcpyDeviceToHost));
+  }
   CONAN_CUDA_OK(cudaDeviceSynchronize());
   e->finalized = true;
   return 0;

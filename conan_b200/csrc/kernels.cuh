@@ -88,8 +88,10 @@ int launch_pitch(const float* h, const float* ln_g, const float* ln_b, const flo
 int launch_rows_to_view(const float* src_slot, RowView out, int n, const int* slot_ids, int rows, int C, cudaStream_t st);
 
 // vocoder ------------------------------------------------------------------------------------
+// taps_host: optional HOST copy of [k*C weights | bias] (enables the fast path whose taps travel as a kernel parameter)
 int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, int row_stride, int row0, int L, int C, int k,
-                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st);
+                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st,
+                          const float* taps_host = nullptr);
 
 // fused HiFi-GAN residual block on tcgen05 (resblock_fused.cu) -------------------------------------------------
 struct ResblockFusedParams {
