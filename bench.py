@@ -10,8 +10,9 @@ scaling, streams are independent, there is no collective on the data path).
 
   value  = (stream-chunks processed per second, all ranks) x 0.08 s
          = concurrent real-time streams the job sustains with inputs already resident in HBM
-  e2e    = the same through the plugin call conan_step_host: slot ids + mel chunks copied from
-           pinned host memory and wav copied back, every step, inside the timed region
+  e2e    = the same through the plugin calls conan_step_host_submit / _wait (two steps in flight): slot ids +
+           mel chunks copied from pinned host memory and wav copied back, every step, inside the timed region;
+           the synchronous conan_step_host figure is reported next to it
   roofline: the tcgen05 implicit-GEMM conv kernels of the vocoder (96 % of the path's FLOPs),
            algorithmic FLOPs / CUDA-event time of those launches, vs the measured dense
            16-bit tensor peak in MEASURED_PEAKS.json
@@ -312,7 +313,7 @@ def run_b200(args):
         line = {
             "metric": "concurrent real-time 80 ms-chunk streams", "value": value, "unit": "streams", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (Emformer/Conan) + f16 operands / f32 accumulate (vocoder)"
+            "vs_baseline": None, "dtype": "split-f16 operands, f32 accumulate = f32-grade (Emformer/Conan) + f16 operands / f32 accumulate (vocoder)"
             if args.voc_precision == "fp16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(S=S), "streams_per_gpu": S, "chunk_ms": 80, "ref_frames": 150,
                        "weights": "synthetic seeded (conan_b200.synth, reference state_dict layout)",

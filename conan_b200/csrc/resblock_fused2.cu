@@ -390,6 +390,11 @@ int launch_fused2_k(const CUtensorMap& tmA, const CUtensorMap& tmW, const Fused2
 
 }  // namespace
 
+int r2_stages32() {
+  static int v = [] { const char* e = getenv("CONAN_FUSED2_STAGES32"); int x = e ? atoi(e) : 3; return x < 2 ? 2 : (x > 4 ? 4 : x); }();   // 3: k = 11 launch 366 -> 338 us, others unchanged; still two CTAs per SM
+  return v;
+}
+
 // shared-memory bytes the two-lane kernel needs, or 0 if the shape does not fit
 size_t resblock_fused2_smem(int C, int k, const int* dil) {
   const int ROWB = C * 2, TAPB = C * ROWB;
@@ -401,7 +406,7 @@ size_t resblock_fused2_smem(int C, int k, const int* dil) {
   }
   const int bufb = align1k2((TILE_M + hmax) * ROWB);
   const int lane = 3 * bufb + align1k2(hsum * ROWB);
-  const int stages = C == 64 ? 3 : 2, group = C == 64 ? 2 : 4;
+  const int stages = C == 64 ? 3 : r2_stages32(), group = C == 64 ? 2 : 4;
   const size_t total = (size_t)2 * lane + (size_t)stages * group * TAPB + 512 + R2_CONVS * C * 4 + 1024;
   return total <= 227 * 1024 ? total : 0;
 }
@@ -431,7 +436,7 @@ int launch_resblock_fused2(const ResblockFusedParams& p, cudaStream_t st) {
   a.hs_off = 3 * a.bufb;
   a.lane_bytes = 3 * a.bufb + align1k2(hrow * ROWB);
   a.group = C == 64 ? 2 : 4;
-  a.stages = C == 64 ? 3 : 2;
+  a.stages = C == 64 ? 3 : r2_stages32();
   int off = 2 * a.lane_bytes;
   a.wt_off = off; off += a.stages * a.group * TAPB;
   a.bar_off = off; off += 512;
