@@ -73,6 +73,62 @@ def load_wav(path: str, sample_rate: int) -> np.ndarray:
     return data
 
 
+def integrated_loudness(wav: np.ndarray, rate: int) -> float:
+    """ITU-R BS.1770-4 integrated loudness (LUFS) of a mono signal, as `pyloudnorm.Meter(rate).integrated_loudness`
+    computes it (K-weighting = high-shelf 1500 Hz +4 dB, Q 1/sqrt(2), then high-pass 38 Hz, Q 0.5, both as RBJ biquads;
+    400 ms blocks with 75 % overlap; absolute gate -70 LUFS, relative gate -10 LU).  pyloudnorm is not in the image:
+    restated from the published algorithm, parity against the package itself unpinned."""
+    from scipy.signal import lfilter
+    x = np.asarray(wav, dtype=np.float64)
+
+    def biquad(kind, G, Q, fc):
+        A = 10 ** (G / 40.0)
+        w0 = 2.0 * np.pi * (fc / rate)
+        alpha = np.sin(w0) / (2.0 * Q)
+        c = np.cos(w0)
+        if kind == "high_shelf":
+            b = np.array([A * ((A + 1) + (A - 1) * c + 2 * np.sqrt(A) * alpha), -2 * A * ((A - 1) + (A + 1) * c),
+                          A * ((A + 1) + (A - 1) * c - 2 * np.sqrt(A) * alpha)])
+            a = np.array([(A + 1) - (A - 1) * c + 2 * np.sqrt(A) * alpha, 2 * ((A - 1) - (A + 1) * c),
+                          (A + 1) - (A - 1) * c - 2 * np.sqrt(A) * alpha])
+        else:
+            b = np.array([(1 + c) / 2, -(1 + c), (1 + c) / 2])
+            a = np.array([1 + alpha, -2 * c, 1 - alpha])
+        return b / a[0], a / a[0]
+
+    for kind, G, Q, fc in (("high_shelf", 4.0, 1 / np.sqrt(2), 1500.0), ("high_pass", 0.0, 0.5, 38.0)):
+        b, a = biquad(kind, G, Q, fc)
+        x = lfilter(b, a, x)
+    T_g, overlap = 0.400, 0.75
+    step = 1.0 - overlap
+    T = x.shape[0] / rate
+    n_blocks = int(np.round((T - T_g) / (T_g * step)) + 1)
+    if n_blocks < 1:
+        raise ValueError("audio must be longer than the 400 ms gating block")
+    z = np.empty(n_blocks)
+    for j in range(n_blocks):
+        lo, hi = int(T_g * (j * step) * rate), int(T_g * (j * step + 1) * rate)
+        z[j] = np.sum(np.square(x[lo:hi])) / (T_g * rate)
+    with np.errstate(divide="ignore"):
+        l = -0.691 + 10.0 * np.log10(z)
+    keep = l >= -70.0
+    if not keep.any():
+        return -np.inf
+    gamma_r = -0.691 + 10.0 * np.log10(np.mean(z[keep])) - 10.0
+    keep = (l > gamma_r) & (l > -70.0)
+    if not keep.any():
+        return -np.inf
+    return float(-0.691 + 10.0 * np.log10(np.mean(z[keep])))
+
+
+def loudness_normalize(wav: np.ndarray, rate: int, target_lufs: float = -22.0) -> np.ndarray:
+    """`loud_norm=True` branch of librosa_wav2spec (utils/audio/__init__.py:57-62): normalise to -22 LUFS, then peak-limit."""
+    loud = integrated_loudness(wav, rate)
+    out = np.asarray(wav, dtype=np.float32) * np.float32(10.0 ** ((target_lufs - loud) / 20.0))
+    peak = np.abs(out).max()
+    return out / peak if peak > 1 else out
+
+
 def save_wav(wav: np.ndarray, path: str, sr: int, norm: bool = False):
     from scipy.io import wavfile
     if norm:

@@ -16,8 +16,10 @@ OUT = os.path.join(HERE, "libconan_b200.so")
 STAMP = OUT + ".stamp"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # precise math only: no --use_fast_math anywhere on this path (erf GELU, tanh, exp must match torch)
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-shared"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",
+         "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map")]
 
 
 def _digest() -> str:
@@ -28,7 +30,8 @@ def _digest() -> str:
         h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(open(os.path.join(CSRC, "exports.map"), "rb").read())
+    h.update(" ".join(f for f in FLAGS if "version-script" not in f).encode())
     return h.hexdigest()
 
 

@@ -53,23 +53,44 @@ def load_state_dict(ckpt_base_dir: str, model_name: str = "model", force: bool =
     return {k: v.detach().float().contiguous() for k, v in state_dict.items()}
 
 
-def filter_to_spec(state_dict: Dict[str, torch.Tensor], spec, strict: bool):
-    """strict=False semantics of the reference: shape-mismatched keys are dropped with a
-    message; here a dropped or missing key that the hot path needs is an error, because
-    there is no randomly initialised nn.Module to fall back on."""
-    out = {}
-    for key, shape, _ in spec:
+def filter_to_spec(state_dict: Dict[str, torch.Tensor], spec, strict: bool, defaults: Optional[Dict[str, torch.Tensor]] = None):
+    """The `cur_model.load_state_dict(state_dict, strict=strict)` step of the reference's load_ckpt
+    (utils/commons/ckpt_utils.py:48-58), with `spec` = [(key, shape, ...)] standing in for `cur_model.state_dict()`.
+
+    strict=True : a missing, unexpected or shape-mismatched key raises RuntimeError, as nn.Module.load_state_dict does.
+    strict=False: a shape-mismatched key is DROPPED with the reference's own message (`| Unmatched keys: ...`), unexpected
+                  keys are ignored, and a dropped / missing key keeps the module's initial value -- here `defaults[key]`
+                  (the reference's nn.Module would keep its constructor init; this build has no nn.Module, so the caller
+                  supplies the initial tensors, see streaming.build_engine).  Without `defaults` such a key is an error:
+                  the engine cannot run on an unbound weight."""
+    out, missing, mismatched = {}, [], []
+    for key, shape, *_ in spec:
         if key not in state_dict:
-            raise KeyError(f"checkpoint is missing '{key}'")
+            missing.append(key)
+            continue
         t = state_dict[key]
         if tuple(t.shape) != tuple(shape):
-            print("| Unmatched keys: ", key, tuple(shape), tuple(t.shape))
-            raise ValueError(f"shape mismatch for '{key}': expected {tuple(shape)}, got {tuple(t.shape)}")
+            mismatched.append((key, tuple(shape), tuple(t.shape)))
+            continue
         out[key] = t
     if strict:
-        extra = set(state_dict) - set(out)
-        if extra:
-            raise KeyError(f"unexpected keys in checkpoint: {sorted(extra)[:5]} ...")
+        extra = sorted(set(state_dict) - {k for k, *_ in spec})
+        if missing or extra or mismatched:
+            raise RuntimeError("Error(s) in loading state_dict: "
+                               + (f"Missing key(s): {missing[:5]}... " if missing else "")
+                               + (f"Unexpected key(s): {extra[:5]}... " if extra else "")
+                               + "".join(f"size mismatch for {k}: checkpoint {got}, model {want}. " for k, want, got in mismatched[:5]))
+        return out
+    for k, want, got in mismatched:
+        print("| Unmatched keys: ", k, want, got)          # ckpt_utils.py:55
+    holes = missing + [k for k, _, _ in mismatched]
+    if holes:
+        if defaults is None:
+            raise KeyError(f"checkpoint leaves {len(holes)} tensors of the hot path without a value (e.g. '{holes[0]}') and no "
+                           "initial values were given (strict=False keeps the module's init in the reference)")
+        for k in holes:
+            out[k] = defaults[k]
+        print(f"| {len(holes)} keys left at their initial value (strict=False): {holes[:5]}{' ...' if len(holes) > 5 else ''}")
     return out
 
 

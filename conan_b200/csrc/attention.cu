@@ -340,12 +340,14 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
   if (ring_rows < lc + seg) { set_error("emformer_attention: ring too short"); return 1; }
   if (ep && (size_t)D * D + (size_t)(seg + rc) * D > (size_t)2 * (rc + lc + seg) * (D + 1)) { set_error("emformer_attention: fused tail does not fit in the K/V staging area"); return 1; }
   size_t sh = ((size_t)2 * (rc + lc + seg) * (D + 1) + (size_t)(seg + rc) * D) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }
   emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv,
                                                 ep ? *ep : EmfAttnEpilogue{}, ep ? 1 : 0);
@@ -360,24 +362,28 @@ int launch_cross_attention(const float* q, const float* kv_cache, const float* k
   if (rows > XA_MAX_ROWS || hd % 4 != 0) { set_error("cross_attention: rows above 8 or head_dim not a multiple of 4"); return 1; }
   const size_t sh_staged = ((size_t)2 * tp_max * (hd + 4) + (size_t)rows * hd + (size_t)rows * tp_max) * sizeof(float);
   if (sh_staged <= 100 * 1024 && H % 4 == 0) {
-    static size_t attr_s = 0;
-    if (sh_staged > attr_s) {
-      cudaFuncSetAttribute(cross_attention_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_staged);
-      cudaFuncSetAttribute(cross_attention_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_s = sh_staged;
-    }
+    static DeviceOnce once;
+    if (device_once(once, nullptr, [&](int*) {
+          cudaError_t e = cudaFuncSetAttribute(cross_attention_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(cross_attention_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+          return 0;
+        }))
+      return 1;
     cross_attention_staged_kernel<<<n * heads, XS_THREADS, sh_staged, st>>>(q, kv_cache, kpm, n_keys, out, slot_ids, rows, H, heads, layer,
                                                                             n_layers, tp_max);
     CONAN_CHECK_LAUNCH();
     return 0;
   }
   size_t sh = (size_t)XA_WARPS * (XA_MAX_ROWS * hd + XA_MAX_ROWS * tp_max) * sizeof(float);
-  static size_t attr = 0;
-  if (sh > attr) {
-    if (sh > 200 * 1024) { set_error("cross_attention: too many keys for the score buffer"); return 1; }
-    cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    attr = sh;
-  }
+  if (sh > 200 * 1024) { set_error("cross_attention: too many keys for the score buffer"); return 1; }
+  static DeviceOnce once_general;
+  if (device_once(once_general, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
   const int pairs = n * heads;
   cross_attention_kernel<<<(pairs + XA_WARPS - 1) / XA_WARPS, XA_WARPS * 32, sh, st>>>(q, kv_cache, kpm, n_keys, out, slot_ids, n, rows, H,
                                                                                        heads, layer, n_layers, tp_max);

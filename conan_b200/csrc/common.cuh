@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/conan_b200.h"
@@ -53,6 +54,30 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Per-device one-time setup.  cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in, the carve-out preference) and the
+// occupancy figures derived from it apply to the CURRENT device only, so launchers cache them per device ordinal, under a mutex
+// (two host threads may drive engines on different GPUs of one process).  `setup(int* value)` returns 0 on success.
+struct DeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  int value[kMaxDevices] = {};
+};
+template <typename F>
+inline int device_once(DeviceOnce& o, int* value, F&& setup) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DeviceOnce::kMaxDevices) { set_error("device_once: bad current device"); return 1; }
+  std::lock_guard<std::mutex> lk(o.mu);
+  if (!o.done[dev]) {
+    int v = 0;
+    if (setup(&v)) return 1;
+    o.value[dev] = v;
+    o.done[dev] = true;
+  }
+  if (value) *value = o.value[dev];
+  return 0;
 }
 
 // launchers implemented in the .cu files

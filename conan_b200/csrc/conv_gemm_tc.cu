@@ -690,7 +690,13 @@ int resident_ctas(const void* func, int threads, size_t dyn_smem, int tmem_cols)
 }
 
 int num_sms() {
-  static int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+  static DeviceOnce once;
+  int n = 148;
+  device_once(once, &n, [](int* v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return cudaDeviceGetAttribute(v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess ? 0 : 1;
+  });
   return n;
 }
 
@@ -730,15 +736,16 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, lon
   using SL = SmemLayout<BN, BK, STAGES, MT>;
   auto kern = conv_gemm_tc_kernel<BN, BK, STAGES, MT, ES, LEAN>;
   constexpr int threads = 64 + 128 * MT * ES;
-  static bool attr_set = false;
-  static int per_sm = 1;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-    per_sm = resident_ctas((const void*)kern, threads, SL::TOTAL, 2 * MT * BN);
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  int per_sm = 1;
+  if (device_once(once, &per_sm, [&](int* v) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        *v = resident_ctas((const void*)kern, threads, SL::TOTAL, 2 * MT * BN);
+        return 0;
+      }))
+    return 1;
   a.m_tiles = (int)m_tiles;
   a.num_tiles = (int)(((m_tiles + MT - 1) / MT) * a.n_tiles);
   const int grid = std::min(a.num_tiles, num_sms() * per_sm);           // persistent: exactly the co-resident CTAs
@@ -781,13 +788,14 @@ bool window_eligible(const conan_conv_params_t& p) {
 template <int C, int BN, int NEPI>
 int launch_window_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const WinArgs& a, size_t smem, cudaStream_t st) {
   auto kern = conv_window_tc_kernel<C, BN, WIN_NBUF, NEPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
   const int per_sm = resident_ctas((const void*)kern, 64 + 128 * NEPI, smem, 2 * BN);
   const int grid = std::min(a.num_tiles, num_sms() * per_sm);
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "window<%d,%d,%d> k %d tiles %d smem %zu per_sm %d grid %d\n", C, BN, NEPI, a.k, a.num_tiles, smem, per_sm, grid);

@@ -218,7 +218,8 @@ __global__ void pitch_kernel(const float* __restrict__ h, const float* __restric
 template <typename T>
 __global__ void conv_post_tanh_kernel(const T* __restrict__ x, long long slot_stride, int row_stride, int row0, int L, int C,
                                       int k, const float* __restrict__ w, const float* __restrict__ bias,
-                                      float* __restrict__ wav, int n, const int* slot_ids) {
+                                      float* __restrict__ wav, int n, const int* slot_ids, long long lo_off) {
+  // lo_off != 0 (T = __half): x is a split fp16 pair, value = x[..] + x[.. + lo_off]
   extern __shared__ float ws[];                // [k*C]
   for (int q = threadIdx.x; q < k * C; q += blockDim.x) ws[q] = w[q];
   __syncthreads();
@@ -235,9 +236,14 @@ __global__ void conv_post_tanh_kernel(const T* __restrict__ x, long long slot_st
         uint4 u = r[v];
         if (sizeof(T) == 2) {
           const __half2* h = reinterpret_cast<const __half2*>(&u);
+          uint4 ul = make_uint4(0, 0, 0, 0);
+          if (lo_off) ul = *(reinterpret_cast<const uint4*>(xp + lo_off + (long long)j * row_stride) + v);
+          const __half2* hl = reinterpret_cast<const __half2*>(&ul);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float2 f = __half22float2(h[q]);
+            const float2 g = __half22float2(hl[q]);
+            f.x += g.x; f.y += g.y;
             acc = fmaf(f.x, wj[v * 8 + 2 * q], acc);
             acc = fmaf(f.y, wj[v * 8 + 2 * q + 1], acc);
           }
@@ -440,11 +446,12 @@ __global__ void kpm_kernel(const float* __restrict__ pe, float* __restrict__ kpm
 }
 
 __global__ void masked_time_mean_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ style,
-                                        const int* __restrict__ slots, int T, int C) {
+                                        const int* __restrict__ slots, int T, int TS, int C) {
+  // TS: rows per session in x / mask (>= T)
   int i = blockIdx.x; int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f, cnt = 0.f;
-  for (int t = 0; t < T; ++t) { float m = mask[(long long)i * T + t]; s += x[((long long)i * T + t) * C + c] * m; cnt += m; }
+  for (int t = 0; t < T; ++t) { float m = mask[(long long)i * TS + t]; s += x[((long long)i * TS + t) * C + c] * m; cnt += m; }
   style[(long long)slots[i] * C + c] = s / cnt;
 }
 
@@ -546,11 +553,12 @@ int launch_pitch(const float* h, const float* ln_g, const float* ln_b, const flo
 }
 
 int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, int row_stride, int row0, int L, int C, int k,
-                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st, const float* taps_host) {
+                          const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st, const float* taps_host,
+                          long long lo_off) {
   if (n <= 0) return 0;
   unsigned grid = grid_for((long long)n * L, 256, 148u * 32u);
   size_t sh = (size_t)k * C * sizeof(float);
-  if (taps_host && x_is_half && C == 32 && k == 7 && row_stride == C && L % 256 == 0 && slot_stride % 8 == 0 && ((uintptr_t)x) % 16 == 0) {
+  if (taps_host && x_is_half && !lo_off && C == 32 && k == 7 && row_stride == C && L % 256 == 0 && slot_stride % 8 == 0 && ((uintptr_t)x) % 16 == 0) {
     PostTaps<32, 7> taps;
     memcpy(taps.w, taps_host, sizeof(taps.w));
     taps.bias = taps_host[7 * 32];
@@ -560,9 +568,9 @@ int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, i
     return 0;
   }
   if (x_is_half)
-    conv_post_tanh_kernel<__half><<<grid, 256, sh, st>>>((const __half*)x, slot_stride, row_stride, row0, L, C, k, w, bias, wav_out, n, slot_ids);
+    conv_post_tanh_kernel<__half><<<grid, 256, sh, st>>>((const __half*)x, slot_stride, row_stride, row0, L, C, k, w, bias, wav_out, n, slot_ids, lo_off);
   else
-    conv_post_tanh_kernel<float><<<grid, 256, sh, st>>>((const float*)x, slot_stride, row_stride, row0, L, C, k, w, bias, wav_out, n, slot_ids);
+    conv_post_tanh_kernel<float><<<grid, 256, sh, st>>>((const float*)x, slot_stride, row_stride, row0, L, C, k, w, bias, wav_out, n, slot_ids, 0);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -641,9 +649,9 @@ int launch_kpm(const float* pe, float* kpm, int* n_keys, const int* slots_dev, i
   return 0;
 }
 
-int launch_masked_time_mean(const float* x, const float* mask, float* style, const int* slots_dev, int n, int T, int C, cudaStream_t st) {
+int launch_masked_time_mean(const float* x, const float* mask, float* style, const int* slots_dev, int n, int T, int TS, int C, cudaStream_t st) {
   if (n <= 0) return 0;
-  masked_time_mean_kernel<<<dim3(n, (C + 127) / 128), 128, 0, st>>>(x, mask, style, slots_dev, T, C);
+  masked_time_mean_kernel<<<dim3(n, (C + 127) / 128), 128, 0, st>>>(x, mask, style, slots_dev, T, TS, C);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

@@ -58,6 +58,7 @@ struct conan_engine {
   size_t state_bytes = 0;
   int S = 0, tp_max = 0;
   bool lin_tc = false;       // Emformer / Conan contractions on tcgen05 with split-fp16 operands
+  bool ses_tc = false;       // session setup: the style encoder's ConvBlocks (95 % of the setup FLOPs) on tcgen05, split-fp16 operands
   int DP = 0, QP = 0, LP = 0;   // (padded) Emformer model dim, QKV width, logits width
   // ---- Emformer
   int ring_rows = 0;
@@ -93,6 +94,8 @@ struct conan_engine {
   ZeroDesc* zeroVoc = nullptr; int nZeroVoc = 0;
   // ---- session scratch (compact index)
   int SB = 0;
+  __half *qC31h = nullptr, *qHGh = nullptr, *qC3Gh = nullptr;   // split-fp16 operands of the style encoder's tensor-core path
+  float* qMAp = nullptr;                                          // the reference-frame mask with the padded row stride of that path
   float *qMA = nullptr, *qMF = nullptr, *qXG = nullptr, *qC31 = nullptr, *qHG = nullptr, *qC3G = nullptr, *qPG = nullptr,
         *qXW = nullptr, *qCW = nullptr, *qAW = nullptr, *qACT = nullptr, *qRS = nullptr, *qSKIP = nullptr, *qGRP = nullptr,
         *qMP = nullptr, *qMPB = nullptr, *qXP = nullptr, *qC5 = nullptr, *qHP = nullptr, *qC3P = nullptr, *qPZ = nullptr,
@@ -109,6 +112,7 @@ struct conan_engine {
   float* hWav2 = nullptr; float* hMel2 = nullptr; int* hTok2 = nullptr;
   cudaStream_t copyStream = nullptr; cudaEvent_t evCompute[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
   unsigned long long submitCount = 0; bool ticketPending[2] = {false, false};
+  std::vector<uint8_t> idSeen;     // host-side duplicate check of a ready list
 
   const WeightSlot* W(const std::string& name) const {
     auto it = windex.find(name);
@@ -129,8 +133,8 @@ inline int pad32(int x) { return (x + 31) / 32 * 32; }
 
 // A contraction that runs on the tensor cores when lin_tc is on: fp16 [Npad, 3*k*Kpad] = [W_hi | W_lo | W_hi]
 // (pre-scaled by 2^10) + fp32 bias [Npad]; otherwise fp32 [N, k*K] + bias [N].
-void need_linear(conan_engine* e, const std::string& name, int N, int K, int k = 1) {
-  if (e->lin_tc) {
+void need_linear(conan_engine* e, const std::string& name, int N, int K, int k = 1, int force_tc = -1) {
+  if (force_tc < 0 ? e->lin_tc : force_tc != 0) {
     need(e, name + ".w", (size_t)pad32(N) * 3 * k * pad32(K), CONAN_DTYPE_F16);
     need(e, name + ".b", pad32(N));
   } else {
@@ -187,15 +191,15 @@ void declare_weights(conan_engine* e) {
     for (int s = 0; s < 2; ++s) {
       std::string p = "conan.genc." + std::to_string(b) + "." + std::to_string(s) + ".";
       need(e, p + "ln.g", H); need(e, p + "ln.b", H);
-      need(e, p + "conv.w", (size_t)2 * H * 31 * H); need(e, p + "conv.b", 2 * H);
-      need(e, p + "pw.w", (size_t)H * 2 * H); need(e, p + "pw.b", H);
+      need_linear(e, p + "conv", 2 * H, H, 31, e->ses_tc);
+      need_linear(e, p + "pw", H, 2 * H, 1, e->ses_tc);
       std::string q = "conan.penc." + std::to_string(b) + "." + std::to_string(s) + ".";
       need(e, q + "ln.g", 80); need(e, q + "ln.b", 80);
       need(e, q + "conv.w", (size_t)160 * 5 * 80); need(e, q + "conv.b", 160);
       need(e, q + "pw.w", (size_t)80 * 160); need(e, q + "pw.b", 80);
     }
   need(e, "conan.genc.last_norm.g", H); need(e, "conan.genc.last_norm.b", H);
-  need(e, "conan.genc.post.w", (size_t)H * 3 * H); need(e, "conan.genc.post.b", H);
+  need_linear(e, "conan.genc.post", H, H, 3, e->ses_tc);
   need(e, "conan.penc.last_norm.g", 80); need(e, "conan.penc.last_norm.b", 80);
   need(e, "conan.penc.post.w", (size_t)H * 3 * 80); need(e, "conan.penc.post.b", H);
   for (int i = 0; i < 4; ++i) {
@@ -209,18 +213,19 @@ void declare_weights(conan_engine* e) {
   need(e, "conan.l1.w", (size_t)H * 2 * H); need(e, "conan.l1.b", H);
   // vocoder
   const int wdt = c.voc_precision ? CONAN_DTYPE_F16 : CONAN_DTYPE_F32;
+  const size_t vsp = c.voc_precision == 2 ? 3 : 1;      // split fp16: [W_hi | W_lo | W_hi] of 2^10 W (fp32-grade on tensor cores)
   int ch = c.voc_initial_channel;
-  need(e, "voc.pre.w", (size_t)ch * 7 * (c.voc_use_tensor_cores ? pad32(c.n_mels) : c.n_mels), wdt); need(e, "voc.pre.b", ch);
+  need(e, "voc.pre.w", vsp * ch * 7 * (c.voc_use_tensor_cores ? pad32(c.n_mels) : c.n_mels), wdt); need(e, "voc.pre.b", ch);
   for (int i = 0; i < c.voc_n_ups; ++i) {
     int co = ch / 2;
     std::string p = "voc.up." + std::to_string(i) + ".";
-    need(e, p + "w", (size_t)co * c.voc_rates[i] * c.voc_up_kernels[i] * ch, wdt); need(e, p + "b", (size_t)co * c.voc_rates[i]);
+    need(e, p + "w", vsp * co * c.voc_rates[i] * c.voc_up_kernels[i] * ch, wdt); need(e, p + "b", (size_t)co * c.voc_rates[i]);
     for (int r = 0; r < c.voc_n_res; ++r)
       for (int j = 0; j < c.voc_n_dil; ++j) {
         std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
-        need(e, q + "c1." + std::to_string(j) + ".w", (size_t)co * c.voc_res_kernels[r] * co, wdt);
+        need(e, q + "c1." + std::to_string(j) + ".w", vsp * co * c.voc_res_kernels[r] * co, wdt);
         need(e, q + "c1." + std::to_string(j) + ".b", co);
-        need(e, q + "c2." + std::to_string(j) + ".w", (size_t)co * c.voc_res_kernels[r] * co, wdt);
+        need(e, q + "c2." + std::to_string(j) + ".w", vsp * co * c.voc_res_kernels[r] * co, wdt);
         need(e, q + "c2." + std::to_string(j) + ".b", co);
       }
     ch = co;
@@ -431,7 +436,7 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->sKV, (size_t)S * 2 * e->tp_max * 2 * H));
   TRY(dalloc(e, &e->sKPM, (size_t)S * e->tp_max)); TRY(dalloc(e, &e->sNKEYS, (size_t)S));
   // ---- vocoder
-  const int hf = c.voc_precision ? 1 : 0;
+  const int hf = c.voc_precision;       // context element type: 0 fp32, 1 fp16, 2 split fp16 pair
   e->vL[0] = seg; e->vC[0] = c.voc_initial_channel;
   for (int i = 0; i < c.voc_n_ups; ++i) { e->vL[i + 1] = e->vL[i] * c.voc_rates[i]; e->vC[i + 1] = e->vC[i] / 2; }
   // tensor-core mode: mel rows padded to a multiple of 32 channels (pad columns stay zero) so conv_pre is tcgen05-eligible
@@ -444,7 +449,7 @@ int allocate_state(conan_engine* e) {
     int hmax = 0;
     for (int r = 0; r < c.voc_n_res; ++r) hmax = std::max(hmax, (c.voc_res_kernels[r] - 1) * c.voc_res_dilations[0]);
     TRY(alloc_ctx(e, &e->vXA[i], hmax, L, 0, C, hf));
-    e->vFused[i] = c.voc_fuse_resblocks && c.voc_use_tensor_cores && c.voc_residual_from_ctx && hf && c.voc_n_dil == 3;
+    e->vFused[i] = c.voc_fuse_resblocks && c.voc_use_tensor_cores && c.voc_residual_from_ctx && hf == 1 && c.voc_n_dil == 3;
     for (int r = 0; r < c.voc_n_res && e->vFused[i]; ++r)
       e->vFused[i] = resblock_fused_eligible(C, L, c.voc_res_kernels[r], c.voc_res_dilations) && c.voc_res_dilations[0] == 1;
     maxLC = std::max(maxLC, (size_t)L * C);
@@ -533,8 +538,13 @@ int allocate_state(conan_engine* e) {
     TRY(build_tables(cs, {}, &e->histVoc, &e->nHistVoc, &e->zeroVoc, &e->nZeroVoc, fused_zero));
   }
   // ---- session scratch
-  e->SB = std::min(S, 32);
-  const int SB = e->SB, T = c.max_ref_frames, Tp = e->tp_max;
+  e->SB = std::min(S, 64);
+  // T: rows per session in the scratch buffers.  The tensor-core path pads every session to a multiple of 32 rows (tile geometry)
+  const int SB = e->SB, T = (c.max_ref_frames + 31) / 32 * 32, Tp = e->tp_max;
+  if (e->ses_tc) {
+    TRY(dalloc(e, &e->qC31h, (size_t)2 * SB * (T + 30) * H)); TRY(dalloc(e, &e->qHGh, (size_t)2 * SB * T * 2 * H));
+    TRY(dalloc(e, &e->qC3Gh, (size_t)2 * SB * (T + 2) * H)); TRY(dalloc(e, &e->qMAp, (size_t)SB * T));
+  }
   TRY(dalloc(e, &e->qMA, (size_t)SB * T)); TRY(dalloc(e, &e->qMF, (size_t)SB * T)); TRY(dalloc(e, &e->qMGB, (size_t)SB * T));
   TRY(dalloc(e, &e->qXG, (size_t)SB * T * H)); TRY(dalloc(e, &e->qC31, (size_t)SB * (T + 30) * H));
   TRY(dalloc(e, &e->qHG, (size_t)SB * T * 2 * H)); TRY(dalloc(e, &e->qC3G, (size_t)SB * (T + 2) * H));
@@ -746,7 +756,8 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
       auto p = conv_on_ctx(e, e->vUP[i], c.voc_up_kernels[i], 1, e->P(u + "w"), e->F(u + "b"), r_up * C, n);
       if (!from_ctx) { p.y = e->vXS; p.y_slot_stride = (long long)L * C; p.y_row_stride = r_up * C; p.y_row0 = 0; }
       p.y2 = e->vXA[i].at_row(e->vXA[i].H); p.y2_slot_stride = e->vXA[i].slot_stride(); p.y2_row_stride = r_up * C; p.y2_row0 = 0;
-      p.y2_is_half = e->vXA[i].is_half; p.act2 = ACT_LRELU; p.slope2 = sl;
+      p.y2_is_half = e->vXA[i].is_half ? 1 : 0; p.act2 = ACT_LRELU; p.slope2 = sl;
+      if (e->vXA[i].is_half == 2) { p.y2_split = 1; p.y2_lo_off = e->vXA[i].plane; }
       TRY(run_conv(e, p, st, e->cfg.voc_use_tensor_cores != 0));
     }
     const bool last_scale = (i == c.voc_n_ups - 1);
@@ -789,7 +800,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
         if (j + 1 < c.voc_n_dil) {
           if (!from_ctx) { float* xn = e->vXR[j & 1]; out_rows(p2, xn, L, C); xj = xn; }
           out2_ctx(p2, e->vC1[i][r][j + 1], ACT_LRELU, sl);
-        } else if (from_ctx && e->vXA[i].is_half) {
+        } else if (from_ctx && e->vXA[i].is_half == 1) {
           // MRF average (hifigan_causal.py:324-329) with the running sum carried in fp16: resblock 0 writes it, 1 adds to it,
           // the last one only reads it and emits lrelu(sum / 3) into the next layer's context
           if (r > 0) { p2.res2 = e->vSUMh; p2.res2_slot_stride = (long long)L * C; p2.res2_row_stride = C; p2.res2_is_half = 1; }
@@ -809,9 +820,9 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
     }
   }
   const int Lw = e->vL[c.voc_n_ups];
-  TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
+  TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half ? 1 : 0, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
                             e->F("voc.post.w"), e->F("voc.post.b"), wav_out, n, nullptr, st,
-                            e->postTapsHost.empty() ? nullptr : e->postTapsHost.data()));
+                            e->postTapsHost.empty() ? nullptr : e->postTapsHost.data(), e->vPOST.is_half == 2 ? e->vPOST.plane : 0));
   TRY(launch_hist_scatter(e->histVoc, e->nHistVoc, n, ids, st));
   return 0;
 }
@@ -829,30 +840,43 @@ int vocoder_step(conan_engine* e, int n, const int* ids, const float* mel_ext, f
 }
 
 // ============================================================================ session setup
-// ConvBlocks.forward on compact [n, T, C] rows (modules/commons/conv.py:84-125 / prosody_util.py:299-336)
+// ConvBlocks.forward on compact [n, TS, C] rows of which the first T are real (modules/commons/conv.py:84-125 /
+// prosody_util.py:299-336).  TS > T only on the tensor-core path (tile geometry): the convs then run over TS rows per session,
+// the LayerNorms over T, so the context rows T.. stay zero (the reference's zero padding) and the rows T.. of X stay zero
+// through the block masks.  tc: operands are split-fp16 pairs in ctxk_h / Hbuf_h / ctx3_h (capacity 2 * SB sessions).
 int conv_blocks_noncausal(conan_engine* e, const std::string& pre, float* X, int C, int k, float* ctxk, float* Hbuf, float* ctx3,
-                          float* OUT, int outC, const float* nonpad, float* maskb, int n, int T, cudaStream_t st) {
-  const int pad = (k - 1) / 2;
-  Ctx ck; ck.p = ctxk; ck.H = pad; ck.L = T; ck.R = pad; ck.C = C; ck.is_half = 0;
-  Ctx c3; c3.p = ctx3; c3.H = 1; c3.L = T; c3.R = 1; c3.C = C; c3.is_half = 0;
-  CONAN_CUDA_OK(cudaMemsetAsync(ctxk, 0, (size_t)n * ck.rows() * C * 4, st));
-  CONAN_CUDA_OK(cudaMemsetAsync(ctx3, 0, (size_t)n * c3.rows() * C * 4, st));
+                          float* OUT, int outC, const float* nonpad, float* maskb, int n, int T, int TS, cudaStream_t st,
+                          bool tc = false, __half* ctxk_h = nullptr, __half* Hbuf_h = nullptr, __half* ctx3_h = nullptr) {
+  const int pad = (k - 1) / 2, SB = e->SB;
+  Ctx ck; ck.p = tc ? (void*)ctxk_h : (void*)ctxk; ck.H = pad; ck.L = TS; ck.R = pad; ck.C = C; ck.is_half = tc ? 2 : 0;
+  Ctx c3; c3.p = tc ? (void*)ctx3_h : (void*)ctx3; c3.H = 1; c3.L = TS; c3.R = 1; c3.C = C; c3.is_half = tc ? 2 : 0;
+  Ctx hb; hb.p = Hbuf_h; hb.H = 0; hb.L = TS; hb.R = 0; hb.C = 2 * C; hb.is_half = 2;
+  ck.plane = (long long)SB * ck.rows() * C; c3.plane = (long long)SB * c3.rows() * C; hb.plane = (long long)SB * hb.rows() * 2 * C;
+  auto fix = [&](conan_conv_params_t& p) {          // session scratch holds SB sessions (not max_slots); lo plane SB slots further
+    p.n_slots = tc ? SB : n;
+    if (p.x_split) p.x_lo_slot_off = SB;
+  };
+  CONAN_CUDA_OK(cudaMemsetAsync(ck.p, 0, (size_t)(tc ? 2 * SB : n) * ck.rows() * C * ck.elem(), st));
+  CONAN_CUDA_OK(cudaMemsetAsync(c3.p, 0, (size_t)(tc ? 2 * SB : n) * c3.rows() * C * c3.elem(), st));
+  if (TS != T) CONAN_CUDA_OK(cudaMemsetAsync(maskb, 0, (size_t)n * TS * 4, st));
   for (int b = 0; b < 5; ++b)
     for (int s = 0; s < 2; ++s) {
       std::string d = pre + "." + std::to_string(b) + "." + std::to_string(s) + ".";
-      TRY(ln_rows(X, T, C, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, st, nullptr, nullptr, T,
+      TRY(ln_rows(X, TS, C, 0, ck.new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), C, T, n, st, nullptr, nullptr, TS,
                   s == 0 ? maskb : nullptr, nullptr));
       auto p = conv_on_ctx(e, ck, k, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * C, n, false);
-      p.n_slots = n; out_rows(p, Hbuf, T, 2 * C); p.scale = 1.0f / sqrtf((float)k); p.act = ACT_GELU;
-      TRY(run_conv(e, p, st));
-      auto w = conv_on_rows(e, Hbuf, T, 0, T, 2 * C, e->P(d + "pw.w"), e->F(d + "pw.b"), C, n);
-      w.n_slots = n; out_rows(w, X, T, C); res_rows(w, X, T, C); w.rowmask = maskb; w.mask_slot_stride = T;
-      TRY(run_conv(e, w, st));
+      fix(p); p.scale = 1.0f / sqrtf((float)k); p.act = ACT_GELU;
+      if (tc) out2_ctx(p, hb, ACT_NONE, 0.f); else out_rows(p, Hbuf, TS, 2 * C);
+      TRY(run_conv(e, p, st, tc));
+      auto w = tc ? conv_on_ctx(e, hb, 1, 1, e->P(d + "pw.w"), e->F(d + "pw.b"), C, n)
+                  : conv_on_rows(e, Hbuf, TS, 0, TS, 2 * C, e->P(d + "pw.w"), e->F(d + "pw.b"), C, n);
+      fix(w); out_rows(w, X, TS, C); res_rows(w, X, TS, C); w.rowmask = maskb; w.mask_slot_stride = TS;
+      TRY(run_conv(e, w, st, tc));
     }
-  TRY(ln_rows(X, T, C, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, st, nonpad, nonpad, T));
+  TRY(ln_rows(X, TS, C, 0, c3.new_rows(), e->F(pre + ".last_norm.g"), e->F(pre + ".last_norm.b"), C, T, n, st, nonpad, nonpad, TS));
   auto p = conv_on_ctx(e, c3, 3, 1, e->P(pre + ".post.w"), e->F(pre + ".post.b"), outC, n, false);
-  p.n_slots = n; out_rows(p, OUT, T, outC); p.rowmask = nonpad; p.mask_slot_stride = T;
-  TRY(run_conv(e, p, st));
+  fix(p); out_rows(p, OUT, TS, outC); p.rowmask = nonpad; p.mask_slot_stride = TS;
+  TRY(run_conv(e, p, st, tc));
   return 0;
 }
 
@@ -864,11 +888,22 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
   TRY(launch_row_masks(ref, e->qMA, e->qMF, n, T, M, st));
   // ---- global style encoder (Conan.py:200-219)
   {
+    // tensor-core path: sessions padded to TS = multiple of 32 rows (rows T.. of X and of the masks are zero)
+    const bool tc = e->ses_tc;
+    const int TS = tc ? (T + 31) / 32 * 32 : T;
+    const float* mask = e->qMA;
+    if (TS != T) {
+      CONAN_CUDA_OK(cudaMemsetAsync(e->qXG, 0, (size_t)n * TS * H * 4, st));
+      CONAN_CUDA_OK(cudaMemsetAsync(e->qMAp, 0, (size_t)n * TS * 4, st));
+      CONAN_CUDA_OK(cudaMemcpy2DAsync(e->qMAp, (size_t)TS * 4, e->qMA, (size_t)T * 4, (size_t)T * 4, n, cudaMemcpyDeviceToDevice, st));
+      mask = e->qMAp;
+    }
     auto p = conv_on_rows(e, ref, T, 0, T, M, e->P("conan.global_in.w"), e->F("conan.global_in.b"), H, n);
-    p.n_slots = n; out_rows(p, e->qXG, T, H); p.rowmask = e->qMA; p.mask_slot_stride = T;
+    p.n_slots = n; out_rows(p, e->qXG, TS, H); p.rowmask = e->qMA; p.mask_slot_stride = T;
     TRY(run_conv(e, p, st));
-    TRY(conv_blocks_noncausal(e, "conan.genc", e->qXG, H, 31, e->qC31, e->qHG, e->qC3G, e->qPG, H, e->qMA, e->qMGB, n, T, st));
-    TRY(launch_masked_time_mean(e->qPG, e->qMA, e->sSTYLE, e->qSlots, n, T, H, st));
+    TRY(conv_blocks_noncausal(e, "conan.genc", e->qXG, H, 31, e->qC31, e->qHG, e->qC3G, e->qPG, H, mask, e->qMGB, n, T, TS, st,
+                              tc, e->qC31h, e->qHGh, e->qC3Gh));
+    TRY(launch_masked_time_mean(e->qPG, mask, e->sSTYLE, e->qSlots, n, T, TS, H, st));
   }
   // ---- LocalStyleAdaptor: WN (wavenet.py:55-88)
   {
@@ -896,7 +931,7 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
   {
     TRY(launch_row_masks(e->qGRP, e->qMP, e->qMPB, n, Tp, M, st));      // qMPB is overwritten by the block masks below
     CONAN_CUDA_OK(cudaMemcpyAsync(e->qXP, e->qGRP, (size_t)n * Tp * M * 4, cudaMemcpyDeviceToDevice, st));
-    TRY(conv_blocks_noncausal(e, "conan.penc", e->qXP, M, 5, e->qC5, e->qHP, e->qC3P, e->qPZ, H, e->qMP, e->qMPB, n, Tp, st));
+    TRY(conv_blocks_noncausal(e, "conan.penc", e->qXP, M, 5, e->qC5, e->qHP, e->qC3P, e->qPZ, H, e->qMP, e->qMPB, n, Tp, Tp, st));
     auto d = conv_on_rows(e, e->qPZ, Tp, 0, Tp, H, e->P("conan.vq.embedding"), nullptr, c.n_vq, n);
     d.n_slots = n; out_rows(d, e->qXE, Tp, c.n_vq);
     TRY(run_conv(e, d, st));
@@ -913,6 +948,19 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
       TRY(run_conv(e, kv, st));
       TRY(launch_scatter_kv(e->qKVs, e->sKV, e->qSlots, n, Tp, 2 * H, l, 2, e->tp_max, st));
     }
+  }
+  return 0;
+}
+
+// A ready list handed over in HOST memory is checked before it reaches the device: an out-of-range id would be an
+// out-of-bounds read / write of resident state, a duplicate would make two CTAs race on one stream's K/V ring and history.
+int check_ids_host(conan_engine* e, int n, const int32_t* ids, const char* who) {
+  e->idSeen.assign((size_t)e->S, 0);
+  for (int i = 0; i < n; ++i) {
+    const int s = ids[i];
+    if (s < 0 || s >= e->S) { set_error(std::string(who) + ": slot id " + std::to_string(s) + " out of range [0, " + std::to_string(e->S) + ")"); return 1; }
+    if (e->idSeen[s]) { set_error(std::string(who) + ": slot id " + std::to_string(s) + " appears twice in one step"); return 1; }
+    e->idSeen[s] = 1;
   }
   return 0;
 }
@@ -938,7 +986,13 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
   if (cfg->abi_version != CONAN_B200_ABI_VERSION) { set_error("ABI version mismatch"); return 1; }
   if (cfg->max_slots <= 0 || cfg->max_ref_frames <= 0) { set_error("max_slots and max_ref_frames must be positive"); return 1; }
   if (cfg->voc_n_ups > 8 || cfg->voc_n_res > 4 || cfg->voc_n_dil > 4 || cfg->dec_blocks > 8) { set_error("config above compiled limits"); return 1; }
-  if (cfg->voc_use_tensor_cores && !cfg->voc_precision) { set_error("voc_use_tensor_cores requires voc_precision = 1 (fp16 operands)"); return 1; }
+  if (cfg->voc_precision < 0 || cfg->voc_precision > 2) { set_error("voc_precision must be 0 (fp32), 1 (fp16 operands) or 2 (split fp16 operands)"); return 1; }
+  if (cfg->voc_use_tensor_cores && !cfg->voc_precision) { set_error("voc_use_tensor_cores requires voc_precision 1 (fp16 operands) or 2 (split fp16 operands)"); return 1; }
+  if (cfg->voc_precision == 2 && (!cfg->voc_use_tensor_cores || cfg->voc_residual_from_ctx || cfg->voc_fuse_resblocks)) {
+    set_error("voc_precision 2 (split fp16) runs on the tensor cores with an fp32 residual stream: needs voc_use_tensor_cores = 1, "
+              "voc_residual_from_ctx = 0, voc_fuse_resblocks = 0");
+    return 1;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) {
     set_error("no CUDA device: the conan_b200 engine has no CPU fallback");
@@ -953,6 +1007,7 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
   e->S = cfg->max_slots;
   e->tp_max = (cfg->max_ref_frames - 1) / 4 + 1;
   e->lin_tc = cfg->lin_use_tensor_cores != 0;
+  e->ses_tc = cfg->ses_use_tensor_cores != 0;
   declare_weights(e);
   *out = e;
   return 0;
@@ -1074,6 +1129,12 @@ int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, cons
                     float* mel_out_host, int32_t* tokens_out_host, void* stream) {
   if (check_ready(e)) return 1;
   if (n < 0 || n > e->S || !slot_ids_host || !chunk_host || !wav_out_host) { set_error("bad arguments to conan_step_host"); return 1; }
+  if (e->ticketPending[0] || e->ticketPending[1]) {
+    // the synchronous call shares output set 0 with the pipelined one: its result copy may still be in flight
+    set_error("conan_step_host: pipelined steps are in flight; call conan_step_host_wait first");
+    return 1;
+  }
+  if (check_ids_host(e, n, slot_ids_host, "conan_step_host")) return 1;
   const conan_config_t& c = e->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rows = c.segment + c.right_context, Lw = e->vL[c.voc_n_ups];
@@ -1095,6 +1156,7 @@ int conan_step_host_submit(conan_engine_t* e, int n, const int32_t* slot_ids_hos
   cudaStream_t st = (cudaStream_t)stream;
   const int b = (int)(e->submitCount & 1);
   if (e->ticketPending[b]) { set_error("conan_step_host_submit: two steps already in flight; call conan_step_host_wait first"); return 1; }
+  if (check_ids_host(e, n, slot_ids_host, "conan_step_host_submit")) return 1;
   const size_t rows = c.segment + c.right_context, Lw = e->vL[c.voc_n_ups];
   float* dWav = b ? e->hWav2 : e->hWav; float* dMel = b ? e->hMel2 : e->hMel; int* dTok = b ? e->hTok2 : e->hTok;
   CONAN_CUDA_OK(cudaMemcpyAsync(e->hIds, slot_ids_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));

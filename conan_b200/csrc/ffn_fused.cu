@@ -269,13 +269,14 @@ int launch_ffn_fused(const FfnFusedParams& p, cudaStream_t st) {
   if (get_tensor_map(&tmW2, p.w2, 2, (unsigned long long)3 * p.hidden, FF_KP, 1, (unsigned long long)3 * p.hidden * 2, 0, 64, FF_KP, 1, 128)) return 1;
   FfnArgs a;
   a.M = p.M; a.n_chunks = p.hidden / FF_CH; a.FS = p.FS; a.hidden = p.hidden; a.b1 = p.b1; a.P = p.partials; a.acc_scale = p.acc_scale;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
   ffn_fused_kernel<<<mt * p.FS, FF_THREADS, FF_SMEM, st>>>(tmX, tmW1, tmW2, a);
   CONAN_CHECK_LAUNCH();
   return 0;

@@ -91,7 +91,7 @@ int launch_rows_to_view(const float* src_slot, RowView out, int n, const int* sl
 // taps_host: optional HOST copy of [k*C weights | bias] (enables the fast path whose taps travel as a kernel parameter)
 int launch_conv_post_tanh(const void* x, int x_is_half, long long slot_stride, int row_stride, int row0, int L, int C, int k,
                           const float* w, const float* bias, float* wav_out, int n, const int* slot_ids, cudaStream_t st,
-                          const float* taps_host = nullptr);
+                          const float* taps_host = nullptr, long long lo_off = 0);   // lo_off: lo plane of a split fp16 input (elements)
 
 // fused HiFi-GAN residual block on tcgen05 (resblock_fused.cu) -------------------------------------------------
 struct ResblockFusedParams {
@@ -154,7 +154,7 @@ int launch_vq_quantize(const float* x, const float* xe, const float* E, const fl
 // key padding mask of the aligner (Conan.py:249): kpm[slot, p] = (pe[i, p, 0] == 0); also n_keys[slot] = Tp
 int launch_kpm(const float* pe, float* kpm, int* n_keys, const int* slots_dev, int n, int Tp, int H, int tp_max, cudaStream_t st);
 // masked temporal mean (Conan.py:214-219): style[slot, c] = sum_t x*mask / sum_t mask
-int launch_masked_time_mean(const float* x, const float* mask, float* style, const int* slots_dev, int n, int T, int C, cudaStream_t st);
+int launch_masked_time_mean(const float* x, const float* mask, float* style, const int* slots_dev, int n, int T, int TS, int C, cudaStream_t st);
 // scatter session K/V [n, Tp, 2H] -> cache[slot, layer, tp_max, 2H]
 int launch_scatter_kv(const float* kv, float* cache, const int* slots_dev, int n, int Tp, int H2, int layer, int n_layers,
                       int tp_max, cudaStream_t st);

@@ -351,13 +351,14 @@ inline int align1k(int x) { return (x + 1023) & ~1023; }
 template <int C, int KT>
 int launch_fused_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const FusedArgs& a, size_t smem, cudaStream_t st) {
   auto kern = resblock_fused_kernel<C, KT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
   const int per_sm = resident_ctas((const void*)kern, rf_threads(C), smem, 2 * C < 32 ? 32 : 2 * C);
   const int grid = std::min(a.n_streams, num_sms() * per_sm);
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused<%d,%d> k %d tiles/stream %d smem %zu per_sm %d grid %d\n", C, KT, a.k, a.tiles, smem, per_sm, grid);

@@ -363,13 +363,14 @@ inline int align1k2(int x) { return (x + 1023) & ~1023; }
 template <int C, int KT>
 int launch_fused2_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const Fused2Args& a, size_t smem, cudaStream_t st) {
   auto kern = resblock_fused2_kernel<C, KT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
   // one CTA per SM at C = 64, two at C = 32; two streams in flight per CTA
   const int grid = std::min((a.n_streams + 1) / 2, num_sms() * (C == 32 ? 2 : 1));
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused2<%d,%d> k %d tiles/stream %d smem %zu grid %d\n", C, KT, a.k, a.tiles, smem, grid);

@@ -22,7 +22,7 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
                 max_ref_frames: int = 512, device: int = 0, voc_precision: str = "fp16",
                 voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None,
                 voc_residual_from_ctx: Optional[bool] = None, voc_fuse_resblocks: Optional[bool] = None,
-                lin_fuse_ffn: Optional[bool] = None) -> _lib.ConanConfig:
+                lin_fuse_ffn: Optional[bool] = None, ses_tensor_cores: Optional[bool] = None) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -58,8 +58,13 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     cfg.voc_n_dil = len(dil[0])
     for i, d in enumerate(dil[0]):
         cfg.voc_res_dilations[i] = d
-    cfg.voc_precision = {"fp32": 0, "fp16": 1}[voc_precision]
-    cfg.voc_use_tensor_cores = int(bool(voc_tensor_cores) and cfg.voc_precision == 1)
+    # "fp32": fp32 operands on the CUDA cores (exact-fp32 cross-check engine); "fp16": fp16 operands / fp32 accumulate on
+    # tcgen05 (the fast mode); "split": split-fp16 operands (x_hi W_hi + x_hi W_lo + x_lo W_hi, fp32 accumulate) on tcgen05 --
+    # fp32-grade results at a third of the fp16 mode's tensor rate
+    cfg.voc_precision = {"fp32": 0, "fp16": 1, "split": 2}[voc_precision]
+    if cfg.voc_precision == 2 and not voc_tensor_cores:
+        raise ValueError("voc_precision='split' is a tensor-core mode")
+    cfg.voc_use_tensor_cores = int(bool(voc_tensor_cores) and cfg.voc_precision >= 1)
     cfg.voc_group = voc_group
     # fp16-operand vocoder: recover the resblock residual from the activated fp16 context rows (halves the HBM traffic of
     # every second conv; costs 1.7 dB of the 59 dB SNR).  The fp32 vocoder keeps its fp32 residual stream.
@@ -68,9 +73,13 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     # vocoder is on; lin_tensor_cores=False keeps them on the exact-fp32 FFMA engine
     cfg.lin_use_tensor_cores = int(cfg.voc_use_tensor_cores if lin_tensor_cores is None else bool(lin_tensor_cores))
     # whole residual blocks as one kernel at the 32 / 64 channel scales (activations stay in shared memory)
-    can_fuse = bool(cfg.voc_use_tensor_cores and cfg.voc_residual_from_ctx)
+    if cfg.voc_precision == 2:
+        cfg.voc_residual_from_ctx = 0      # fp32 residual stream next to the split operands
+    can_fuse = bool(cfg.voc_use_tensor_cores and cfg.voc_residual_from_ctx and cfg.voc_precision == 1)
     cfg.voc_fuse_resblocks = int(can_fuse if voc_fuse_resblocks is None else (bool(voc_fuse_resblocks) and can_fuse))
     cfg.lin_fuse_ffn = int(bool(cfg.lin_use_tensor_cores) if lin_fuse_ffn is None else (bool(lin_fuse_ffn) and bool(cfg.lin_use_tensor_cores)))
+    # session setup: the style encoder (95 % of the setup FLOPs) on the tensor cores, same split-fp16 operand format
+    cfg.ses_use_tensor_cores = int(bool(cfg.lin_use_tensor_cores) if ses_tensor_cores is None else bool(ses_tensor_cores))
     return cfg
 
 

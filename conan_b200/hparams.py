@@ -69,7 +69,7 @@ def _apply_overrides(cfg: dict, spec: str):
 
 def set_hparams(config: str = "", exp_name: str = "", hparams_str: str = "", print_hparams: bool = True,
                 global_hparams: bool = True) -> dict:
-    reset = infer = False
+    reset = infer = debug = validate = False
     if config == "" and exp_name == "":
         ap = argparse.ArgumentParser(description="")
         ap.add_argument("--config", type=str, default="")
@@ -83,6 +83,7 @@ def set_hparams(config: str = "", exp_name: str = "", hparams_str: str = "", pri
         args, unknown = ap.parse_known_args()
         print("| Unknown hparams: ", unknown)
         config, exp_name, hparams_str, reset, infer = args.config, args.exp_name, args.hparams, args.reset, args.infer
+        debug, validate = args.debug, args.validate
     assert config != "" or exp_name != ""
     if config != "":
         assert os.path.exists(config), config
@@ -100,7 +101,8 @@ def set_hparams(config: str = "", exp_name: str = "", hparams_str: str = "", pri
     cfg["work_dir"] = work_dir
     if hparams_str:
         _apply_overrides(cfg, hparams_str)
-    cfg.setdefault("infer", infer)
+    # assigned unconditionally, as the reference does (utils/commons/hparams.py:113-116): a saved config.yaml cannot mask --infer
+    cfg["infer"], cfg["debug"], cfg["validate"] = infer, debug, validate
     cfg["exp_name"] = exp_name
     if global_hparams:
         hparams.clear()

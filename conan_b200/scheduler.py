@@ -6,140 +6,338 @@ re-runs the models on all history.  The contract kept here is that loop's chunk 
   emit = min(seg, T - pos); look = min(rc, T - pos - emit); the chunk is frames [pos, pos+emit+look)
   padded to seg+rc rows by repeating its last frame (:97-110); a stream advances by `emit` frames.
 A stream whose source is still arriving is *ready* when seg+rc frames past `pos` are buffered; once
-`end()` was called the remaining frames are flushed with the same padding rule.  `step()` gathers the
-ready streams' chunks into one [n, seg+rc, 80] host buffer, makes ONE engine call (slot ids + chunks
+`end()` was called the remaining frames are flushed with the same padding rule.  One step gathers the
+ready streams' chunks into one [n, seg+rc, 80] staging buffer, makes ONE engine call (slot ids + chunks
 in, wav/mel/tokens out) and hands each stream its `emit` frames of output.
 
-The engine is duck-typed (`reset_slots`, `open_sessions`, `step_host`, `segment`, `rows_in`,
-`hop_out`, `n_mels`) so the host logic is unit-tested on CPU with a recording fake.
+Host data structures (all indexed by slot, struct-of-arrays, so a step is a handful of vectorised numpy
+operations whatever the number of streams -- there is no per-stream Python loop on the step path):
+  * `ring  [max_streams, cap, n_mels]` fp32: the not-yet-consumed source frames of every stream, frame f of a
+    stream at row f mod cap.  Bounded: a stream holds at most `cap` frames here whatever its length;
+  * `recv / pos / ended / total`: frames written to the ring, frames consumed, end-of-stream flag, final length;
+  * a per-stream backlog (only for callers that push more than the ring holds, e.g. a whole utterance at
+    once): the caller's arrays wait there and refill the ring as frames are consumed.
+Chunk assembly is one `np.take` with the index  min(pos + i, last) mod cap  (the clamp IS the reference's
+repeat-last-frame padding) straight into the staging buffer the engine copies from.
+
+Two stepping styles: `step_packed()` (synchronous: results of this step) and `submit()` / `collect()`
+(two steps in flight: the result copy of step i runs under the compute of step i+1).
+
+The engine is duck-typed (`reset_slots`, `open_sessions`, `step_host`, optionally `step_host_submit` /
+`step_host_wait`, `segment`, `rows_in`, `hop_out`, `n_mels`) so the host logic is unit-tested on CPU with a
+recording fake.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from collections import deque
+from dataclasses import dataclass
+from typing import Deque, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 
 @dataclass
-class _Stream:
-    slot: int
-    frames: List[np.ndarray] = field(default_factory=list)   # pending source mel, [n_i, 80] pieces
-    buffered: Optional[np.ndarray] = None                     # concatenated view, lazily rebuilt
-    pos: int = 0                                              # frames already consumed (emitted)
-    ended: bool = False
+class PackedStep:
+    """Result of one packed step: row i belongs to stream `sids[i]` (slot `slots[i]`); only the first
+    `emits[i]` frames (emits[i] * hop samples) of a row are output, the rest is look-ahead padding."""
+    sids: np.ndarray       # [n] int64
+    slots: np.ndarray      # [n] int32
+    emits: np.ndarray      # [n] int32
+    wav: np.ndarray        # [n, seg * hop] fp32
+    mel: np.ndarray        # [n, seg, n_mels] fp32
+    tokens: np.ndarray     # [n, seg] int32
+    hop: int
 
-    def mel(self) -> np.ndarray:
-        if self.frames:
-            parts = ([self.buffered] if self.buffered is not None else []) + self.frames
-            self.buffered = np.concatenate(parts, axis=0)
-            self.frames = []
-        return self.buffered if self.buffered is not None else np.zeros((0, 80), np.float32)
+    def __len__(self):
+        return len(self.sids)
+
+    def per_stream(self) -> Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+        return {int(s): (self.wav[i, :e * self.hop].copy(), self.mel[i, :e].copy(), self.tokens[i, :e].copy())
+                for i, (s, e) in enumerate(zip(self.sids, self.emits))}
+
+
+class _StreamView:
+    """Read-only view of one stream's scheduler state (kept for callers that look at `.slot` / `.pos`)."""
+
+    def __init__(self, sch: "ChunkScheduler", slot: int):
+        self._s, self.slot = sch, slot
+
+    @property
+    def pos(self) -> int:
+        return int(self._s.pos[self.slot])
+
+    @property
+    def ended(self) -> bool:
+        return bool(self._s.ended[self.slot])
+
+
+def _pinned_empty(shape, dtype):
+    """Page-locked staging memory when a CUDA runtime is present (the engine copies from / to it asynchronously)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(shape, dtype={np.float32: torch.float32, np.int32: torch.int32}[dtype]).pin_memory()
+            return t.numpy(), t
+    except Exception:
+        pass
+    return np.zeros(shape, dtype), None
 
 
 class ChunkScheduler:
-    def __init__(self, engine, max_streams: int):
+    def __init__(self, engine, max_streams: int, capacity_frames: int = 64):
         self.eng = engine
         self.seg, self.rows = engine.segment, engine.rows_in
         self.rc = self.rows - self.seg
+        self.n_mels = engine.n_mels
+        self.hop = engine.hop_out // self.seg
+        self.S = max_streams
+        self.cap = max(int(capacity_frames), 2 * self.rows)
         self.free = list(range(max_streams - 1, -1, -1))
-        self.streams: Dict[int, _Stream] = {}
+        self.streams: Dict[int, _StreamView] = {}
         self._next_id = 0
-        self._chunk_buf = np.zeros((max_streams, self.rows, engine.n_mels), np.float32)
-        self._wav_buf = np.zeros((max_streams, engine.hop_out), np.float32)
-        self._mel_buf = np.zeros((max_streams, self.seg, engine.n_mels), np.float32)
-        self._tok_buf = np.zeros((max_streams, self.seg), np.int32)
+        S = max_streams
+        self.ring = np.zeros((S, self.cap, self.n_mels), np.float32)
+        self._ring2d = self.ring.reshape(S * self.cap, self.n_mels)
+        self.recv = np.zeros(S, np.int64)          # frames written to the ring so far
+        self.pos = np.zeros(S, np.int64)           # frames consumed (emitted)
+        self.total = np.zeros(S, np.int64)         # frames pushed in all (ring + backlog)
+        self.ended = np.zeros(S, bool)
+        self.active = np.zeros(S, bool)
+        self.sid_of = np.full(S, -1, np.int64)
+        self._backlog: Dict[int, Deque[np.ndarray]] = {}     # slot -> frames waiting for ring space
+        self._row_off = np.arange(self.rows, dtype=np.int64)[None, :]
+        # two sets of staging buffers (pipelined stepping alternates between them)
+        self._keep = []
+        self._stage = []
+        for _ in range(2):
+            bufs = {}
+            for name, shape, dt in (("chunk", (S, self.rows, self.n_mels), np.float32), ("wav", (S, engine.hop_out), np.float32),
+                                    ("mel", (S, self.seg, self.n_mels), np.float32), ("tok", (S, self.seg), np.int32),
+                                    ("slots", (S,), np.int32)):
+                arr, keep = _pinned_empty(shape, dt)
+                bufs[name] = arr
+                self._keep.append(keep)
+            self._stage.append(bufs)
+        self._flip = 0
+        self._inflight: Deque[Tuple[int, int, np.ndarray, np.ndarray, np.ndarray, int]] = deque()
 
     # ------------------------------------------------------------------ session admission
     def open(self, ref_mel) -> int:
         return self.open_many([ref_mel])[0]
 
     def open_many(self, ref_mels) -> List[int]:
-        """ref_mels: list of [T_ref, 80] arrays.  Streams with equal T_ref share one session-setup call."""
+        """ref_mels: list of [T_ref, 80] arrays.  Streams with equal T_ref share one session-setup call.
+        Nothing is allocated if a reference is malformed; if the engine rejects a session every slot taken by
+        this call is returned to the pool."""
         import torch
-        if len(ref_mels) > len(self.free):
-            raise RuntimeError(f"no free stream slot ({len(ref_mels)} requested, {len(self.free)} free)")
-        ids, by_len = [], {}
-        for m in ref_mels:
-            m = np.asarray(m, dtype=np.float32)
+        refs = [np.asarray(m, dtype=np.float32) for m in ref_mels]
+        max_ref = getattr(getattr(self.eng, "cfg", None), "max_ref_frames", None)
+        for m in refs:
+            if m.ndim != 2 or m.shape[1] != self.n_mels or m.shape[0] < 1:
+                raise ValueError(f"reference mel must be [T_ref >= 1, {self.n_mels}], got {m.shape}")
+            if max_ref is not None and m.shape[0] > max_ref:
+                raise ValueError(f"reference mel has {m.shape[0]} frames; this engine was built for at most {max_ref} "
+                                 "(max_ref_frames)")
+        if len(refs) > len(self.free):
+            raise RuntimeError(f"no free stream slot ({len(refs)} requested, {len(self.free)} free)")
+        ids, slots, by_len = [], [], {}
+        for m in refs:
             slot = self.free.pop()
             sid = self._next_id
             self._next_id += 1
-            self.streams[sid] = _Stream(slot=slot)
+            self._activate(slot, sid)
             ids.append(sid)
+            slots.append(slot)
             by_len.setdefault(m.shape[0], []).append((slot, m))
-        self.eng.reset_slots([self.streams[s].slot for s in ids])
-        for _, group in by_len.items():
-            slots = [g[0] for g in group]
-            ref = torch.from_numpy(np.stack([g[1] for g in group]))
-            self.eng.open_sessions(slots, ref.to(self.eng.device) if hasattr(self.eng, "device") else ref)
+        try:
+            self.eng.reset_slots(slots)
+            for _, group in by_len.items():
+                ref = torch.from_numpy(np.stack([g[1] for g in group]))
+                self.eng.open_sessions([g[0] for g in group], ref.to(self.eng.device) if hasattr(self.eng, "device") else ref)
+        except Exception:
+            for sid in ids:
+                self.close(sid)
+            raise
         return ids
+
+    def _activate(self, slot: int, sid: int):
+        self.recv[slot] = self.pos[slot] = self.total[slot] = 0
+        self.ended[slot] = False
+        self.active[slot] = True
+        self.sid_of[slot] = sid
+        self.streams[sid] = _StreamView(self, slot)
 
     def close(self, sid: int):
         st = self.streams.pop(sid)
+        self.active[st.slot] = False
+        self.sid_of[st.slot] = -1
+        self._backlog.pop(st.slot, None)
         self.free.append(st.slot)
 
     # ------------------------------------------------------------------ input side
+    def _ring_write(self, slot: int, f: np.ndarray) -> int:
+        """Copies as many leading frames of f as the ring has room for; returns how many."""
+        room = self.cap - int(self.recv[slot] - self.pos[slot])
+        n = min(room, f.shape[0])
+        if n > 0:
+            w = int(self.recv[slot] % self.cap)
+            first = min(n, self.cap - w)
+            self.ring[slot, w:w + first] = f[:first]
+            if n > first:
+                self.ring[slot, :n - first] = f[first:n]
+            self.recv[slot] += n
+        return n
+
     def push(self, sid: int, mel_frames):
         st = self.streams[sid]
-        if st.ended:
+        slot = st.slot
+        if self.ended[slot]:
             raise RuntimeError("push() after end()")
         f = np.asarray(mel_frames, dtype=np.float32)
-        if f.ndim != 2 or f.shape[1] != self.eng.n_mels:
+        if f.ndim != 2 or f.shape[1] != self.n_mels:
             raise ValueError("mel_frames must be [n, n_mels]")
-        if f.shape[0]:
-            st.frames.append(f)
+        if not f.shape[0]:
+            return
+        self.total[slot] += f.shape[0]
+        bl = self._backlog.get(slot)
+        if bl:                                   # keep arrival order: frames queue behind the backlog
+            bl.append(f)
+            return
+        n = self._ring_write(slot, f)
+        if n < f.shape[0]:
+            self._backlog.setdefault(slot, deque()).append(f[n:])
+
+    def push_many(self, slots: np.ndarray, frames: np.ndarray):
+        """Vectorised push for streams fed in lock-step (a serving loop that receives the same number of new frames for a
+        batch of streams): slots [n] (distinct), frames [n, f, n_mels].  Every stream must have ring room for f frames."""
+        slots = np.asarray(slots, dtype=np.int64)
+        f = frames.shape[1]
+        if f == 0 or len(slots) == 0:
+            return
+        if self._backlog and any(int(s) in self._backlog for s in slots):
+            raise BufferError("push_many: a stream still has a backlog from push(); drain it first")
+        if (self.cap - (self.recv[slots] - self.pos[slots]) < f).any():
+            raise BufferError("push_many: ring full for at least one stream (consumer is behind: back-pressure)")
+        idx = (self.recv[slots][:, None] + np.arange(f, dtype=np.int64)[None, :]) % self.cap + slots[:, None] * self.cap
+        self._ring2d[idx.reshape(-1)] = frames.reshape(-1, self.n_mels)
+        self.recv[slots] += f
+        self.total[slots] += f
 
     def end(self, sid: int):
-        self.streams[sid].ended = True
+        self.ended[self.streams[sid].slot] = True
 
-    def _ready(self, st: _Stream) -> bool:
-        avail = st.mel().shape[0] - st.pos
-        return avail >= self.rows or (st.ended and avail > 0)
+    def buffered_frames(self, sid: int) -> int:
+        """Frames held for this stream in the scheduler's own ring (bounded by the ring capacity)."""
+        slot = self.streams[sid].slot
+        return int(self.recv[slot] - self.pos[slot])
+
+    def pending_frames(self, sid: int) -> int:
+        slot = self.streams[sid].slot
+        return int(self.total[slot] - self.pos[slot])
+
+    # ------------------------------------------------------------------ readiness
+    def _ready_mask(self) -> np.ndarray:
+        avail = self.recv - self.pos
+        flush = self.ended & (self.recv == self.total) & (avail > 0)
+        return self.active & ((avail >= self.rows) | flush)
+
+    def ready_slots(self) -> np.ndarray:
+        return np.flatnonzero(self._ready_mask()).astype(np.int32)
 
     def ready(self) -> List[int]:
-        return [sid for sid, st in self.streams.items() if self._ready(st)]
+        return [int(s) for s in self.sid_of[self.ready_slots()]]
 
     def finished(self, sid: int) -> bool:
-        st = self.streams[sid]
-        return st.ended and st.mel().shape[0] - st.pos <= 0
+        slot = self.streams[sid].slot
+        return bool(self.ended[slot]) and int(self.total[slot] - self.pos[slot]) <= 0
 
     # ------------------------------------------------------------------ one packed step
-    def assemble(self, st: _Stream) -> Tuple[np.ndarray, int]:
-        mel = st.mel()
-        T = mel.shape[0] if st.ended else max(mel.shape[0], st.pos + self.rows)
-        emit = min(self.seg, T - st.pos)
-        look = min(self.rc, T - (st.pos + emit))
-        chunk = mel[st.pos:st.pos + emit + look]
-        need = self.rows - chunk.shape[0]
-        if need > 0:
-            chunk = np.concatenate([chunk, np.repeat(chunk[-1:], need, axis=0)], axis=0)
-        return chunk, emit
+    def _assemble(self, slots: np.ndarray, out: np.ndarray) -> np.ndarray:
+        """chunk rows of `slots` -> out[:n]; returns emit[n].  inference/Conan.py:97-110 as index arithmetic."""
+        s64 = slots.astype(np.int64)
+        pos, ended = self.pos[s64], self.ended[s64]
+        remaining = np.where(ended, self.total[s64] - pos, np.int64(1 << 40))
+        emit = np.minimum(self.seg, remaining)
+        last = pos + np.minimum(self.rows, remaining) - 1                 # last real frame of the chunk (then repeated)
+        src = np.minimum(pos[:, None] + self._row_off, last[:, None])
+        flat = (src % self.cap + s64[:, None] * self.cap).reshape(-1)
+        np.take(self._ring2d, flat, axis=0, out=out[:len(slots)].reshape(-1, self.n_mels), mode="clip")
+        return emit.astype(np.int32)
+
+    def _advance(self, slots: np.ndarray, emits: np.ndarray):
+        self.pos[slots.astype(np.int64)] += emits
+        for slot in [s for s in self._backlog if self._backlog[s]]:      # only streams that over-filled the ring
+            bl = self._backlog[slot]
+            while bl:
+                n = self._ring_write(slot, bl[0])
+                if n < bl[0].shape[0]:
+                    bl[0] = bl[0][n:]
+                    break
+                bl.popleft()
+            if not bl:
+                del self._backlog[slot]
+
+    def _pick(self, max_batch: Optional[int]) -> np.ndarray:
+        # a stream may be part of both in-flight steps: the engine runs them in submission order on one CUDA stream, and
+        # `pos` advanced when the first one was staged
+        slots = self.ready_slots()
+        if max_batch is not None:
+            slots = slots[:max_batch]
+        return slots
+
+    def submit(self, max_batch: Optional[int] = None) -> Optional[int]:
+        """Assembles the ready streams' chunks and enqueues one engine step without waiting for it (needs an engine with
+        step_host_submit / step_host_wait).  Returns a ticket for collect(), or None when no stream is ready.
+        At most two steps may be in flight."""
+        if len(self._inflight) >= 2:
+            raise RuntimeError("two steps already in flight: collect() first")
+        slots = self._pick(max_batch)
+        n = len(slots)
+        if n == 0:
+            return None
+        b = self._stage[self._flip]
+        b["slots"][:n] = slots
+        emits = self._assemble(slots, b["chunk"])
+        sids = self.sid_of[slots.astype(np.int64)].copy()
+        ticket = self.eng.step_host_submit(b["slots"][:n], b["chunk"][:n], b["wav"][:n], b["mel"][:n], b["tok"][:n])
+        self._advance(slots, emits)              # the chunk is staged: the ring rows are free for new frames
+        self._inflight.append((ticket, self._flip, slots.copy(), emits, sids, n))
+        self._flip ^= 1
+        return ticket
+
+    def collect(self, ticket: Optional[int] = None) -> PackedStep:
+        """Waits for the oldest in-flight step and returns its outputs (views of the staging buffers: valid until the
+        second-next submit())."""
+        if not self._inflight:
+            raise RuntimeError("no step in flight")
+        t, flip, slots, emits, sids, n = self._inflight.popleft()
+        if ticket is not None and ticket != t:
+            raise RuntimeError("steps must be collected in submission order")
+        self.eng.step_host_wait(t)
+        b = self._stage[flip]
+        return PackedStep(sids, slots, emits, b["wav"][:n], b["mel"][:n], b["tok"][:n], self.hop)
+
+    def step_packed(self, max_batch: Optional[int] = None) -> Optional[PackedStep]:
+        """One synchronous chunk step for every ready stream (one launch sequence)."""
+        if self._inflight:
+            raise RuntimeError("step_packed() while pipelined steps are in flight")
+        slots = self._pick(max_batch)
+        n = len(slots)
+        if n == 0:
+            return None
+        b = self._stage[self._flip]
+        b["slots"][:n] = slots
+        emits = self._assemble(slots, b["chunk"])
+        sids = self.sid_of[slots.astype(np.int64)].copy()
+        self.eng.step_host(b["slots"][:n], b["chunk"][:n], b["wav"][:n], b["mel"][:n], b["tok"][:n])
+        self._advance(slots, emits)
+        return PackedStep(sids, slots.copy(), emits, b["wav"][:n], b["mel"][:n], b["tok"][:n], self.hop)
 
     def step(self, max_batch: Optional[int] = None) -> Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]]:
-        """Runs one chunk step for every ready stream (one launch sequence).  Returns
-        {stream id: (wav [emit*hop], mel [emit, 80], tokens [emit])}."""
-        sids = self.ready()
-        if max_batch is not None:
-            sids = sids[:max_batch]
-        n = len(sids)
-        if n == 0:
-            return {}
-        slots = np.empty(n, np.int32)
-        emits = []
-        for i, sid in enumerate(sids):
-            st = self.streams[sid]
-            self._chunk_buf[i], emit = self.assemble(st)
-            slots[i] = st.slot
-            emits.append(emit)
-        self.eng.step_host(slots, self._chunk_buf[:n], self._wav_buf[:n], self._mel_buf[:n], self._tok_buf[:n])
-        hop = self.eng.hop_out // self.seg
-        out = {}
-        for i, sid in enumerate(sids):
-            e = emits[i]
-            self.streams[sid].pos += e
-            out[sid] = (self._wav_buf[i, :e * hop].copy(), self._mel_buf[i, :e].copy(), self._tok_buf[i, :e].copy())
-        return out
+        """Runs one chunk step for every ready stream.  Returns
+        {stream id: (wav [emit*hop], mel [emit, 80], tokens [emit])} (copies; small-scale convenience over step_packed)."""
+        r = self.step_packed(max_batch)
+        return {} if r is None else r.per_stream()
 
 
 def shard_streams(n_streams: int, world_size: int, rank: int) -> range:

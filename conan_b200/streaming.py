@@ -43,13 +43,31 @@ def load_voc_config(vocoder_ckpt: str) -> dict:
     return set_hparams(f"{vocoder_ckpt}/config.yaml", global_hparams=False, print_hparams=False)
 
 
+class _LazyDefaults:
+    """Initial tensors of a spec, generated only if a checkpoint really leaves a hole."""
+
+    def __init__(self, spec, seed):
+        self.spec, self.seed, self._sd = spec, seed, None
+
+    def __getitem__(self, key):
+        if self._sd is None:
+            self._sd = synth.make_state_dict(self.spec, self.seed)
+        return self._sd[key]
+
+
 def build_engine(hp: Dict, *, max_streams: int = 8, max_ref_frames: int = 1024, voc_precision: str = "fp16",
                  voc_tensor_cores: bool = True, device: int = 0) -> Engine:
     """Reads the three checkpoints named by the hparams (work_dir / emformer_ckpt / vocoder_ckpt, same
     selection rules as utils/commons/ckpt_utils.py:26-66) and builds the native engine."""
     voc_hp = load_voc_config(hp["vocoder_ckpt"])
-    sd_c = ckpt.filter_to_spec(ckpt.load_state_dict(hp["work_dir"], "model"), synth.conan_spec(hp), strict=False)
-    sd_e = ckpt.filter_to_spec(ckpt.load_state_dict(hp["emformer_ckpt"], "model"), synth.emformer_spec(hp), strict=False)
+    # strict=False (inference/Conan.py:37,51): shape-mismatched / missing keys keep the initial value; the reference's
+    # nn.Module supplies it, here it is the seeded default init of conan_b200.synth (hparams `seed`)
+    seed = int(hp.get("seed", 1234))
+    spec_c, spec_e = synth.conan_spec(hp), synth.emformer_spec(hp)
+    sd_c = ckpt.filter_to_spec(ckpt.load_state_dict(hp["work_dir"], "model"), spec_c, strict=False,
+                               defaults=_LazyDefaults(spec_c, seed))
+    sd_e = ckpt.filter_to_spec(ckpt.load_state_dict(hp["emformer_ckpt"], "model"), spec_e, strict=False,
+                               defaults=_LazyDefaults(spec_e, seed))
     sd_v = ckpt.filter_to_spec(ckpt.load_state_dict(hp["vocoder_ckpt"], "model_gen"), synth.hifigan_spec(voc_hp), strict=True)
     cfg = make_config(hp, voc_hp, max_slots=max_streams, max_ref_frames=max_ref_frames, device=device,
                       voc_precision=voc_precision, voc_tensor_cores=voc_tensor_cores)
@@ -142,6 +160,8 @@ class HifiGAN:
     def spec2wav(self, mel, **kwargs):
         mel = np.asarray(mel, dtype=np.float32)
         T, seg = mel.shape[0], self.eng.segment
+        if T == 0:
+            return np.zeros(0, np.float32)
         pad = (-T) % seg
         m = torch.from_numpy(np.pad(mel, ((0, pad), (0, 0)), mode="edge"))[None].to(self.device)
         self.eng.reset_slots([self.slot], PARTS_VOCODER)
@@ -169,8 +189,16 @@ class StreamingVoiceConversion:
         self.scheduler = ChunkScheduler(self.engine, max_streams)
         self.model = ConanView(self.engine, view_slots[:1])
         self.emformer = EmformerView(self.engine, view_slots[1:2])
-        HifiGAN._engine_factory = lambda: (self.engine, view_slots[2])
-        self.vocoder = get_vocoder_cls(hp["vocoder"])()
+        # the registry contract is a zero-argument constructor (base_vocoder.py:17 / inference/Conan.py:40-45); the engine is handed
+        # over through a factory that is in effect for the duration of this one constructor call only, so a second
+        # StreamingVoiceConversion cannot rebind the vocoder of the first
+        voc_cls = get_vocoder_cls(hp["vocoder"])
+        prev_factory = getattr(voc_cls, "_engine_factory", None)
+        voc_cls._engine_factory = lambda: (self.engine, view_slots[2])
+        try:
+            self.vocoder = voc_cls()
+        finally:
+            voc_cls._engine_factory = prev_factory
         self.frontend = GpuLogMel(hp)
         self._vocoder_warm_zero()
 
@@ -180,18 +208,22 @@ class StreamingVoiceConversion:
     def _wav_to_mel(self, path: str) -> np.ndarray:
         """inference/Conan.py:58-70: wav file -> clipped log-mel [T, 80], computed on the device (`conan_logmel`)."""
         wav = audio.load_wav(path, self.hparams["audio_sample_rate"])
+        if self.hparams.get("loud_norm", False):
+            wav = audio.loudness_normalize(wav, self.hparams["audio_sample_rate"])
         return self.frontend.offline(wav)[0].cpu().numpy()
 
     def infer_mels(self, ref_mel: np.ndarray, src_mel: np.ndarray):
         """The loop of infer_once on precomputed mels: (wav float32 [T*hop], mel float32 [T, 80])."""
         sid = self.scheduler.open(ref_mel)
-        self.scheduler.push(sid, src_mel)
-        self.scheduler.end(sid)
         wavs, mels = [], []
-        while not self.scheduler.finished(sid):
-            w, m, _ = self.scheduler.step()[sid]
-            wavs.append(w), mels.append(m)
-        self.scheduler.close(sid)
+        try:
+            self.scheduler.push(sid, src_mel)
+            self.scheduler.end(sid)
+            while not self.scheduler.finished(sid):
+                w, m, _ = self.scheduler.step()[sid]
+                wavs.append(w), mels.append(m)
+        finally:
+            self.scheduler.close(sid)              # the slot goes back to the pool even if a step raised
         if not wavs:
             return np.zeros(0, np.float32), np.zeros((0, 80), np.float32)
         return np.concatenate(wavs), np.concatenate(mels)

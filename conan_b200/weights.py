@@ -130,7 +130,7 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
     out["conan.l1.w"], out["conan.l1.b"] = c["l1.weight"], c["l1.bias"]
     # ---- vocoder
     v = sd_voc
-    wdt = torch.float16 if cfg.voc_precision else torch.float32
+    wdt = torch.float16 if cfg.voc_precision == 1 else torch.float32      # 2 (split): packed in fp32 here, split below
     w_pre = fold_weight_norm(v, "conv_pre.conv")
     if cfg.voc_use_tensor_cores:      # mel channels padded to a multiple of 32 (zero weights): conv_pre runs on the tcgen05 ring kernel
         pad = (-w_pre.shape[1]) % 32
@@ -155,6 +155,16 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
     wpost = fold_weight_norm(v, "conv_post.conv")                                # [1, ch, 7]
     out["voc.post.w"] = wpost[0].t().contiguous().reshape(-1)                    # [7, ch]
     out["voc.post.b"] = v["conv_post.conv.bias"]
+    if cfg.voc_precision == 2:
+        # fp32-grade tensor-core vocoder: every conv weight becomes the split-fp16 operand [W_hi | W_lo | W_hi] of 2^10 W
+        taps = {"voc.pre": 7}
+        for i in range(cfg.voc_n_ups):
+            taps[f"voc.up.{i}"] = cfg.voc_up_kernels[i]
+            for rr in range(cfg.voc_n_res):
+                for j in range(cfg.voc_n_dil):
+                    taps[f"voc.res.{i}.{rr}.c1.{j}"] = taps[f"voc.res.{i}.{rr}.c2.{j}"] = cfg.voc_res_kernels[rr]
+        for n, k in taps.items():
+            out[n + ".w"], out[n + ".b"] = split_linear(out[n + ".w"].float(), out[n + ".b"].float(), k)
     # ---- fp32-grade tensor-core mode: the per-chunk linear / conv contractions take split-fp16 weights
     if cfg.lin_use_tensor_cores and cfg.lin_fuse_ffn:
         # fused Emformer path: the attention kernel applies out_proj itself (fp32, 80 x 80): transposed weight [k][c] + bias
@@ -171,5 +181,11 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
         taps.update({f"conan.uv.{i}": cfg.predictor_kernel for i in range(5)})
         taps.update({f"conan.dec.{b_}.{s_}.conv": cfg.dec_kernel for b_ in range(cfg.dec_blocks) for s_ in range(2)})
         for n, k in taps.items():
+            out[n + ".w"], out[n + ".b"] = split_linear(out[n + ".w"].float(), out[n + ".b"].float(), k)
+    if cfg.ses_use_tensor_cores:
+        ses = {f"conan.genc.{b_}.{s_}.conv": 31 for b_ in range(5) for s_ in range(2)}
+        ses.update({f"conan.genc.{b_}.{s_}.pw": 1 for b_ in range(5) for s_ in range(2)})
+        ses["conan.genc.post"] = 3
+        for n, k in ses.items():
             out[n + ".w"], out[n + ".b"] = split_linear(out[n + ".w"].float(), out[n + ".b"].float(), k)
     return {k: t.detach().contiguous() for k, t in out.items()}

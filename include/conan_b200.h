@@ -30,6 +30,13 @@ extern "C" {
 
 #define CONAN_B200_ABI_VERSION 1
 
+/* The library is built with -fvisibility=hidden: only the entry points declared here are exported. */
+#if defined(__GNUC__)
+#define CONAN_API __attribute__((visibility("default")))
+#else
+#define CONAN_API
+#endif
+
 typedef struct conan_engine conan_engine_t;
 
 /* Hyper-parameters of the path.  Field names follow the reference's hparams keys
@@ -68,8 +75,10 @@ typedef struct conan_config {
   int32_t voc_res_dilations[8];   /* resblock_dilation_sizes[*] = 1,3,5 (same for every kernel size) */
   int32_t voc_n_dil;              /* 3 */
   /* numerics / engine selection */
-  int32_t voc_precision;          /* 0: fp32 operands (FFMA);  1: fp16 operands, fp32 accumulate */
-  int32_t voc_use_tensor_cores;   /* 1: tcgen05 implicit-GEMM kernels where eligible (needs voc_precision 1) */
+  int32_t voc_precision;          /* 0: fp32 operands (FFMA);  1: fp16 operands, fp32 accumulate (tcgen05 or FFMA);
+                                     2: split-fp16 operands (x_hi*W_hi + x_hi*W_lo + x_lo*W_hi), fp32 accumulate, tcgen05 only:
+                                        fp32-grade results (the reference arithmetic is fp32), needs voc_residual_from_ctx = 0 */
+  int32_t voc_use_tensor_cores;   /* 1: tcgen05 implicit-GEMM kernels where eligible (needs voc_precision 1 or 2) */
   int32_t voc_group;              /* streams per vocoder pass (L2 blocking); 0 = all at once */
   int32_t voc_residual_from_ctx;  /* 1: the vocoder's resblock residual x_j is recovered from the activated copy lrelu(x_j) that is the
                                      next conv's input anyway (inverse LeakyReLU), so no separate fp32 residual stream is written or
@@ -80,7 +89,9 @@ typedef struct conan_config {
                                      with the activations kept in shared memory (needs tensor cores + voc_residual_from_ctx) */
   int32_t lin_fuse_ffn;           /* 1: the Emformer position-wise FFN (80 -> 2048 -> 80) runs as one tcgen05 kernel, the hidden
                                      activation stays in shared memory (needs lin_use_tensor_cores) */
-  int32_t reserved[4];
+  int32_t ses_use_tensor_cores;   /* 1: session setup runs the style encoder's ConvBlocks (conv k31 256 -> 512, 1x1 512 -> 256: 95 % of the
+                                     12.8 GFLOP per session) on tcgen05 with split-fp16 operands; 0: fp32 FFMA */
+  int32_t reserved[3];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */
@@ -88,38 +99,38 @@ typedef struct conan_config {
 #define CONAN_DTYPE_F16 1
 #define CONAN_DTYPE_I32 2
 
-const char* conan_last_error(void);
-int conan_abi_version(void);
+CONAN_API const char* conan_last_error(void);
+CONAN_API int conan_abi_version(void);
 /* sizeof(conan_config_t) / sizeof(conan_conv_params_t) as compiled, so a foreign-language binding can
  * verify its struct layout before the first call */
-size_t conan_sizeof_config(void);
-size_t conan_sizeof_conv_params(void);
+CONAN_API size_t conan_sizeof_config(void);
+CONAN_API size_t conan_sizeof_conv_params(void);
 
 /* Replaces StreamingVoiceConversion.__init__ / _build_model / _build_vocoder /
  * _build_emformer (inference/Conan.py:26-52): create, bind every tensor the path
  * needs (names listed by conan_engine_weight_name), then finalize. */
-int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out);
-void conan_engine_destroy(conan_engine_t* eng);
-int conan_engine_num_weights(const conan_engine_t* eng);
+CONAN_API int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out);
+CONAN_API void conan_engine_destroy(conan_engine_t* eng);
+CONAN_API int conan_engine_num_weights(const conan_engine_t* eng);
 /* name / expected element count / dtype of weight #idx (for the host-side packer) */
-int conan_engine_weight_info(const conan_engine_t* eng, int idx, const char** name, size_t* numel, int* dtype);
+CONAN_API int conan_engine_weight_info(const conan_engine_t* eng, int idx, const char** name, size_t* numel, int* dtype);
 /* The engine keeps the pointer (no copy); the caller keeps the allocation alive. */
-int conan_engine_bind_weight(conan_engine_t* eng, const char* name, const void* data_dev, size_t numel, int dtype);
-int conan_engine_finalize(conan_engine_t* eng);
+CONAN_API int conan_engine_bind_weight(conan_engine_t* eng, const char* name, const void* data_dev, size_t numel, int dtype);
+CONAN_API int conan_engine_finalize(conan_engine_t* eng);
 /* bytes of device memory held by the state slab + scratch */
-size_t conan_engine_state_bytes(const conan_engine_t* eng);
+CONAN_API size_t conan_engine_state_bytes(const conan_engine_t* eng);
 
 /* Zero the resident state of `n` slots (stream start).  parts: bit0 Emformer, bit1 Conan
  * rings, bit2 vocoder rings.  Replaces `state = None` (inference/Conan.py:92) and the
  * zero left-padding every causal conv of the reference starts from. */
-int conan_slots_reset(conan_engine_t* eng, int n, const int32_t* slots_host, int parts, void* stream);
+CONAN_API int conan_slots_reset(conan_engine_t* eng, int n, const int32_t* slots_host, int parts, void* stream);
 
 /* Once per session: the reference-speech branch of Conan.forward
  * (modules/Conan/Conan.py:157-159,200-219 encode_spk_embed; :221-249 get_prosody up to
  * the aligner's keys; modules/Conan/prosody_util.py:183-200 LocalStyleAdaptor) for `n`
  * sessions whose reference mels all have `ref_frames` frames.  Caches style_embed and
  * the aligner K/V per slot.  ref_mel_dev: [n, ref_frames, n_mels] fp32. */
-int conan_session_open(conan_engine_t* eng, int n, const int32_t* slots_host, const float* ref_mel_dev,
+CONAN_API int conan_session_open(conan_engine_t* eng, int n, const int32_t* slots_host, const float* ref_mel_dev,
                        int ref_frames, void* stream);
 
 /* One streaming step of torchaudio Emformer.infer + proj + argmax for n streams
@@ -127,55 +138,55 @@ int conan_session_open(conan_engine_t* eng, int n, const int32_t* slots_host, co
  * laid out as the reference passes it (utterance rows first, look-ahead rows last).
  * Any of the outputs may be NULL.  enc [n,segment,dim], logits [n,segment,out_dim],
  * tokens [n,segment] int32. */
-int conan_emformer_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* chunk_dev,
+CONAN_API int conan_emformer_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* chunk_dev,
                         float* enc_out_dev, float* logits_out_dev, int32_t* tokens_out_dev, void* stream);
 
 /* Incremental Conan.forward(infer=True) on the newest `segment` tokens of each stream
  * (inference/Conan.py:131-145; modules/Conan/Conan.py:115-198).  tokens [n,segment] int32,
  * mel_out [n,segment,n_mels] fp32. */
-int conan_decoder_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const int32_t* tokens_dev,
+CONAN_API int conan_decoder_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const int32_t* tokens_dev,
                        float* mel_out_dev, void* stream);
 
 /* Incremental HifiGanGenerator.forward on the newest `segment` mel frames
  * (tasks/tts/vocoder_infer/hifigan.py:23-31, hifigan_causal.py:314-333).
  * mel [n,segment,n_mels] fp32 -> wav [n, segment*hop] fp32. */
-int conan_vocoder_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* mel_dev,
+CONAN_API int conan_vocoder_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* mel_dev,
                        float* wav_out_dev, void* stream);
 
 /* The whole chunk step (one iteration of the loop at inference/Conan.py:95-156) for n
  * ready streams packed into one launch sequence.  Outputs may be NULL except wav. */
-int conan_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* chunk_dev,
+CONAN_API int conan_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* chunk_dev,
                float* wav_out_dev, float* mel_out_dev, int32_t* tokens_out_dev, void* stream);
 
 /* Same, with HOST buffers (pinned or pageable): copies slot ids + mel chunks to the
  * device, runs the step, copies wav (and mel/tokens if non-NULL) back, and waits.
  * This is the call the reference-facing plugin makes per chunk step. */
-int conan_step_host(conan_engine_t* eng, int n, const int32_t* slot_ids_host, const float* chunk_host,
+CONAN_API int conan_step_host(conan_engine_t* eng, int n, const int32_t* slot_ids_host, const float* chunk_host,
                     float* wav_out_host, float* mel_out_host, int32_t* tokens_out_host, void* stream);
 
 /* Pipelined variant for a serving loop: submit enqueues the input copies and the step on `stream`, the result copies on an
  * engine-owned copy stream, and returns a ticket; the result copies of step i overlap the compute of step i+1.  At most two
  * steps may be in flight.  Every host buffer passed to a submit (pinned memory) must stay valid and untouched until its ticket
  * has been waited for: use two sets of chunk / result buffers, alternating. */
-int conan_step_host_submit(conan_engine_t* eng, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
+CONAN_API int conan_step_host_submit(conan_engine_t* eng, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
                            float* mel_out_host, int32_t* tokens_out_host, void* stream, int* ticket);
-int conan_step_host_wait(conan_engine_t* eng, int ticket);
+CONAN_API int conan_step_host_wait(conan_engine_t* eng, int ticket);
 
 /* kernels launched by this engine since creation (bench.py's gpu_launches claim) */
-uint64_t conan_engine_launch_count(const conan_engine_t* eng);
+CONAN_API uint64_t conan_engine_launch_count(const conan_engine_t* eng);
 
 /* Per-launch CUDA-event timing of the conv engines (measurement only: events are recorded on the
  * launching stream around every conv launch while enabled).  category 0 = FFMA, 1 = tcgen05 ring kernel
  * (fp16 operands), 2 = tcgen05 window kernel, 3 = tcgen05 ring kernel with split-fp16 operands.
  * profile_read synchronises the device and returns the summed kernel time, launch count, algorithmic
  * FLOPs (2*M*N*K) and algorithmic HBM bytes since profiling was (re-)enabled. */
-int conan_engine_set_profiling(conan_engine_t* eng, int enabled);
-int conan_engine_profile_read(conan_engine_t* eng, int category, double* ms, uint64_t* launches, double* flops, double* bytes);
+CONAN_API int conan_engine_set_profiling(conan_engine_t* eng, int enabled);
+CONAN_API int conan_engine_profile_read(conan_engine_t* eng, int category, double* ms, uint64_t* launches, double* flops, double* bytes);
 
 /* Debug/test access: copy a named internal per-slot tensor (fp32) of one slot to the
  * device buffer.  Returns the element count through *numel. Names: "style", "kv_cache",
  * "kpm", "emformer_past_len", "vq_index". */
-int conan_debug_read(conan_engine_t* eng, const char* name, int slot, float* out_dev, size_t capacity,
+CONAN_API int conan_debug_read(conan_engine_t* eng, const char* name, int slot, float* out_dev, size_t capacity,
                      size_t* numel, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -245,13 +256,13 @@ typedef struct conan_conv_params {
  * DFT basis [2*bins][taps*hop] fp32 (rows 0..bins-1 cos, bins..2*bins-1 -sin); mel_basis_t: [bins][n_mels] fp32.
  * mel_out [n_streams][n_frames][n_mels] = clip(log10(max(mel_basis . |DFT|, eps)), vmin, vmax).
  * spec_scratch: n_streams*n_frames*2*bins floats. */
-int conan_logmel(const float* wav_rows, int n_streams, int rows_per_stream, int hop, int taps, int row0, int n_frames,
+CONAN_API int conan_logmel(const float* wav_rows, int n_streams, int rows_per_stream, int hop, int taps, int row0, int n_frames,
                  const float* dft_w, int bins, const float* mel_basis_t, int n_mels, float eps, float vmin, float vmax,
                  float* spec_scratch, float* mel_out, void* stream);
 
 /* engine: 0 = FFMA (fp32 accumulate on CUDA cores, fp32 or fp16 operands),
  *         1 = tcgen05 tensor cores (fp16 operands, fp32 accumulate in TMEM). */
-int conan_conv_gemm(const conan_conv_params_t* p, int engine, void* stream);
+CONAN_API int conan_conv_gemm(const conan_conv_params_t* p, int engine, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,14 @@ def eng_fp16_ffma(state_dicts):
 
 
 @pytest.fixture(scope="module")
+def eng_split(state_dicts):
+    """fp32-grade tensor-core engine: split-fp16 operands everywhere (vocoder included)."""
+    e = _engine(state_dicts, voc_precision="split", voc_tensor_cores=True)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
 def eng_tc(state_dicts):
     e = _engine(state_dicts, voc_precision="fp16", voc_tensor_cores=True)
     yield e
@@ -288,10 +296,14 @@ def test_emformer_staggered_streams_match_independent_runs(state_dicts, eng_fp32
 # ------------------------------------------------------------------------------------------
 # Conan main model
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["eng_fp32", "eng_tc"])
 @pytest.mark.parametrize("t_ref", [150, 64, 9])
-def test_session_open_vs_oracle(state_dicts, eng_fp32, t_ref):
+def test_session_open_vs_oracle(state_dicts, which, request, t_ref):
+    """eng_fp32: the whole setup on the fp32 FFMA engine; eng_tc: the style encoder's ConvBlocks on tcgen05 with split-fp16
+    operands over sessions padded to a multiple of 32 rows (150 -> 160, 9 -> 32; 64 is exact)."""
     from oracle.incremental import ConanOracle
-    eng = eng_fp32
+    eng = request.getfixturevalue(which)
+    assert bool(eng.cfg.ses_use_tensor_cores) == (which == "eng_tc")
     B = 2
     ref = torch.stack([synth.synth_mel(t_ref, 11 + s) for s in range(B)])
     o = ConanOracle(state_dicts[0])
@@ -402,6 +414,29 @@ def test_vocoder_fp32_vs_oracle_and_golden(state_dicts, eng_fp32, golden_dir):
     assert np.abs(wav[0].numpy() - d["wav"]).max() < 1e-4
 
 
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+def test_vocoder_split_fp16_tensor_cores_is_fp32_grade(state_dicts, eng_split, golden_dir):
+    """voc_precision = 'split': every vocoder conv on tcgen05 with x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, fp32 residual stream.
+    Same tolerance as the fp32 FFMA engine: wav max-abs <= 1e-4 against the oracle AND against the unmodified reference."""
+    from oracle.incremental import HifiGanOracle
+    d = np.load(os.path.join(golden_dir, "vocoder_24f.npz"))
+    mel = torch.from_numpy(d["mel"])[None].repeat(2, 1, 1)
+    mel[1] = mel[1].flip(0)
+    o = HifiGanOracle(state_dicts[2])
+    o.reset(2)
+    with torch.no_grad():
+        ref = torch.cat([o.step(mel[:, i:i + 4]) for i in range(0, 24, 4)], 1)
+    l0 = eng_split.launch_count
+    wav = _run_vocoder(eng_split, mel, [7, 2])
+    assert eng_split.launch_count > l0
+    err = (wav - ref).abs().max().item()
+    print("vocoder split-fp16 max-abs vs oracle", err, "vs reference golden", np.abs(wav[0].numpy() - d["wav"]).max(),
+          "SNR_ac", snr_ac_db(d["wav"], wav[0].numpy()))
+    assert err < 1e-4
+    assert np.abs(wav[0].numpy() - d["wav"]).max() < 1e-4
+    assert snr_ac_db(d["wav"], wav[0].numpy()) > 80.0
+
+
 @pytest.mark.parametrize("which", ["eng_fp16_ffma", "eng_tc"])
 def test_vocoder_fp16_operands_snr(which, request, golden_dir):
     eng = request.getfixturevalue(which)
@@ -476,7 +511,8 @@ def _run_e2e(eng, ref, src, slots):
     return torch.cat(wavs, 1), torch.cat(mels, 1), torch.cat(toks, 1)
 
 
-@pytest.mark.parametrize("which,name", [("eng_fp32", "e2e_short"), ("eng_tc", "e2e_short"), ("eng_tc", "e2e_long")])
+@pytest.mark.parametrize("which,name", [("eng_fp32", "e2e_short"), ("eng_tc", "e2e_short"), ("eng_tc", "e2e_long"),
+                                        ("eng_split", "e2e_short"), ("eng_split", "e2e_long")])
 def test_end_to_end_vs_reference_golden(which, name, request, golden_dir):
     eng = request.getfixturevalue(which)
     d = np.load(os.path.join(golden_dir, name + ".npz"))
@@ -492,7 +528,7 @@ def test_end_to_end_vs_reference_golden(which, name, request, golden_dir):
     assert agree == 1.0
     assert mel_err <= MEL_TOL
     assert sa >= SNR_MIN_DB
-    if which == "eng_fp32":
+    if which in ("eng_fp32", "eng_split"):          # fp32-grade engines: CUDA-core fp32, and split-fp16 on the tensor cores
         assert np.abs(wav - d["wav"]).max() < 2e-4
 
 
@@ -626,11 +662,81 @@ def test_config3_full_pipeline_1024_streams_properties(state_dicts):
         wav, mel, tok = torch.cat(wavs, 1), torch.cat(mels, 1), torch.cat(toks, 1)
         for d in range(D):
             assert (wav[d::D] == wav[d:d + 1]).all() and (mel[d::D] == mel[d:d + 1]).all() and (tok[d::D] == tok[d:d + 1]).all()
+        # ... and the 16 distinct streams against the CPU oracle (lock-step batch of 16), not only replica equality
+        from oracle.incremental import StreamingOracle
+        o = StreamingOracle(*state_dicts)
+        wav_o, mel_o, tok_o = o.infer(ref[:D], src[:D])
+        assert torch.equal(tok[:D].long(), tok_o)
+        mel_err = (mel[:D] - mel_o).abs().max().item()
+        worst = min(snr_ac_db(wav_o[d].numpy(), wav[d].numpy()) for d in range(D))
+        print("1024 streams: mel max-abs vs oracle", mel_err, "worst wav SNR_ac over 16 distinct streams", worst)
+        assert mel_err <= MEL_TOL and worst >= SNR_MIN_DB
         single, mel1, tok1 = _run_e2e(eng, ref[3:4], src[3:4], [slots[0]])
         assert torch.equal(tok1[0], tok[3]) and torch.equal(mel1[0], mel[3, :mel1.shape[1]])
         assert torch.equal(single[0], wav[3, :single.shape[1]])
     finally:
         eng.close()
+
+
+def test_full_step_changing_ready_subsets_different_ages_and_recycled_slots(state_dicts, eng_tc):
+    """The packing path end to end (ChunkScheduler -> conan_step_host -> compact buffers + history gather / scatter of every
+    sub-model): the ready subset changes every step (frames arrive in uneven bursts), streams are opened at different times
+    with references of different lengths, finished streams are closed mid-run and their slots reused by new sessions while the
+    other streams keep running.  Every stream must equal its own single-stream CPU oracle run."""
+    from conan_b200.scheduler import ChunkScheduler
+    from oracle.incremental import StreamingOracle
+    eng = eng_tc
+    n_streams, n_slots = 7, 3                              # 7 sessions over 3 slots: every slot is recycled at least once
+    rng = np.random.default_rng(5)
+    T_ref = [40, 23, 64, 40, 9, 31, 50]
+    T_src = [26, 41, 18, 33, 22, 37, 14]
+    refs = [synth.synth_mel(T_ref[i], 900 + i) for i in range(n_streams)]
+    srcs = [synth.synth_mel(T_src[i], 950 + i) for i in range(n_streams)]
+    expect = []
+    for i in range(n_streams):
+        o = StreamingOracle(*state_dicts)
+        expect.append(o.infer(refs[i][None], srcs[i][None]))
+    sch = ChunkScheduler(eng, n_slots, capacity_frames=16)
+    waiting = list(range(n_streams))
+    live = {}                                              # stream index -> [sid, frames fed]
+    got = {i: ([], [], []) for i in range(n_streams)}
+    subsets, slots_used = set(), {}
+    for it in range(400):
+        while waiting and len(live) < n_slots and (it % 3 == 0 or not live):      # staggered admission
+            i = waiting.pop(0)
+            sid = sch.open(refs[i].numpy())
+            live[i] = [sid, 0]
+            slots_used.setdefault(sch.streams[sid].slot, []).append(i)
+        for i, st in live.items():                          # uneven arrivals: 0..7 frames per stream per iteration
+            n = int(rng.integers(0, 8))
+            n = min(n, T_src[i] - st[1])
+            if n:
+                sch.push(st[0], srcs[i][st[1]:st[1] + n].numpy())
+                st[1] += n
+            if st[1] == T_src[i] and not sch.streams[st[0]].ended:
+                sch.end(st[0])
+        out = sch.step()
+        if out:
+            subsets.add(tuple(sorted(out)))
+        by_sid = {st[0]: i for i, st in live.items()}
+        for sid, (w, m, t) in out.items():
+            i = by_sid[sid]
+            got[i][0].append(w), got[i][1].append(m), got[i][2].append(t)
+        for i in [i for i, st in live.items() if sch.finished(st[0])]:
+            sch.close(live.pop(i)[0])
+        if not waiting and not live:
+            break
+    assert not waiting and not live
+    assert len(subsets) >= 6 and any(len(v) >= 2 for v in slots_used.values())      # subsets really changed, slots really reused
+    for i in range(n_streams):
+        wav, mel, tok = np.concatenate(got[i][0]), np.concatenate(got[i][1]), np.concatenate(got[i][2])
+        wav_o, mel_o, tok_o = (x[0].numpy() for x in expect[i])
+        assert wav.shape == wav_o.shape and mel.shape == mel_o.shape
+        assert (tok == tok_o).all(), i
+        mel_err = np.abs(mel - mel_o).max()
+        sa = snr_ac_db(wav_o, wav)
+        print(f"stream {i} (T_ref {T_ref[i]}, T {T_src[i]}): mel max-abs {mel_err:.2e}, wav SNR_ac {sa:.1f} dB")
+        assert mel_err <= MEL_TOL and sa >= SNR_MIN_DB
 
 
 def test_fast_system_right_context_zero(state_dicts):

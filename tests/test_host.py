@@ -62,8 +62,37 @@ def test_checkpoint_layout_roundtrip_and_selection(tmp_path):
     with pytest.raises(AssertionError):
         ckpt.load_state_dict(str(tmp_path / "empty"), "model")
     assert ckpt.load_state_dict(str(tmp_path / "empty"), "model", force=False) is None
-    with pytest.raises(ValueError):
-        ckpt.filter_to_spec({"a.weight": torch.zeros(2, 2)}, [("a.weight", (3, 2), "x")], strict=False)
+
+
+def test_filter_to_spec_follows_load_state_dict_semantics(capsys):
+    """utils/commons/ckpt_utils.py:48-58: strict=False drops shape-mismatched keys (printing `| Unmatched keys:`) and lets
+    missing keys keep their initial value; strict=True raises like nn.Module.load_state_dict."""
+    spec = [("a.weight", (3, 2), "x"), ("b", (4,), "x")]
+    init = {"a.weight": torch.full((3, 2), 7.0), "b": torch.full((4,), 8.0)}
+    got = ckpt.filter_to_spec({"a.weight": torch.zeros(2, 2), "b": torch.ones(4), "extra": torch.zeros(1)}, spec, strict=False, defaults=init)
+    assert "| Unmatched keys:  a.weight (3, 2) (2, 2)" in capsys.readouterr().out
+    assert torch.equal(got["a.weight"], init["a.weight"]) and torch.equal(got["b"], torch.ones(4)) and "extra" not in got
+    got = ckpt.filter_to_spec({"b": torch.ones(4)}, spec, strict=False, defaults=init)           # missing key -> initial value
+    assert torch.equal(got["a.weight"], init["a.weight"])
+    with pytest.raises(KeyError):
+        ckpt.filter_to_spec({"b": torch.ones(4)}, spec, strict=False)                            # no initial values to keep
+    for bad in ({"a.weight": torch.zeros(2, 2), "b": torch.ones(4)}, {"b": torch.ones(4)},
+                {"a.weight": torch.zeros(3, 2), "b": torch.ones(4), "extra": torch.zeros(1)}):
+        with pytest.raises(RuntimeError):
+            ckpt.filter_to_spec(bad, spec, strict=True)
+
+
+def test_set_hparams_assigns_infer_debug_validate_unconditionally(tmp_path, monkeypatch):
+    """utils/commons/hparams.py:113-116: a saved checkpoints/<exp>/config.yaml cannot mask the flags."""
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("checkpoints/e")
+    (tmp_path / "checkpoints" / "e" / "config.yaml").write_text("infer: true\ndebug: true\na: 3\n")
+    (tmp_path / "c.yaml").write_text("a: 1\n")
+    cfg = hp_mod.set_hparams(config="c.yaml", exp_name="e", print_hparams=False, global_hparams=False)
+    assert cfg["a"] == 3 and cfg["infer"] is False and cfg["debug"] is False and cfg["validate"] is False
+    monkeypatch.setattr(sys, "argv", ["x", "--config", "c.yaml", "--exp_name", "e", "--infer", "--debug"])
+    cfg = hp_mod.set_hparams(print_hparams=False, global_hparams=False)
+    assert cfg["infer"] is True and cfg["debug"] is True and cfg["validate"] is False
 
 
 def test_weight_norm_folding_matches_torch():
@@ -110,6 +139,18 @@ def test_slaney_mel_basis_matches_torchaudio():
     mel = audio.wav2mel(wav)
     assert mel.shape == (16000 // 320 + 1, 80) and np.isfinite(mel).all()
     assert 8 <= int(mel[10].argmax()) <= 16                         # 440 Hz lands in the low mel bins
+
+
+def test_bs1770_loudness_normalisation():
+    """`loud_norm` branch of librosa_wav2spec (utils/audio/__init__.py:57-62).  BS.1770 anchor: a 997 Hz full-scale sine reads
+    -3.01 LUFS (the K-weighting is ~0 dB there), so amplitude 0.1 reads ~ -23.0."""
+    sr = 16000
+    x = (0.1 * np.sin(2 * np.pi * 997 * np.arange(3 * sr) / sr)).astype(np.float32)
+    assert abs(audio.integrated_loudness(x, sr) + 23.01) < 0.15
+    y = audio.loudness_normalize(x, sr)
+    assert abs(audio.integrated_loudness(y, sr) + 22.0) < 1e-3 and y.dtype == np.float32
+    loud = audio.loudness_normalize(x * 9.5, sr, target_lufs=0.0)           # would exceed full scale: peak-limited
+    assert abs(np.abs(loud).max() - 1.0) < 1e-6
 
 
 # ------------------------------------------------------------------ scheduler (fake engine)
@@ -178,6 +219,110 @@ def test_scheduler_packs_only_ready_streams_and_recycles_slots():
     assert sch.streams[d].slot == slot_a and eng.resets[-1] == [slot_a]
     sch.end(c)
     assert c not in sch.ready()                                        # ended with nothing buffered
+
+
+def test_scheduler_host_buffers_stay_bounded_over_a_long_stream():
+    """per-stream host memory must not grow with the stream's length (1e5 frames ~ 33 minutes of audio)."""
+    eng = FakeEngine()
+    sch = ChunkScheduler(eng, 2, capacity_frames=32)
+    sid = sch.open(np.zeros((10, 80), np.float32))
+    ring_bytes = sch.ring.nbytes
+    rng = np.random.default_rng(0)
+    fed = emitted = 0
+    first = None
+    while fed < 100_000:
+        f = rng.standard_normal((40, 80)).astype(np.float32)        # 40 frames per push: more than the ring has room for at times
+        if first is None:
+            first = f.copy()
+        sch.push(sid, f)
+        fed += 40
+        while sch.ready():
+            out = sch.step()[sid]
+            if emitted == 0:
+                assert np.array_equal(out[1], first[:4])
+            emitted += out[1].shape[0]
+        assert sch.buffered_frames(sid) <= sch.cap and sch.pending_frames(sid) < 40 + sch.rows
+    sch.end(sid)
+    while not sch.finished(sid):
+        emitted += sch.step()[sid][1].shape[0]
+    assert emitted == fed and sch.ring.nbytes == ring_bytes and not sch._backlog
+    assert len(eng.calls) == fed // 4
+
+
+def test_scheduler_whole_utterance_push_goes_through_the_backlog():
+    eng = FakeEngine()
+    sch = ChunkScheduler(eng, 1, capacity_frames=16)
+    src = synth.synth_mel(203, 7).numpy()
+    sid = sch.open(np.zeros((10, 80), np.float32))
+    sch.push(sid, src[:150])
+    sch.push(sid, src[150:])                                           # queued behind the backlog, order kept
+    sch.end(sid)
+    mels = []
+    while not sch.finished(sid):
+        mels.append(sch.step()[sid][1])
+    assert np.array_equal(np.concatenate(mels), src)
+
+
+class PipelinedFakeEngine(FakeEngine):
+    """step_host_submit / _wait with the result written only at wait time (like the real copy stream)."""
+
+    def __init__(self):
+        super().__init__()
+        self.pending = {}
+        self.n_sub = 0
+
+    def step_host_submit(self, slots, chunk, wav, mel, tok):
+        t = self.n_sub & 1
+        assert t not in self.pending
+        self.pending[t] = (slots, chunk, wav, mel, tok)
+        self.n_sub += 1
+        return t
+
+    def step_host_wait(self, t):
+        self.step_host(*self.pending.pop(t))
+
+
+def test_scheduler_vectorised_lockstep_and_pipelined_stepping():
+    eng = PipelinedFakeEngine()
+    S = 64
+    sch = ChunkScheduler(eng, S)
+    sids = sch.open_many([np.zeros((12, 80), np.float32)] * S)
+    slots = np.array([sch.streams[s].slot for s in sids])
+    src = np.stack([synth.synth_mel(46, 100 + i).numpy() for i in range(S)])            # [S, 46, 80]
+    got = {s: [] for s in sids}
+    prev, fed = None, 0
+    for step in range(11):
+        sch.push_many(slots, src[:, fed:fed + (6 if step == 0 else 4)])
+        fed += 6 if step == 0 else 4
+        t = sch.submit()
+        assert t is not None and len(sch._inflight) <= 2
+        if prev is not None:
+            r = sch.collect(prev)
+            assert len(r) == S and (r.emits == 4).all()
+            for i, s in enumerate(r.sids):
+                got[int(s)].append(r.mel[i].copy())
+        prev = t
+    r = sch.collect(prev)
+    for i, s in enumerate(r.sids):
+        got[int(s)].append(r.mel[i].copy())
+    for k, s in enumerate(sids):
+        assert np.array_equal(np.concatenate(got[s]), src[k, :44])
+    with pytest.raises(BufferError):
+        for _ in range(40):
+            sch.push_many(slots, src[:, :4])                           # nobody consumes: back-pressure
+
+
+def test_scheduler_failed_admission_releases_slots():
+    class Rejecting(FakeEngine):
+        def open_sessions(self, slots, ref):
+            raise RuntimeError("ref_frames outside [1, max_ref_frames]")
+    sch = ChunkScheduler(Rejecting(), 2)
+    with pytest.raises(RuntimeError):
+        sch.open_many([np.zeros((8, 80), np.float32), np.zeros((9, 80), np.float32)])
+    assert len(sch.free) == 2 and not sch.streams and not sch.active.any()
+    with pytest.raises(ValueError):
+        sch.open(np.zeros((8, 79), np.float32))                        # malformed reference: nothing allocated
+    assert len(sch.free) == 2
 
 
 # ------------------------------------------------------------------ multi-rank partition (gloo)
