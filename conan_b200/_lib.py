@@ -30,7 +30,7 @@ class ConanConfig(C.Structure):
         ("voc_res_dilations", C.c_int32 * 8), ("voc_n_dil", C.c_int32),
         ("voc_precision", C.c_int32), ("voc_use_tensor_cores", C.c_int32), ("voc_group", C.c_int32),
         ("voc_residual_from_ctx", C.c_int32), ("lin_use_tensor_cores", C.c_int32), ("voc_fuse_resblocks", C.c_int32), ("lin_fuse_ffn", C.c_int32),
-        ("ses_use_tensor_cores", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("ses_use_tensor_cores", C.c_int32), ("emformer_memory_size", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -72,6 +72,7 @@ SYMBOLS = {
     "conan_slots_reset": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     "conan_session_open": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
     "conan_emformer_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "conan_emformer_forward": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "conan_decoder_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "conan_vocoder_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "conan_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),

@@ -67,6 +67,11 @@ struct conan_engine {
   std::vector<float> postTapsHost;                 // host copy of conv_post's taps + bias (kernel-parameter fast path)
   bool ffnFused = false; float* eFFP = nullptr;    // fused FFN: partial outputs [split][rows][DP]
   std::vector<float*> eRing;
+  // generic step (memory bank M > 0, summary query, partial segments): its own work buffers with seg + rc + 1 rows per stream
+  int eM = 0;                                   // max_memory_size
+  float *gX = nullptr, *gQKV = nullptr, *gR1 = nullptr, *gR2 = nullptr, *gXNf = nullptr, *gMKV = nullptr, *gMEM[2] = {nullptr, nullptr};
+  Ctx gXN, gATT, gFN, gHF, gMB;
+  std::vector<float*> eBank;                    // [layer][slot, M, D] resident
   int* ePast = nullptr;
   int* TOK = nullptr;
   // ---- Conan chunk path
@@ -408,10 +413,25 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->eLOG, (size_t)S * seg * e->LP));
   TRY(alloc_ctx(e, &e->eXN, 0, rows, 0, DP, lt)); TRY(alloc_ctx(e, &e->eATT, 0, rows, 0, DP, lt));
   TRY(alloc_ctx(e, &e->eFN, 0, rows, 0, DP, lt)); TRY(alloc_ctx(e, &e->eHF, 0, rows, 0, c.emformer_ffn, lt));
-  e->ffnFused = e->lin_tc && c.lin_fuse_ffn && ffn_fused_eligible(DP, c.emformer_ffn, DP);
+  e->ffnFused = e->lin_tc && c.lin_fuse_ffn && ffn_fused_eligible(DP, c.emformer_ffn, DP);   // M = 0 fast path only; M > 0 steps take the generic path
   if (e->ffnFused) TRY(dalloc(e, &e->eFFP, (size_t)4 * S * rows * DP));
   e->eRing.resize(c.emformer_layers);
   for (int l = 0; l < c.emformer_layers; ++l) TRY(dalloc(e, &e->eRing[l], (size_t)S * e->ring_rows * 2 * D));
+  {
+    // generic-step buffers (allocated for every engine: a full-utterance forward with a partial last segment uses them at M = 0 too)
+    const int er = rows + 1, M = e->eM;
+    TRY(dalloc(e, &e->gX, (size_t)S * er * DP)); TRY(dalloc(e, &e->gQKV, (size_t)S * er * e->QP));
+    TRY(dalloc(e, &e->gR1, (size_t)S * er * DP)); TRY(dalloc(e, &e->gR2, (size_t)S * er * DP));
+    TRY(dalloc(e, &e->gXNf, (size_t)S * er * DP));
+    TRY(alloc_ctx(e, &e->gXN, 0, er, 0, DP, lt)); TRY(alloc_ctx(e, &e->gATT, 0, er, 0, DP, lt));
+    TRY(alloc_ctx(e, &e->gFN, 0, er, 0, DP, lt)); TRY(alloc_ctx(e, &e->gHF, 0, er, 0, c.emformer_ffn, lt));
+    TRY(dalloc(e, &e->gMEM[0], (size_t)S * D)); TRY(dalloc(e, &e->gMEM[1], (size_t)S * D));
+    if (M > 0) {
+      TRY(alloc_ctx(e, &e->gMB, 0, M, 0, DP, lt)); TRY(dalloc(e, &e->gMKV, (size_t)S * M * e->QP));
+      e->eBank.resize(c.emformer_layers);
+      for (int l = 0; l < c.emformer_layers; ++l) TRY(dalloc(e, &e->eBank[l], (size_t)S * M * D));
+    }
+  }
   TRY(dalloc(e, &e->ePast, (size_t)S)); TRY(dalloc(e, &e->TOK, (size_t)S * seg));
   // ---- Conan chunk path
   TRY(alloc_ctx(e, &e->cC, c.content_kernel - 1, seg, 0, H, lt));
@@ -516,6 +536,7 @@ int allocate_state(conan_engine* e) {
     for (int l = 0; l < c.emformer_layers; ++l)
       ez.push_back(ZeroDesc{e->eRing[l], (long long)e->ring_rows * 2 * D * 4, (long long)e->ring_rows * 2 * D * 4});
     ez.push_back(ZeroDesc{e->ePast, 4, 4});
+    for (size_t l = 0; l < e->eBank.size(); ++l) ez.push_back(ZeroDesc{e->eBank[l], (long long)e->eM * D * 4, (long long)e->eM * D * 4});
     HistDesc* dummy = nullptr; int nd = 0;
     TRY(build_tables({}, {}, &dummy, &nd, &e->zeroEmf, &e->nZeroEmf, ez));
   }
@@ -574,6 +595,9 @@ int allocate_state(conan_engine* e) {
   return 0;
 }
 
+int emformer_step_generic(conan_engine* e, int n, const int* ids, const float* src, long long src_stride, int utt_row0, int rc_row0,
+                          int n_utt, float* enc_out, float* logits_out, int* tokens_out, int out_row0, int out_nrows, cudaStream_t st);
+
 // ============================================================================ Emformer step
 int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, float* enc_out, float* logits_out,
                   int* tokens_out, cudaStream_t st) {
@@ -581,6 +605,8 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
   const int D = c.emformer_dim, DP = e->DP, QP = e->QP, LP = e->LP, seg = c.segment, rc = c.right_context, rows = seg + rc,
             F = c.emformer_ffn;
   const bool tc = e->lin_tc;
+  if (e->eM > 0)        // memory bank: generic step; the chunk is [utt (seg) | look-ahead (rc)] rows per stream
+    return emformer_step_generic(e, n, ids, chunk, (long long)rows * D, 0, seg, seg, enc_out, logits_out, tokens_out, 0, seg, st);
   TRY(launch_emformer_assemble(chunk, e->eX, DP, n, nullptr, seg, rc, D, st));
   for (int l = 0; l < c.emformer_layers; ++l) {
     std::string p = "emf." + std::to_string(l) + ".";
@@ -655,6 +681,82 @@ int emformer_step(conan_engine* e, int n, const int* ids, const float* chunk, fl
   if (enc_out) TRY(launch_copy_rows_out(e->eX, (long long)rows * DP, DP, rc, enc_out, n, nullptr, seg, D, st));
   if (logits_out)
     TRY(launch_copy_rows_out(e->eLOG, (long long)seg * LP, LP, 0, logits_out, n, nullptr, seg, c.emformer_output_dim, st));
+  return 0;
+}
+
+// ============================================================================ Emformer step, generic form
+// Memory bank (M > 0), summary query, partial segments (n_utt < seg): see emformer_mem.cu.  `src` holds, for stream i, the
+// utterance rows at src[i*src_stride + (utt_row0 + t)*D] and the look-ahead rows at src[i*src_stride + (rc_row0 + q)*D].
+// Outputs (any may be null) are written for the n_utt real rows at row offset out_row0 of buffers with out_nrows rows per stream.
+int emformer_step_generic(conan_engine* e, int n, const int* ids, const float* src, long long src_stride, int utt_row0, int rc_row0,
+                          int n_utt, float* enc_out, float* logits_out, int* tokens_out, int out_row0, int out_nrows, cudaStream_t st) {
+  const conan_config_t& c = e->cfg;
+  const int D = c.emformer_dim, DP = e->DP, QP = e->QP, LP = e->LP, seg = c.segment, rc = c.right_context, rows = seg + rc, er = rows + 1,
+            F = c.emformer_ffn, M = e->eM;
+  const bool tc = e->lin_tc;
+  TRY(launch_emformer_assemble_generic(src, src_stride, utt_row0, rc_row0, e->gX, DP, M > 0 ? e->gMEM[0] : nullptr, n, seg, n_utt, rc, D, st));
+  int cur = 0;
+  for (int l = 0; l < c.emformer_layers; ++l) {
+    std::string p = "emf." + std::to_string(l) + ".";
+    // input norm over the rc + seg real rows (TA:427-434); an fp32 copy feeds the summary mean
+    TRY(ln_rows(e->gX, er, DP, 0, e->gXN.new_rows(), e->F(p + "ln_in.g"), e->F(p + "ln_in.b"), D, rows, n, st, nullptr, nullptr, 0, nullptr,
+                nullptr, view_f32(e->gXNf, (long long)er * DP, DP)));
+    if (M > 0)
+      TRY(launch_emformer_mem_prepare(e->gXNf, DP, e->gXN.new_rows(), e->eBank[l], e->gMB.new_rows(), n, ids, seg, n_utt, rc, D, M, st));
+    auto q = conv_on_ctx(e, e->gXN, 1, 1, e->P(p + "qkv.w"), e->F(p + "qkv.b"), QP, n);       // Q | K | V of [rc | utt | summary]
+    out_rows(q, e->gQKV, er, QP);
+    TRY(run_conv(e, q, st, tc));
+    if (M > 0) {
+      auto mk = conv_on_ctx(e, e->gMB, 1, 1, e->P(p + "qkv.w"), e->F(p + "qkv.b"), QP, n);    // K | V of the bank rows (their Q columns are unused)
+      out_rows(mk, e->gMKV, M, QP);
+      TRY(run_conv(e, mk, st, tc));
+    }
+    TRY(launch_emformer_attention_mem(e->gQKV, M > 0 ? e->gMKV : nullptr, e->eRing[l], e->ePast, e->gATT.new_rows(), n, ids, seg, n_utt, rc,
+                                      c.left_context, e->ring_rows, D, c.emformer_heads, QP, M, st));
+    auto o = conv_on_ctx(e, e->gATT, 1, 1, e->P(p + "out.w"), e->F(p + "out.b"), DP, n);      // out_proj; + residual (the summary row's is 0)
+    out_rows(o, e->gR1, er, DP); res_rows(o, e->gX, er, DP);
+    TRY(run_conv(e, o, st, tc));
+    if (M > 0) {
+      TRY(launch_emformer_mem_update(e->gR1, DP, e->gMEM[cur], e->gMEM[cur ^ 1], e->eBank[l], n, ids, seg, rc, D, M, st));
+      cur ^= 1;
+    }
+    TRY(ln_rows(e->gR1, er, DP, 0, e->gFN.new_rows(), e->F(p + "ffn_ln.g"), e->F(p + "ffn_ln.b"), D, rows, n, st));
+    auto f1 = conv_on_ctx(e, e->gFN, 1, 1, e->P(p + "ffn1.w"), e->F(p + "ffn1.b"), F, n);
+    out2_ctx(f1, e->gHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
+    TRY(run_conv(e, f1, st, tc));
+    auto f2 = conv_on_ctx(e, e->gHF, 1, 1, e->P(p + "ffn2.w"), e->F(p + "ffn2.b"), DP, n);
+    out_rows(f2, e->gR2, er, DP); res_rows(f2, e->gR1, er, DP);
+    TRY(run_conv(e, f2, st, tc));
+    // output norm over the real rows -> next layer's input (row `rows` of gX stays zero: the summary has no residual)
+    const bool last = (l == c.emformer_layers - 1);
+    TRY(ln_rows(e->gR2, er, DP, 0, view_f32(e->gX, (long long)er * DP, DP), e->F(p + "ln_out.g"), e->F(p + "ln_out.b"), D, rows, n, st,
+                nullptr, nullptr, 0, nullptr, nullptr, last ? e->gXN.new_rows() : RowView{}));
+  }
+  TRY(launch_advance_past_len_by(e->ePast, n, ids, n_utt, st));
+  auto pj = conv_on_ctx(e, e->gXN, 1, 1, e->P("emf.proj.w"), e->F("emf.proj.b"), LP, n, true, rc, seg);   // utterance rows
+  out_rows(pj, e->eLOG, seg, LP);
+  TRY(run_conv(e, pj, st, tc));
+  // tokens of the real rows only, straight into the caller's layout
+  if (tokens_out || n_utt == seg) {
+    if (n_utt == seg && out_nrows == seg && out_row0 == 0) {
+      TRY(launch_argmax_rows(e->eLOG, LP, e->TOK, tokens_out, n, seg, c.emformer_output_dim, st));
+    } else {
+      TRY(launch_argmax_rows(e->eLOG, LP, e->TOK, nullptr, n, seg, c.emformer_output_dim, st));
+      if (tokens_out)
+        CONAN_CUDA_OK(cudaMemcpy2DAsync(tokens_out + out_row0, (size_t)out_nrows * 4, e->TOK, (size_t)seg * 4, (size_t)n_utt * 4, n,
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (enc_out)
+    CONAN_CUDA_OK(cudaMemcpy2DAsync(enc_out + (size_t)out_row0 * D, (size_t)out_nrows * D * 4, e->gX + (size_t)rc * DP, (size_t)er * DP * 4,
+                                    (size_t)n_utt * D * 4, n, cudaMemcpyDeviceToDevice, st));
+  if (logits_out) {
+    // logits rows are LP wide in the work buffer, out_dim wide in the caller's
+    for (int t = 0; t < n_utt; ++t)
+      CONAN_CUDA_OK(cudaMemcpy2DAsync(logits_out + (size_t)(out_row0 + t) * c.emformer_output_dim, (size_t)out_nrows * c.emformer_output_dim * 4,
+                                      e->eLOG + (size_t)t * LP, (size_t)seg * LP * 4, (size_t)c.emformer_output_dim * 4, n,
+                                      cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 
@@ -986,6 +1088,11 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
   if (cfg->abi_version != CONAN_B200_ABI_VERSION) { set_error("ABI version mismatch"); return 1; }
   if (cfg->max_slots <= 0 || cfg->max_ref_frames <= 0) { set_error("max_slots and max_ref_frames must be positive"); return 1; }
   if (cfg->voc_n_ups > 8 || cfg->voc_n_res > 4 || cfg->voc_n_dil > 4 || cfg->dec_blocks > 8) { set_error("config above compiled limits"); return 1; }
+  if (cfg->emformer_memory_size < 0 || cfg->emformer_memory_size > 8 ||
+      cfg->emformer_memory_size + cfg->right_context + cfg->left_context + cfg->segment > 64) {
+    set_error("emformer_memory_size must be in [0, 8] and memory + contexts + segment at most 64 keys");
+    return 1;
+  }
   if (cfg->voc_precision < 0 || cfg->voc_precision > 2) { set_error("voc_precision must be 0 (fp32), 1 (fp16 operands) or 2 (split fp16 operands)"); return 1; }
   if (cfg->voc_use_tensor_cores && !cfg->voc_precision) { set_error("voc_use_tensor_cores requires voc_precision 1 (fp16 operands) or 2 (split fp16 operands)"); return 1; }
   if (cfg->voc_precision == 2 && (!cfg->voc_use_tensor_cores || cfg->voc_residual_from_ctx || cfg->voc_fuse_resblocks)) {
@@ -1008,6 +1115,7 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
   e->tp_max = (cfg->max_ref_frames - 1) / 4 + 1;
   e->lin_tc = cfg->lin_use_tensor_cores != 0;
   e->ses_tc = cfg->ses_use_tensor_cores != 0;
+  e->eM = cfg->emformer_memory_size;
   declare_weights(e);
   *out = e;
   return 0;
@@ -1077,7 +1185,8 @@ int conan_slots_reset(conan_engine_t* e, int n, const int32_t* slots_host, int p
   if (parts & 1) TRY(launch_zero_slots(e->zeroEmf, e->nZeroEmf, n, e->hIdsSmall, st));
   if (parts & 2) TRY(launch_zero_slots(e->zeroConan, e->nZeroConan, n, e->hIdsSmall, st));
   if (parts & 4) TRY(launch_zero_slots(e->zeroVoc, e->nZeroVoc, n, e->hIdsSmall, st));
-  CONAN_CUDA_OK(cudaStreamSynchronize(st));     // hIdsSmall is reused by the next call
+  // no synchronisation: the id copy above is stream-ordered (a pageable source is staged before cudaMemcpyAsync returns; a
+  // page-locked one must stay valid until the stream reaches this call), and so is the reuse of hIdsSmall by the next call
   return 0;
 }
 
@@ -1089,8 +1198,9 @@ int conan_session_open(conan_engine_t* e, int n, const int32_t* slots_host, cons
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < n; g += e->SB) {
     int nb = std::min(e->SB, n - g);
+    // stream-ordered, no host synchronisation: the next batch's copy into qSlots and its use of the scratch buffers queue
+    // behind this batch on `st` (a serving loop opens sessions between chunk steps without stalling the host)
     TRY(session_open_batch(e, nb, slots_host + g, ref_mel_dev + (size_t)g * ref_frames * e->cfg.n_mels, ref_frames, st));
-    CONAN_CUDA_OK(cudaStreamSynchronize(st));   // qSlots / scratch are reused by the next batch
   }
   return 0;
 }
@@ -1100,6 +1210,50 @@ int conan_emformer_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, c
   if (check_ready(e)) return 1;
   if (n < 0 || n > e->S || !slot_ids_dev || !chunk_dev) { set_error("bad arguments to conan_emformer_step"); return 1; }
   return emformer_step(e, n, slot_ids_dev, chunk_dev, enc_out_dev, logits_out_dev, tokens_out_dev, (cudaStream_t)stream);
+}
+
+int conan_emformer_forward(conan_engine_t* e, int n, const int32_t* slots_host, const float* input_dev, int frames, float* enc_out_dev,
+                           float* logits_out_dev, int32_t* tokens_out_dev, void* stream) {
+  if (check_ready(e)) return 1;
+  if (n <= 0) return 0;
+  const conan_config_t& c = e->cfg;
+  const int seg = c.segment, rc = c.right_context, D = c.emformer_dim, T = frames - rc;
+  if (n > e->S || !slots_host || !input_dev || T < 1) { set_error("bad arguments to conan_emformer_forward (needs frames > right_context)"); return 1; }
+  if (check_ids_host(e, n, slots_host, "conan_emformer_forward")) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  CONAN_CUDA_OK(cudaMemcpyAsync(e->hIds, slots_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  TRY(launch_zero_slots(e->zeroEmf, e->nZeroEmf, n, e->hIds, st));
+  // segment i: utterance rows [i*seg, min((i+1)*seg, T)); its look-ahead block is the rc rows after it, the last segment's the
+  // rc rows at the end of the input (_gen_right_context, TA:619-628)
+  for (int t0 = 0; t0 < T; t0 += seg) {
+    const int n_utt = std::min(seg, T - t0);
+    const int rc_row0 = t0 + seg < T ? t0 + seg : T;
+    if (e->eM == 0 && n_utt == seg) {
+      // whole segment, no memory: the fused M = 0 step on a gathered [utt | rc] chunk
+      for (int q = 0; q < 2; ++q)
+        CONAN_CUDA_OK(cudaMemcpy2DAsync(e->hChunk + (size_t)(q ? seg : 0) * D, (size_t)(seg + rc) * D * 4,
+                                        input_dev + (size_t)(q ? rc_row0 : t0) * D, (size_t)frames * D * 4, (size_t)(q ? rc : seg) * D * 4, n,
+                                        cudaMemcpyDeviceToDevice, st));
+      TRY(emformer_step(e, n, e->hIds, e->hChunk, nullptr, nullptr, nullptr, st));
+      // rows of the step's work buffers (eX: [rc | utt] rows of DP floats; eLOG: seg rows of LP floats) -> the caller's layout
+      const int rows = seg + rc, OD = c.emformer_output_dim;
+      for (int t = 0; t < seg; ++t) {
+        if (enc_out_dev)
+          CONAN_CUDA_OK(cudaMemcpy2DAsync(enc_out_dev + (size_t)(t0 + t) * D, (size_t)T * D * 4, e->eX + (size_t)(rc + t) * e->DP,
+                                          (size_t)rows * e->DP * 4, (size_t)D * 4, n, cudaMemcpyDeviceToDevice, st));
+        if (logits_out_dev)
+          CONAN_CUDA_OK(cudaMemcpy2DAsync(logits_out_dev + (size_t)(t0 + t) * OD, (size_t)T * OD * 4, e->eLOG + (size_t)t * e->LP,
+                                          (size_t)seg * e->LP * 4, (size_t)OD * 4, n, cudaMemcpyDeviceToDevice, st));
+      }
+      if (tokens_out_dev)
+        CONAN_CUDA_OK(cudaMemcpy2DAsync(tokens_out_dev + t0, (size_t)T * 4, e->TOK, (size_t)seg * 4, (size_t)seg * 4, n,
+                                        cudaMemcpyDeviceToDevice, st));
+    } else {
+      TRY(emformer_step_generic(e, n, e->hIds, input_dev, (long long)frames * D, t0, rc_row0, n_utt, enc_out_dev, logits_out_dev,
+                                tokens_out_dev, t0, T, st));
+    }
+  }
+  return 0;
 }
 
 int conan_decoder_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const int32_t* tokens_dev, float* mel_out_dev, void* stream) {

@@ -64,6 +64,18 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
                               const int* slot_ids, int seg, int rc, int lc, int ring_rows, int D, int heads, int ld_qkv,
                               cudaStream_t st, const EmfAttnEpilogue* ep = nullptr);
 int launch_advance_past_len(int* past_len, int n, const int* slot_ids, int seg, cudaStream_t st);
+// generic step (emformer_mem.cu): memory bank M > 0, summary query, partial segments.  Work buffers hold seg + rc + 1 rows
+// per stream: [rc | utt | summary].
+int launch_emformer_assemble_generic(const float* src, long long stream_stride, int utt_row0, int rc_row0, float* X, int ldx,
+                                     float* mem0, int n, int seg, int n_utt, int rc, int D, cudaStream_t st);
+int launch_emformer_mem_prepare(const float* xnf, int ld, RowView xn, const float* bank, RowView mb, int n, const int* slot_ids,
+                                int seg, int n_utt, int rc, int D, int M, cudaStream_t st);
+int launch_emformer_mem_update(const float* r1, int ld, const float* mem_in, float* mem_out, float* bank, int n, const int* slot_ids,
+                               int seg, int rc, int D, int M, cudaStream_t st);
+int launch_emformer_attention_mem(const float* qkv, const float* memkv, float* ring, const int* past_len, RowView att, int n,
+                                  const int* slot_ids, int seg, int n_utt, int rc, int lc, int ring_rows, int D, int heads, int ldq,
+                                  int M, cudaStream_t st);
+int launch_advance_past_len_by(int* past_len, int n, const int* slot_ids, int by, cudaStream_t st);
 int launch_argmax_rows(const float* logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C, cudaStream_t st);
 int launch_copy_rows_out(const float* src_slot, long long slot_stride, int row_stride, int row0, float* dst, int n,
                          const int* slot_ids, int rows, int C, cudaStream_t st);

@@ -22,7 +22,8 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
                 max_ref_frames: int = 512, device: int = 0, voc_precision: str = "fp16",
                 voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None,
                 voc_residual_from_ctx: Optional[bool] = None, voc_fuse_resblocks: Optional[bool] = None,
-                lin_fuse_ffn: Optional[bool] = None, ses_tensor_cores: Optional[bool] = None) -> _lib.ConanConfig:
+                lin_fuse_ffn: Optional[bool] = None, ses_tensor_cores: Optional[bool] = None,
+                emformer_memory_size: Optional[int] = None) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -80,11 +81,31 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     cfg.lin_fuse_ffn = int(bool(cfg.lin_use_tensor_cores) if lin_fuse_ffn is None else (bool(lin_fuse_ffn) and bool(cfg.lin_use_tensor_cores)))
     # session setup: the style encoder (95 % of the setup FLOPs) on the tensor cores, same split-fp16 operand format
     cfg.ses_use_tensor_cores = int(bool(cfg.lin_use_tensor_cores) if ses_tensor_cores is None else bool(ses_tensor_cores))
+    # torchaudio Emformer max_memory_size: the reference never passes it (modules/Emformer/emformer.py:14-22 -> 0); an
+    # `emformer_memory_size` hparam / argument enables the memory bank for checkpoints trained with one
+    cfg.emformer_memory_size = int(hp.get("emformer_memory_size", 0) if emformer_memory_size is None else emformer_memory_size)
     return cfg
 
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+_PACK_CACHE: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+
+def _packed_weights(sd_conan, sd_emformer, sd_voc, cfg):
+    """pack_engine_weights memoised on the state-dict objects and the config fields the packing depends on (a process that
+    builds several engines over the same checkpoints -- bench.py's sweeps, the test suite -- packs them once)."""
+    key = (id(sd_conan), id(sd_emformer), id(sd_voc), cfg.voc_precision, cfg.voc_use_tensor_cores, cfg.lin_use_tensor_cores,
+           cfg.lin_fuse_ffn, cfg.ses_use_tensor_cores, cfg.max_ref_frames, cfg.emformer_layers, cfg.right_context)
+    hit = _PACK_CACHE.get(key)
+    if hit is None or hit[0] is not sd_conan:
+        if len(_PACK_CACHE) >= 4:
+            _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
+        hit = (sd_conan, pack_engine_weights(sd_conan, sd_emformer, sd_voc, cfg))
+        _PACK_CACHE[key] = hit
+    return hit[1]
 
 
 class Engine:
@@ -100,7 +121,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.lib.conan_engine_create(C.byref(cfg), C.byref(h)), "engine_create")
         self.h = h
-        packed = pack_engine_weights(sd_conan, sd_emformer, sd_voc, cfg)
+        packed = _packed_weights(sd_conan, sd_emformer, sd_voc, cfg)
         self._weights = {}
         nw = self.lib.conan_engine_num_weights(self.h)
         name, numel, dtype = C.c_char_p(), C.c_size_t(), C.c_int()
@@ -177,6 +198,23 @@ class Engine:
         logits = torch.empty(n, self.segment, self.cfg.emformer_output_dim, device=self.device) if want_logits else None
         _lib.check(self.lib.conan_emformer_step(self.h, n, _ptr(ids), _ptr(chunk), _ptr(enc), _ptr(logits), _ptr(tokens), self._stream()), "emformer_step")
         return tokens, enc, logits
+
+    def emformer_forward(self, slots: Sequence[int], inp: torch.Tensor, want_enc=True, want_logits=False, want_tokens=False):
+        """Full-utterance forward (EmformerDistillModel.forward / torchaudio Emformer.forward): inp [n, T + rc, dim], the
+        utterance right-padded with the look-ahead frames -> (enc [n, T, dim], logits [n, T, out_dim], tokens [n, T]).
+        Resets the Emformer state of `slots`."""
+        n, frames, D = inp.shape
+        rc = self.rows_in - self.segment
+        assert n == len(slots) and D == self.cfg.emformer_dim and frames > rc
+        inp = inp.to(self.device, torch.float32).contiguous()
+        T = frames - rc
+        enc = torch.empty(n, T, D, device=self.device) if want_enc else None
+        logits = torch.empty(n, T, self.cfg.emformer_output_dim, device=self.device) if want_logits else None
+        tokens = torch.empty(n, T, dtype=torch.int32, device=self.device) if want_tokens else None
+        arr, p = self._host_ids(slots)
+        _lib.check(self.lib.conan_emformer_forward(self.h, n, p, _ptr(inp), frames, _ptr(enc), _ptr(logits), _ptr(tokens), self._stream()),
+                   "emformer_forward")
+        return enc, logits, tokens
 
     def decoder_step(self, ids: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
         n = ids.numel()

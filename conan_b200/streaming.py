@@ -98,6 +98,17 @@ class _EmformerCore:
         _, enc, _ = self.eng.emformer_step(ids, chunk, want_enc=True)
         return enc, torch.clamp(lengths - (self.eng.rows_in - self.eng.segment), min=0), states
 
+    def forward(self, input: torch.Tensor, lengths: torch.Tensor):
+        """torchaudio Emformer.forward (TA:709-743): input [B, T + rc, D] right-padded with the look-ahead frames ->
+        (output [B, T, D], lengths).  Every batch element is taken at full length (the reference's callers pass full lengths)."""
+        B = input.shape[0]
+        if B > len(self.pool):
+            raise RuntimeError("not enough free slots for a full-utterance forward")
+        enc, _, _ = self.eng.emformer_forward(self.pool[:B], input)
+        return enc, lengths
+
+    __call__ = forward
+
 
 class EmformerView:
     """Stands in for modules/Emformer/emformer.py::EmformerDistillModel on the inference path."""
@@ -108,6 +119,13 @@ class EmformerView:
         self.mode = None
         self.segment_length = eng.segment
         self.right_context_len = eng.rows_in - eng.segment
+
+    def forward(self, mel_input: torch.Tensor, lengths: torch.Tensor):
+        """EmformerDistillModel.forward (modules/Emformer/emformer.py:31-47): (proj(emformer(mel_input, lengths)), lengths)."""
+        output, lengths = self.emformer(mel_input, lengths)
+        return self.proj(output), lengths
+
+    __call__ = forward
 
     def proj(self, x: torch.Tensor) -> torch.Tensor:
         """Linear(80 -> emformer_output_dim) through the FFMA conv-GEMM operator."""

@@ -91,7 +91,9 @@ typedef struct conan_config {
                                      activation stays in shared memory (needs lin_use_tensor_cores) */
   int32_t ses_use_tensor_cores;   /* 1: session setup runs the style encoder's ConvBlocks (conv k31 256 -> 512, 1x1 512 -> 256: 95 % of the
                                      12.8 GFLOP per session) on tcgen05 with split-fp16 operands; 0: fp32 FFMA */
-  int32_t reserved[3];
+  int32_t emformer_memory_size;   /* torchaudio Emformer max_memory_size M (0 in the reference config, modules/Emformer/emformer.py:14-22):
+                                     M > 0 keeps a bank of the last M memory vectors per layer and stream and adds the summary query */
+  int32_t reserved[2];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */
@@ -122,14 +124,16 @@ CONAN_API size_t conan_engine_state_bytes(const conan_engine_t* eng);
 
 /* Zero the resident state of `n` slots (stream start).  parts: bit0 Emformer, bit1 Conan
  * rings, bit2 vocoder rings.  Replaces `state = None` (inference/Conan.py:92) and the
- * zero left-padding every causal conv of the reference starts from. */
+ * zero left-padding every causal conv of the reference starts from.  Stream-ordered; slots_host is read before the call
+ * returns when it is pageable memory (page-locked memory must stay valid until the stream reaches this call). */
 CONAN_API int conan_slots_reset(conan_engine_t* eng, int n, const int32_t* slots_host, int parts, void* stream);
 
 /* Once per session: the reference-speech branch of Conan.forward
  * (modules/Conan/Conan.py:157-159,200-219 encode_spk_embed; :221-249 get_prosody up to
  * the aligner's keys; modules/Conan/prosody_util.py:183-200 LocalStyleAdaptor) for `n`
  * sessions whose reference mels all have `ref_frames` frames.  Caches style_embed and
- * the aligner K/V per slot.  ref_mel_dev: [n, ref_frames, n_mels] fp32. */
+ * the aligner K/V per slot.  ref_mel_dev: [n, ref_frames, n_mels] fp32.  Stream-ordered, does not synchronise: ref_mel_dev
+ * must stay valid until the stream has passed this call (slots_host as for conan_slots_reset). */
 CONAN_API int conan_session_open(conan_engine_t* eng, int n, const int32_t* slots_host, const float* ref_mel_dev,
                        int ref_frames, void* stream);
 
@@ -140,6 +144,15 @@ CONAN_API int conan_session_open(conan_engine_t* eng, int n, const int32_t* slot
  * tokens [n,segment] int32. */
 CONAN_API int conan_emformer_step(conan_engine_t* eng, int n, const int32_t* slot_ids_dev, const float* chunk_dev,
                         float* enc_out_dev, float* logits_out_dev, int32_t* tokens_out_dev, void* stream);
+
+/* Full-utterance EmformerDistillModel.forward (modules/Emformer/emformer.py:31-47 -> torchaudio Emformer.forward, TA:709-743):
+ * input_dev [n, frames, dim] is the utterance right-padded with right_context frames, so frames - right_context utterance frames
+ * are encoded.  Runs as ceil((frames - rc) / segment) streaming steps over the slots' state (which is reset first) -- the block
+ * attention mask of the reference's forward expresses exactly the per-segment visibility of the streaming steps; a partial last
+ * segment and the memory bank are handled by the generic step.  enc [n, frames - rc, dim], logits [n, frames - rc, out_dim],
+ * tokens [n, frames - rc] int32; any output may be NULL. */
+CONAN_API int conan_emformer_forward(conan_engine_t* eng, int n, const int32_t* slots_host, const float* input_dev, int frames,
+                                     float* enc_out_dev, float* logits_out_dev, int32_t* tokens_out_dev, void* stream);
 
 /* Incremental Conan.forward(infer=True) on the newest `segment` tokens of each stream
  * (inference/Conan.py:131-145; modules/Conan/Conan.py:115-198).  tokens [n,segment] int32,
@@ -177,7 +190,8 @@ CONAN_API uint64_t conan_engine_launch_count(const conan_engine_t* eng);
 
 /* Per-launch CUDA-event timing of the conv engines (measurement only: events are recorded on the
  * launching stream around every conv launch while enabled).  category 0 = FFMA, 1 = tcgen05 ring kernel
- * (fp16 operands), 2 = tcgen05 window kernel, 3 = tcgen05 ring kernel with split-fp16 operands.
+ * (fp16 operands), 2 = tcgen05 window kernel, 3 = tcgen05 ring kernel with split-fp16 operands, 4 = fused
+ * residual-block kernel (six convs per launch), 5 = fused feed-forward kernel (two GEMMs per launch).
  * profile_read synchronises the device and returns the summed kernel time, launch count, algorithmic
  * FLOPs (2*M*N*K) and algorithmic HBM bytes since profiling was (re-)enabled. */
 CONAN_API int conan_engine_set_profiling(conan_engine_t* eng, int enabled);

@@ -293,6 +293,80 @@ def test_emformer_staggered_streams_match_independent_runs(state_dicts, eng_fp32
         assert err < 1e-4, (step, err)
 
 
+@pytest.mark.parametrize("M,tc", [(4, True), (4, False), (2, True), (0, True)])
+def test_emformer_memory_bank_and_full_utterance_forward_vs_torchaudio(state_dicts, M, tc):
+    """SURVEY 8f row f4 / north_star (1) "memory-bank update kernels": the generic Emformer step (memory bank of M vectors per
+    layer and stream, summary query masked from the memory keys, clamped memory output, partial segments) against
+    torchaudio.models.Emformer(max_memory_size=M) itself: streaming `infer` over 18 chunks (K/V ring and bank both wrap), streams of
+    different ages in one launch, and the full-utterance `forward` with its block attention mask (whole and partial last segment)."""
+    import torchaudio
+    from oracle.incremental import EmformerOracle
+    sd = state_dicts[1]
+    ta = torchaudio.models.Emformer(80, 8, 2048, 6, 4, left_context_length=50, right_context_length=2, max_memory_size=M).eval()
+    ta.load_state_dict({k[len("emformer."):]: v for k, v in sd.items() if k.startswith("emformer.")})
+    eng = _engine(state_dicts, emformer_memory_size=M, lin_tensor_cores=tc, voc_precision="fp16" if tc else "fp32", voc_tensor_cores=tc)
+    try:
+        assert eng.cfg.emformer_memory_size == M
+        B, T = 3, 74
+        x = torch.stack([synth.synth_mel(T + 2, 60 + b) for b in range(B)])
+        slots = [5, 1, 6]
+        eng.reset_slots(slots)
+        ids = eng.ids_tensor(slots)
+        worst, st = 0.0, None
+        with torch.no_grad():
+            for pos in range(0, 72, 4):
+                ref, _, st = ta.infer(x[:, pos:pos + 6], torch.full((B,), 6), st)
+                _, enc, _ = eng.emformer_step(ids, x[:, pos:pos + 6].contiguous().cuda(), want_enc=True)
+                worst = max(worst, (enc.cpu() - ref).abs().max().item())
+        print(f"M={M} tc={tc}: streaming infer max-abs vs torchaudio {worst:.2e}")
+        assert worst < 1e-4
+        # streams of different ages in one launch: stream b joins at step 2*b (torchaudio runs them one by one)
+        eng.reset_slots(slots)
+        states = [None] * B
+        worst = 0.0
+        with torch.no_grad():
+            for step in range(10):
+                act = [b for b in range(B) if step >= 2 * b]
+                chunks, refs = [], []
+                for b in act:
+                    pos = (step - 2 * b) * 4
+                    ch = x[b:b + 1, pos:pos + 6]
+                    r, _, states[b] = ta.infer(ch, torch.full((1,), 6), states[b])
+                    chunks.append(ch), refs.append(r)
+                _, enc, _ = eng.emformer_step(eng.ids_tensor([slots[b] for b in act]), torch.cat(chunks).contiguous().cuda(), want_enc=True)
+                worst = max(worst, (enc.cpu() - torch.cat(refs)).abs().max().item())
+        assert worst < 1e-4, worst
+        # full-utterance forward (block attention mask in the reference) incl. partial last segments of 3 and 1 frames
+        o = EmformerOracle(sd, max_memory_size=M)
+        for frames in (66, 65, 63):
+            with torch.no_grad():
+                ref, _ = ta(x[:, :frames], torch.full((B,), frames - 2))
+                ref_logits = o.logits(ref)
+            enc, logits, tok = eng.emformer_forward(slots, x[:, :frames], want_logits=True, want_tokens=True)
+            err = (enc.cpu() - ref).abs().max().item()
+            print(f"M={M} tc={tc}: forward({frames} frames) max-abs vs torchaudio {err:.2e}")
+            assert enc.shape == ref.shape and err < 1e-4
+            assert (logits.cpu() - ref_logits).abs().max().item() < 2e-4
+            assert (tok.cpu().long() == ref_logits.argmax(-1)).all()
+    finally:
+        eng.close()
+
+
+def test_emformer_view_forward_matches_streaming_inference(state_dicts, eng_tc):
+    """EmformerDistillModel.forward (modules/Emformer/emformer.py:31-47) through the drop-in view == the streamed `inference`
+    of the same module wherever real look-ahead exists (the last chunk pads by repeating a frame instead, :74-80)."""
+    from conan_b200.streaming import EmformerView
+    view = EmformerView(eng_tc, [0, 1])
+    x = torch.stack([synth.synth_mel(42, 33 + b) for b in range(2)])
+    out, lengths = view(x, torch.full((2,), 42))
+    assert out.shape == (2, 40, 100) and lengths.tolist() == [42, 42]
+    st, toks = None, []
+    for pos in range(0, 36, 4):
+        enc, _, st = view.emformer.infer(x[:, pos:pos + 6], torch.full((2,), 6), st)
+        toks.append(view.proj(enc).argmax(-1).cpu())
+    assert torch.equal(torch.cat(toks, 1), out[:, :36].argmax(-1).cpu())
+
+
 # ------------------------------------------------------------------------------------------
 # Conan main model
 # ------------------------------------------------------------------------------------------
