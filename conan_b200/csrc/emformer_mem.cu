@@ -11,6 +11,8 @@
 //   * partial segments: the last segment of a full-utterance `forward` (TA:709-743) may hold fewer than seg frames; rows
 //     n_utt..seg-1 are neither keys nor appended to the K/V ring, and past_len advances by n_utt.
 // Row layout of every per-stream work buffer on this path: [rc | utt (seg slots) | summary] = seg + rc + 1 rows.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace conan {
@@ -154,6 +156,16 @@ emformer_attention_mem_kernel(const float* __restrict__ qkv, const float* __rest
   }
 }
 
+// rows [src_row0, src_row0 + rows) x C columns of every stream, between two strided per-stream layouts
+__global__ void copy_rows_strided_kernel(const float* __restrict__ src, long long src_slot_stride, int src_ld, int src_row0,
+                                         float* __restrict__ dst, long long dst_slot_stride, int dst_ld, int dst_row0, int n, int rows, int C) {
+  const long long total = (long long)n * rows * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % C; const long long r = idx / C; const int t = r % rows; const long long i = r / rows;
+    dst[i * dst_slot_stride + (long long)(dst_row0 + t) * dst_ld + c] = src[i * src_slot_stride + (long long)(src_row0 + t) * src_ld + c];
+  }
+}
+
 __global__ void advance_past_len_by_kernel(int* past_len, int n, const int* slot_ids, int by) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) past_len[slot_of(slot_ids, i)] += by;
@@ -202,6 +214,16 @@ int launch_emformer_attention_mem(const float* qkv, const float* memkv, float* r
       }))
     return 1;
   emformer_attention_mem_kernel<<<n, 256, sh, st>>>(qkv, memkv, ring, past_len, att, slot_ids, seg, n_utt, rc, lc, ring_rows, D, heads, ldq, M);
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_copy_rows_strided(const float* src, long long src_slot_stride, int src_ld, int src_row0, float* dst, long long dst_slot_stride,
+                             int dst_ld, int dst_row0, int n, int rows, int C, cudaStream_t st) {
+  if (n <= 0 || rows <= 0) return 0;
+  const long long total = (long long)n * rows * C;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  copy_rows_strided_kernel<<<grid, 256, 0, st>>>(src, src_slot_stride, src_ld, src_row0, dst, dst_slot_stride, dst_ld, dst_row0, n, rows, C);
   CONAN_CHECK_LAUNCH();
   return 0;
 }

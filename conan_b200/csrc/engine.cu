@@ -748,15 +748,10 @@ int emformer_step_generic(conan_engine* e, int n, const int* ids, const float* s
     }
   }
   if (enc_out)
-    CONAN_CUDA_OK(cudaMemcpy2DAsync(enc_out + (size_t)out_row0 * D, (size_t)out_nrows * D * 4, e->gX + (size_t)rc * DP, (size_t)er * DP * 4,
-                                    (size_t)n_utt * D * 4, n, cudaMemcpyDeviceToDevice, st));
-  if (logits_out) {
-    // logits rows are LP wide in the work buffer, out_dim wide in the caller's
-    for (int t = 0; t < n_utt; ++t)
-      CONAN_CUDA_OK(cudaMemcpy2DAsync(logits_out + (size_t)(out_row0 + t) * c.emformer_output_dim, (size_t)out_nrows * c.emformer_output_dim * 4,
-                                      e->eLOG + (size_t)t * LP, (size_t)seg * LP * 4, (size_t)c.emformer_output_dim * 4, n,
-                                      cudaMemcpyDeviceToDevice, st));
-  }
+    TRY(launch_copy_rows_strided(e->gX, (long long)er * DP, DP, rc, enc_out, (long long)out_nrows * D, D, out_row0, n, n_utt, D, st));
+  if (logits_out)
+    TRY(launch_copy_rows_strided(e->eLOG, (long long)seg * LP, LP, 0, logits_out, (long long)out_nrows * c.emformer_output_dim,
+                                 c.emformer_output_dim, out_row0, n, n_utt, c.emformer_output_dim, st));
   return 0;
 }
 
@@ -1237,14 +1232,10 @@ int conan_emformer_forward(conan_engine_t* e, int n, const int32_t* slots_host, 
       TRY(emformer_step(e, n, e->hIds, e->hChunk, nullptr, nullptr, nullptr, st));
       // rows of the step's work buffers (eX: [rc | utt] rows of DP floats; eLOG: seg rows of LP floats) -> the caller's layout
       const int rows = seg + rc, OD = c.emformer_output_dim;
-      for (int t = 0; t < seg; ++t) {
-        if (enc_out_dev)
-          CONAN_CUDA_OK(cudaMemcpy2DAsync(enc_out_dev + (size_t)(t0 + t) * D, (size_t)T * D * 4, e->eX + (size_t)(rc + t) * e->DP,
-                                          (size_t)rows * e->DP * 4, (size_t)D * 4, n, cudaMemcpyDeviceToDevice, st));
-        if (logits_out_dev)
-          CONAN_CUDA_OK(cudaMemcpy2DAsync(logits_out_dev + (size_t)(t0 + t) * OD, (size_t)T * OD * 4, e->eLOG + (size_t)t * e->LP,
-                                          (size_t)seg * e->LP * 4, (size_t)OD * 4, n, cudaMemcpyDeviceToDevice, st));
-      }
+      if (enc_out_dev)
+        TRY(launch_copy_rows_strided(e->eX, (long long)rows * e->DP, e->DP, rc, enc_out_dev, (long long)T * D, D, t0, n, seg, D, st));
+      if (logits_out_dev)
+        TRY(launch_copy_rows_strided(e->eLOG, (long long)seg * e->LP, e->LP, 0, logits_out_dev, (long long)T * OD, OD, t0, n, seg, OD, st));
       if (tokens_out_dev)
         CONAN_CUDA_OK(cudaMemcpy2DAsync(tokens_out_dev + t0, (size_t)T * 4, e->TOK, (size_t)seg * 4, (size_t)seg * 4, n,
                                         cudaMemcpyDeviceToDevice, st));

@@ -76,6 +76,8 @@ int launch_emformer_attention_mem(const float* qkv, const float* memkv, float* r
                                   const int* slot_ids, int seg, int n_utt, int rc, int lc, int ring_rows, int D, int heads, int ldq,
                                   int M, cudaStream_t st);
 int launch_advance_past_len_by(int* past_len, int n, const int* slot_ids, int by, cudaStream_t st);
+int launch_copy_rows_strided(const float* src, long long src_slot_stride, int src_ld, int src_row0, float* dst, long long dst_slot_stride,
+                             int dst_ld, int dst_row0, int n, int rows, int C, cudaStream_t st);
 int launch_argmax_rows(const float* logits, int ld, int* tokens_a, int* tokens_b, int n, int rows, int C, cudaStream_t st);
 int launch_copy_rows_out(const float* src_slot, long long slot_stride, int row_stride, int row0, float* dst, int n,
                          const int* slot_ids, int rows, int C, cudaStream_t st);
