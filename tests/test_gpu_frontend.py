@@ -93,3 +93,63 @@ def test_streamed_pcm_equals_offline_bitwise(fe):
     got = torch.cat(got, 1)
     assert got.shape == off.shape and torch.equal(got, off)
     assert 0 < off.shape[1] - n_before_final <= 3                     # only the look-ahead frames wait for the end of the stream
+
+
+def test_gpu_logmel_against_independent_librosa_restatement(fe):
+    """f1 pinning: `conan_logmel` against the committed golden of oracle/librosa_restatement.py (float64 numpy, written
+    independently of conan_b200/audio.py from librosa's documented stft / filters.mel definitions)."""
+    import os
+    from oracle import librosa_restatement as lr
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "logmel_f1.npz"))
+    wav = lr.test_signal(int(d["seed"]), int(d["n"]))
+    mel = fe.offline(wav)[0].cpu().numpy()
+    err = np.abs(mel - d["mel"]).max()
+    print("GPU log-mel vs independent float64 restatement: max-abs", err)
+    assert mel.shape == d["mel"].shape and err < LOGMEL_TOL
+
+
+def test_stream_server_pcm_feed_matches_offline_path(fe, state_dicts):
+    """f3 serving shell on the real engine: PCM fed in uneven pieces (per-stream framing on the GPU front-end, input ring,
+    packed steps, output jitter buffer) == the offline path (whole-utterance mel, one stream through infer-style stepping)."""
+    from conan_b200.engine import Engine, make_config
+    from conan_b200.scheduler import ChunkScheduler
+    from conan_b200.serving import StreamServer
+    eng = Engine(*state_dicts, make_config(max_slots=4, max_ref_frames=64))
+    try:
+        wavs = _audio(2, 1.21, 9)
+        refs = [synth.synth_mel(40, 70 + i).numpy() for i in range(2)]
+        # offline: whole-utterance mel, scheduler one stream at a time
+        expect = []
+        sch = ChunkScheduler(eng, 4)
+        for i in range(2):
+            mel = fe.offline(wavs[i])[0].cpu().numpy()
+            sid = sch.open(refs[i])
+            sch.push(sid, mel)
+            sch.end(sid)
+            out = []
+            while not sch.finished(sid):
+                out.append(sch.step()[sid][0])
+            sch.close(sid)
+            expect.append((np.concatenate(out), mel))
+        # served: two concurrent sessions, PCM in pieces of different sizes, pumped as frames become available
+        srv = StreamServer(eng, 4, frontend=fe, keep_mel=True)
+        sids = [srv.session_of(srv.admit(refs[i])) for i in range(2)]
+        pos, piece = [0, 0], [997, 1603]
+        while any(p < wavs.shape[1] for p in pos):
+            for i in range(2):
+                if pos[i] < wavs.shape[1]:
+                    n = min(piece[i], wavs.shape[1] - pos[i])
+                    took = srv.feed_pcm(sids[i], wavs[i, pos[i]:pos[i] + n], final=pos[i] + n >= wavs.shape[1])
+                    assert took == n
+                    pos[i] += n
+            srv.pump()
+        while not all(srv.done(s) for s in sids):
+            srv.pump()
+        for i, sid in enumerate(sids):
+            wav = srv.read(sid)
+            mel = srv.release(sid)
+            assert wav.shape == expect[i][0].shape
+            assert np.array_equal(wav, expect[i][0])          # same frames, same chunking, same kernels: bit-identical
+        assert srv.stats["closed"] == 2 and srv.stats["admitted"] == 2
+    finally:
+        eng.close()

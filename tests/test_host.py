@@ -363,3 +363,90 @@ def test_reference_arm_is_rank0_only(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "1")
     bench.run_reference(type("A", (), {"steps": 1, "warmup": 1, "gpus": 2})())
     assert capsys.readouterr().out == ""
+
+
+# ------------------------------------------------------------------ serving shell + batch runner (fake engine)
+def test_stream_server_admission_queue_backpressure_and_jitter_buffer():
+    from conan_b200.serving import StreamServer
+    eng = PipelinedFakeEngine()
+    srv = StreamServer(eng, 2, max_queue=1, keep_mel=True)
+    ref = np.zeros((10, 80), np.float32)
+    t0, t1 = srv.admit(ref, tag="a"), srv.admit(ref, tag="b")
+    a, b = srv.session_of(t0), srv.session_of(t1)
+    assert a is not None and b is not None
+    t2 = srv.admit(ref, tag="c")                                       # pool full: queued
+    assert srv.session_of(t2) is None and len(srv.queue) == 1
+    assert srv.admit(ref) is None and srv.stats["refused"] == 1        # queue full too: refused (back-pressure)
+    src = synth.synth_mel(200, 3).numpy()
+    took = srv.feed_mel(a, src)                                        # more than the ring holds: only part is accepted
+    assert 0 < took < 200 and srv.stats["input_backpressure_events"] == 1
+    assert srv.feed_mel(a, src[took:]) == 0                            # still full until the consumer runs
+    fed = took
+    while fed < 200:
+        srv.pump()
+        fed += srv.feed_mel(a, src[fed:])
+    srv.end(a)
+    while not srv.done(a):
+        srv.pump()
+    assert srv.session_of(t2) is not None                              # the freed slot went to the queued admission
+    # output jitter buffer: arbitrary-sized reads reassemble the stream (echo engine: sample block t carries mel[t, 0])
+    total = srv.available(a)
+    assert total == 200 * 320
+    pieces = [srv.read(a, 1000), srv.read(a, 7), srv.read(a)]
+    wav = np.concatenate(pieces)
+    assert wav.shape[0] == total and np.array_equal(wav[::320], src[:, 0])
+    mel = srv.release(a)
+    assert np.array_equal(mel, src)
+
+
+def test_stream_server_pipelined_mode_delivers_everything():
+    from conan_b200.serving import StreamServer
+    eng = PipelinedFakeEngine()
+    srv = StreamServer(eng, 3, pipelined=True, keep_mel=True)
+    srcs = [synth.synth_mel(30 + 7 * i, 20 + i).numpy() for i in range(3)]
+    sids = [srv.session_of(srv.admit(np.zeros((8, 80), np.float32))) for _ in range(3)]
+    for sid, src in zip(sids, srcs):
+        assert srv.feed_mel(sid, src) == src.shape[0]
+        srv.end(sid)
+    for _ in range(40):
+        srv.pump()
+    srv.flush()
+    for sid, src in zip(sids, srcs):
+        assert srv.done(sid) and srv.available(sid) == src.shape[0] * 320
+        assert np.array_equal(srv.release(sid), src)
+    assert srv.stats["closed"] == 3 and not srv.sch.streams
+
+
+def test_voice_conversion_runner_json_contract(tmp_path, monkeypatch):
+    """inference/run_voice_conversion_nvae.py: config schema, output naming, progress / final report keys, error capture."""
+    from conan_b200.serving import VoiceConversionRunner
+    from conan_b200.scheduler import ChunkScheduler
+
+    class FakeSVC:
+        def __init__(self):
+            self.engine = FakeEngine()
+            self.scheduler = ChunkScheduler(self.engine, 2)
+
+        def _wav_to_mel(self, path):
+            if "missing" in path:
+                raise FileNotFoundError(path)
+            return synth.synth_mel(10 + len(path) % 5, len(path)).numpy()
+
+    pairs = [{"ref_wav": f"r{i}.wav", "src_wav": ("missing.wav" if i == 2 else f"s{i}.wav"), "src_corpus": "vctk",
+              "src_utt_id": f"p{i:03d}", "output_name": f"o{i}"} for i in range(5)]
+    cfg = tmp_path / "voice_conversion_config.json"
+    cfg.write_text(__import__("json").dumps({"total_pairs": 5, "conversion_pairs": pairs}))
+    out = tmp_path / "out"
+    runner = VoiceConversionRunner(str(cfg), hparams={"audio_sample_rate": 16000}, engine=FakeSVC(), output_dir=str(out))
+    rep = runner.run_all_conversions(batch_size=2)
+    assert rep["total_processed"] == 5 and rep["successful"] == 4 and rep["failed"] == 1 and rep["success_rate"] == 80.0
+    assert sorted(os.listdir(out)) == ["conversion_progress.json", "final_report.json", "vctk_p000.wav", "vctk_p001.wav",
+                                       "vctk_p003.wav", "vctk_p004.wav"]
+    prog = __import__("json").load(open(out / "conversion_progress.json"))
+    assert set(prog) == {"processed", "total", "successful", "failed", "elapsed_time", "estimated_remaining", "current_batch_end", "errors"}
+    final = __import__("json").load(open(out / "final_report.json"))
+    assert set(final) == {"start_idx", "end_idx", "total_processed", "successful", "failed", "success_rate", "total_time_minutes",
+                          "avg_time_per_file_seconds", "output_directory", "errors", "timestamp"}
+    assert final["errors"] and "Pair 2" in final["errors"][0]
+    with pytest.raises(FileNotFoundError):
+        VoiceConversionRunner(str(tmp_path / "nope.json"), hparams={}, engine=FakeSVC(), output_dir=str(out))
