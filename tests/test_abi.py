@@ -41,3 +41,24 @@ def test_no_cpu_fallback(lib):
     from conan_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine({}, {}, {}, cfg)
+
+
+def test_integration_md_config_mirror_matches_header():
+    """the ctypes mirror shown to maintainers in INTEGRATION.md must be the header's struct, field for field
+    (a same-size struct with stale tail fields silently selects the slow engines)."""
+    import ctypes as C
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "conan_b200.h")).read()
+    body = hdr[hdr.index("typedef struct conan_config {"):hdr.index("} conan_config_t;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"int32_t\s+(\w+)(?:\[(\d+)\])?;", body)
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    snippet = md[md.index("class Cfg(C.Structure):"):md.index("assert lib.conan_sizeof_config()")]
+    ns = {"C": C}
+    exec(snippet, ns)
+    got = [(n, (t._length_ if hasattr(t, "_length_") else 0)) for n, t in ns["Cfg"]._fields_]
+    assert got == [(n, int(k) if k else 0) for n, k in fields]
+    from conan_b200 import _lib
+    assert [f[0] for f in _lib.ConanConfig._fields_] == [n for n, _ in fields]
+    assert C.sizeof(ns["Cfg"]) == C.sizeof(_lib.ConanConfig) == _lib.load().conan_sizeof_config()
