@@ -250,7 +250,7 @@ class Rig:
 
 def _short_window(rig, K, seconds, warm=3):
     """warm-up, one K-step probe, then K-step blocks for ~`seconds`: dict(ms_per_step, latency, value, steps)."""
-    for _ in range(warm):
+    for _ in range(warm + (2 * rig.n_pool if rig.cfg.step_graphs else 0)):
         rig.step()
     rig.torch.cuda.synchronize(rig.dev)
     _, probe = rig.timed(K)
@@ -601,6 +601,11 @@ def run_b200(args):
     # ---------------- device-resident timing
     for _ in range(W):
         rig.step()
+    # untimed priming beyond the W warm-up steps: a chunk step is captured as a CUDA graph the second time its (ready count,
+    # buffer set) is seen, and the input pool rotates over n_pool device buffers
+    n_prime = 2 * rig.n_pool if cfg.step_graphs else 0
+    for _ in range(n_prime):
+        rig.step()
     sync_all()
     if args.ncu_step:
         # profiler window for `ncu --profile-from-start off`: exactly one warmed-up step, no bench line
@@ -722,7 +727,8 @@ def run_b200(args):
                        "weights": "synthetic seeded (conan_b200.synth, reference state_dict layout)",
                        "l2": f"per-step working set (resident state {eng.state_bytes / 2**30:.1f} GiB) is larger than L2; no flush needed",
                        "voc_precision": args.voc_precision, "voc_tensor_cores": not args.no_tensor_cores, "voc_group": args.voc_group,
-                       "voc_fuse_resblocks": bool(cfg.voc_fuse_resblocks),
+                       "voc_fuse_resblocks": bool(cfg.voc_fuse_resblocks), "step_graphs": bool(cfg.step_graphs),
+                       "graph_priming_steps_untimed": n_prime, "graph_replays": eng.graph_replays,
                        "value_window": f"sustained: the {K}-step block repeated {blocks}x = {n_sus} steps, {sus_ms * 1e-3:.2f} s of device time "
                                        "(value, ms_per_step, latency_ms, rtf all from this window)"},
             "sustained": {"blocks": blocks, "steps_timed": n_sus, "seconds": sus_ms * 1e-3},

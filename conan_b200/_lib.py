@@ -30,7 +30,7 @@ class ConanConfig(C.Structure):
         ("voc_res_dilations", C.c_int32 * 8), ("voc_n_dil", C.c_int32),
         ("voc_precision", C.c_int32), ("voc_use_tensor_cores", C.c_int32), ("voc_group", C.c_int32),
         ("voc_residual_from_ctx", C.c_int32), ("lin_use_tensor_cores", C.c_int32), ("voc_fuse_resblocks", C.c_int32), ("lin_fuse_ffn", C.c_int32),
-        ("ses_use_tensor_cores", C.c_int32), ("emformer_memory_size", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("ses_use_tensor_cores", C.c_int32), ("emformer_memory_size", C.c_int32), ("step_graphs", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -80,6 +80,7 @@ SYMBOLS = {
     "conan_step_host_submit": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int)]),
     "conan_step_host_wait": (C.c_int, [_P, C.c_int]),
     "conan_engine_launch_count": (C.c_uint64, [_P]),
+    "conan_engine_graph_replays": (C.c_uint64, [_P]),
     "conan_engine_set_profiling": (C.c_int, [_P, C.c_int]),
     "conan_engine_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "conan_debug_read": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),

@@ -327,11 +327,14 @@ __device__ __forceinline__ void stage_bias(float* s_bias, const float* bias, int
   for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = bias ? bias[i] : 0.f;
 }
 
-template <int BN, int BK, int STAGES, int MT>
+// SP ("split, four-tile stages"): a stage holds A_hi, A_lo, W_hi, W_lo of one k-block and feeds three MMA groups
+// (A_hi W_hi + A_hi W_lo + A_lo W_hi): 4 tiles of L2 -> SM traffic per product instead of the 6 of three plain k-blocks.
+template <int BN, int BK, int STAGES, int MT, bool SP = false>
 struct SmemLayout {
   static constexpr int A1_BYTES = TILE_M * BK * 2;      // one 128-row A tile
-  static constexpr int A_BYTES = MT * A1_BYTES;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = MT * A1_BYTES * (SP ? 2 : 1);
+  static constexpr int B1_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = B1_BYTES * (SP ? 2 : 1);
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_BYTES = 2048 * 4;           // bias of up to 2048 output channels
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/ + BIAS_BYTES;
@@ -343,10 +346,11 @@ struct SmemLayout {
 // one CTA per SM) and its own epilogue warpgroup.
 // ES = epilogue warpgroups per m-tile, each draining BN / ES accumulator columns (the short-K layers are bound by the
 // epilogue's latency, not by the MMAs: more warps in flight per tile).
-template <int BN, int BK, int STAGES, int MT, int ES, bool LEAN>
-__global__ void __launch_bounds__(64 + 128 * MT * ES, MT == 2 ? 1 : (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4)))
+template <int BN, int BK, int STAGES, int MT, int ES, bool LEAN, bool SP = false>
+__global__ void __launch_bounds__(64 + 128 * MT * ES, (MT == 2 || SP) ? 1 : (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4)))
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
-  using SL = SmemLayout<BN, BK, STAGES, MT>;
+  static_assert(!SP || MT == 1, "four-tile split stages take one m-tile per CTA");
+  using SL = SmemLayout<BN, BK, STAGES, MT, SP>;
   constexpr int SWZ = BK * 2;                 // bytes per tile row = swizzle span (128 or 64)
   constexpr int TMEM_COLS = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;     // two accumulators per m-tile: MMAs of tile i+1 overlap the epilogue of tile i
   extern __shared__ uint8_t smem_raw[];
@@ -399,7 +403,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * SL::STAGE_BYTES;
           uint8_t* sb = sa + SL::A_BYTES;
-          if (elect_one_sync()) {
+          if (SP) {
+            if (elect_one_sync()) {                          // A_hi, A_lo, W_hi, W_lo of this (tap, channel block)
+              mbar_expect_tx(&full_bar[s], SL::A_BYTES + SL::B_BYTES);
+              tma_load_3d(sa, &tmA, &full_bar[s], c0, a.row0 + t0m[0] + j * a.dil, stream0m[0]);
+              tma_load_3d(sa + SL::A1_BYTES, &tmA, &full_bar[s], c0, a.row0 + t0m[0] + j * a.dil, stream0m[0] + a.lo_slot_off);
+              tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, nt * BN);
+              tma_load_2d(sb + SL::B1_BYTES, &tmW, &full_bar[s], a.k * a.cin + kb * BK, nt * BN);
+            }
+          } else if (elect_one_sync()) {
             const bool second = MT == 2 && mt + 1 < a.m_tiles;
             mbar_expect_tx(&full_bar[s], SL::B_BYTES + (second ? 2 : 1) * SL::A1_BYTES);
 #pragma unroll
@@ -434,6 +446,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
           const uint32_t sb = sa + SL::A_BYTES;
           const uint64_t bdesc = make_smem_desc<SWZ>(sb);
+          if (SP) {
+            // three products per stage: A_hi W_hi, A_hi W_lo, A_lo W_hi (the dropped A_lo W_lo term is below fp32 resolution)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              const uint64_t ad = make_smem_desc<SWZ>(sa + (g == 2 ? SL::A1_BYTES : 0));
+              const uint64_t bd = make_smem_desc<SWZ>(sb + (g == 1 ? SL::B1_BYTES : 0));
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk)
+                if (elect_one_sync())
+                  tc_mma_f16(tacc, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (kb | g | kk) != 0 ? 1u : 0u);
+            }
+          } else {
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
             const uint64_t adesc = make_smem_desc<SWZ>(sa + m * SL::A1_BYTES);
@@ -443,6 +467,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (elect_one_sync())
                 tc_mma_f16(tacc + (uint32_t)(m * BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
             }
+          }
           }
           if (elect_one_sync()) tc_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -478,6 +503,141 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+
+// ==============================================================================================
+// CTA-pair variant of the ring kernel (tcgen05.mma.cta_group::2, M = 256): the vocoder layers with 128 / 256 output
+// channels ran at the L2 -> SM operand limit with 128 x 128 tiles (16 KB of A + 16 KB of B per four MMAs = 128 B per MMA
+// cycle against ~64 B/cycle of TMA delivery per SM).  A pair of CTAs on the two SMs of a TPC shares one 256 x BN tile: each
+// CTA fetches its own 128 A rows and HALF of the B rows per k-block, the leader issues M = 256 MMAs that read both halves, and
+// each CTA drains the accumulator rows that live in its own TMEM.  Per CTA and k-block: 16 KB + BN/2 x 128 B for 2 x BN MMA
+// cycles -- 64 B per cycle at BN = 256.
+//   full[s]   (leader's copy): leader's producer arrives with the byte count of BOTH CTAs; both CTAs' TMA loads complete on it
+//   empty[s]  (each CTA's own): the leader's commit arrives on both copies (multicast) when the MMAs have read the stage
+//   acc_full  (each CTA's own): multicast commit after a tile's last MMA;  acc_empty (leader's): every epilogue thread of both CTAs
+// ==============================================================================================
+template <int BN, int STAGES>
+struct Smem2Layout {
+  static constexpr int A_BYTES = TILE_M * 64 * 2;
+  static constexpr int B_BYTES = (BN / 2) * 64 * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BIAS_BYTES = 2048 * 4;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES;
+};
+
+template <int BN, int STAGES, int ES, int OCC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * ES, OCC)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
+  using SL = Smem2Layout<BN, STAGES>;
+  constexpr int BK = 64, SWZ = 128;
+  constexpr int TMEM_COLS = 2 * BN;                    // two accumulators: MMAs of tile i+1 overlap the epilogue of tile i
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SL::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * SL::STAGE_BYTES + 256);
+  stage_bias(s_bias, a.e.bias, a.cout);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * 128 * ES); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                          // both CTAs' barriers are initialised before any remote arrival / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs: own A rows, own half of B)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = cluster_id; tile < a.num_tiles; tile += n_clusters) {
+      const int nt = tile % a.n_tiles;
+      int mt = (tile / a.n_tiles) * 2 + rank;
+      if (mt >= a.m_tiles) mt = a.m_tiles - 1;             // odd tile count: the peer computes a duplicate that its epilogue drops
+      const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
+      int j = 0, c0 = 0;
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * SL::STAGE_BYTES;
+        uint8_t* sb = sa + SL::A_BYTES;
+        if (elect_one_sync()) {
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * SL::STAGE_BYTES);
+          tma_load_3d_2sm(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0);      // box {64, TT, NS}
+          tma_load_2d_2sm(sb, &tmW, &full_bar[s], kb * BK, nt * BN + rank * (BN / 2));            // box {64, BN / 2}
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        c0 += BK;
+        if (c0 == a.cin) { c0 = 0; ++j; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, 256>();
+      int it = 0, s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < a.num_tiles; tile += n_clusters, ++it) {
+        const int ab = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[ab], aph ^ 1);                  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc<SWZ>(sa), bdesc = make_smem_desc<SWZ>(sa + SL::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            if (elect_one_sync())
+              tc_mma_f16_2sm(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+          if (elect_one_sync()) tc_commit_2sm(&empty_bar[s]);          // frees the stage in both CTAs
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (elect_one_sync()) tc_commit_2sm(&acc_full[ab]);            // accumulator rows complete in both CTAs
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (both CTAs, own 128 rows; ES column parts)
+    const int cpart = (warp - 2) >> 2;
+    constexpr int BNE = BN / ES;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int q = r / a.TT, tt = r - q * a.TT;
+    int it = 0;
+    for (int tile = cluster_id; tile < a.num_tiles; tile += n_clusters, ++it) {
+      const int ab = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * 2 + rank;
+      const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
+      epilogue_rows<BNE, false>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + cpart * BNE),
+                                nt * BN + cpart * BNE, mt < a.m_tiles && stream < a.n_streams, stream, t, &acc_full[ab], aph);
+      tc_fence_before();
+      mbar_arrive_leader(&acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                          // no CTA may free TMEM / exit while its partner still uses the pair's resources
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
 
 // ==============================================================================================
 // "Window" variant for the long narrow layers (L % 128 == 0, cout = BN in {32, 64}: vocoder scales
@@ -731,10 +891,11 @@ int pick_bn(int cout) {
   return 0;
 }
 
-template <int BN, int BK, int STAGES, int MT = 1, int ES = 1, bool LEAN = false>
+template <int BN, int BK, int STAGES, int MT = 1, int ES = 1, bool LEAN = false, bool SP = false>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, long long m_tiles, cudaStream_t st) {
-  using SL = SmemLayout<BN, BK, STAGES, MT>;
-  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES, MT, ES, LEAN>;
+  using SL = SmemLayout<BN, BK, STAGES, MT, SP>;
+  auto kern = conv_gemm_tc_kernel<BN, BK, STAGES, MT, ES, LEAN, SP>;
+  if (SP) a.kblocks /= 3;                      // one stage per (tap, channel block): the three products share it
   constexpr int threads = 64 + 128 * MT * ES;
   static DeviceOnce once;
   int per_sm = 1;
@@ -749,10 +910,39 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, lon
   a.m_tiles = (int)m_tiles;
   a.num_tiles = (int)(((m_tiles + MT - 1) / MT) * a.n_tiles);
   const int grid = std::min(a.num_tiles, num_sms() * per_sm);           // persistent: exactly the co-resident CTAs
-  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "ring<%d,%d,%d,%d,%d> tiles %d per_sm %d grid %d\n", BN, BK, STAGES, MT, ES, a.num_tiles, per_sm, grid);
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "ring<%d,%d,%d,%d,%d,sp%d> tiles %d per_sm %d grid %d\n", BN, BK, STAGES, MT, ES, (int)SP, a.num_tiles, per_sm, grid);
   if (launch_pdl(kern, grid, threads, SL::TOTAL, st, tmA, tmW, a)) return 1;
   CONAN_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, int STAGES, int ES, int OCC = 1>
+int launch_pair_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, long long m_tiles, cudaStream_t st) {
+  using SL = Smem2Layout<BN, STAGES>;
+  static_assert(OCC * 2 * BN <= 512, "TMEM columns of the co-resident CTAs");
+  auto kern = conv_gemm_tc2_kernel<BN, STAGES, ES, OCC>;
+  constexpr int threads = 64 + 128 * ES;
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
+  a.m_tiles = (int)m_tiles;
+  a.num_tiles = (int)(((m_tiles + 1) / 2) * a.n_tiles);                  // tiles of 256 rows x BN columns
+  const int clusters = std::min(a.num_tiles, (num_sms() / 2) * OCC);     // persistent: OCC CTA pairs per TPC
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "pair<%d,%d,%d,%d> tiles %d clusters %d\n", BN, STAGES, ES, OCC, a.num_tiles, clusters);
+  kern<<<2 * clusters, threads, SL::TOTAL, st>>>(tmA, tmW, a);           // cluster dims (2, 1, 1) are compiled into the kernel
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int pair_mode() {
+  // CONAN_TC_2CTA: 0 = never, 1 = layers with cout % 256 == 0 only, 2 (default) = also cout % 128 == 0
+  static int v = [] { const char* e = getenv("CONAN_TC_2CTA"); return e ? atoi(e) : 2; }();
+  return v;
 }
 
 int es_min_tiles() {
@@ -881,6 +1071,42 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   // Few CTAs and a long K loop (the Emformer / Conan GEMMs: M = 4..6 rows x streams): one CTA per SM anyway, so
   // spend the shared memory on pipeline depth instead of co-residency.
   const bool deep = m_tiles * a.n_tiles <= 2 * num_sms() && a.kblocks >= 12;
+  // split operands: four-tile stages (CONAN_TC_SPLIT4=0 falls back to three plain k-block segments)
+  static const int split4 = [] { const char* v = getenv("CONAN_TC_SPLIT4"); return v ? atoi(v) : 1; }();
+  if (nseg == 3 && split4) {
+    static const int narrow4 = [] { const char* v = getenv("CONAN_TC_NARROW"); return v ? atoi(v) : 1; }();
+    int bn = BN;
+    if (bn == 128 && deep && narrow4 && m_tiles * a.n_tiles * 2 <= num_sms())
+      bn = (m_tiles * (p.cout / 64) * 4 >= 3LL * num_sms() || p.cout % 32 != 0) ? 64 : 32;
+    if (bn != BN) {
+      a.n_tiles = p.cout / bn;
+      if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, bn, 1, BK * 2))
+        return 1;
+    }
+    if (BK == 64) {
+      if (bn == 128) return launch_variant<128, 64, 3, 1, 1, false, true>(tmA, tmW, a, m_tiles, st);
+      if (bn == 64) return launch_variant<64, 64, 4, 1, 1, false, true>(tmA, tmW, a, m_tiles, st);
+      return launch_variant<32, 64, 4, 1, 1, false, true>(tmA, tmW, a, m_tiles, st);
+    }
+    if (bn == 128) return launch_variant<128, 32, 4, 1, 1, false, true>(tmA, tmW, a, m_tiles, st);
+    if (bn == 64) return launch_variant<64, 32, 4, 1, 1, false, true>(tmA, tmW, a, m_tiles, st);
+    return launch_variant<32, 32, 4, 1, 1, false, true>(tmA, tmW, a, m_tiles, st);
+  }
+  // CTA pairs (M = 256 MMAs) for the wide fp16 layers with enough tiles to fill the machine
+  if (nseg == 1 && BK == 64 && pair_mode() && p.cout % 128 == 0) {
+    const int bn2 = (p.cout % 256 == 0) ? 256 : (pair_mode() >= 2 ? 128 : 0);
+    // at least one 256-row tile per CTA pair (CONAN_TC_2CTA_MIN overrides the tile count from which pairs are used)
+    static const long long min_tiles = [] { const char* e = getenv("CONAN_TC_2CTA_MIN"); return e ? atoll(e) : -1LL; }();
+    const long long pair_tiles = bn2 ? ((m_tiles + 1) / 2) * (p.cout / bn2) : 0;
+    if (bn2 && pair_tiles >= (min_tiles >= 0 ? min_tiles : (long long)num_sms() / 2)) {
+      a.n_tiles = p.cout / bn2;
+      if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, bn2 / 2, 1, BK * 2))
+        return 1;
+      if (bn2 == 256) return pair_mode() == 4 ? launch_pair_variant<256, 5, 4>(tmA, tmW, a, m_tiles, st) : launch_pair_variant<256, 5, 2>(tmA, tmW, a, m_tiles, st);
+      // 128 output channels: two pairs per TPC (3 stages each), so one pair's epilogue runs under the other's MMAs
+      return pair_mode() == 3 ? launch_pair_variant<128, 6, 2>(tmA, tmW, a, m_tiles, st) : launch_pair_variant<128, 3, 2, 2>(tmA, tmW, a, m_tiles, st);
+    }
+  }
   if (BK == 64) {
     if (BN == 128) {
       // too few 128-wide tiles to fill the SMs: narrow the tile (more CTAs, each with the same K loop) until ~3/4 of them have one

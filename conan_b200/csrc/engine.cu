@@ -118,6 +118,21 @@ struct conan_engine {
   cudaStream_t copyStream = nullptr; cudaEvent_t evCompute[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
   unsigned long long submitCount = 0; bool ticketPending[2] = {false, false};
   std::vector<uint8_t> idSeen;     // host-side duplicate check of a ready list
+  // the three MRF branches of a vocoder scale (kernel sizes 3 / 7 / 11) are independent chains of six convs until their outputs are
+  // summed: they run on three streams (fork after the upsampling conv, join through the running sum), so one branch's tail wave,
+  // launch latency and prologue run under another branch's MMAs
+  cudaStream_t branchStream[2] = {nullptr, nullptr};
+  cudaEvent_t evFork = nullptr, evBranch[4] = {nullptr, nullptr, nullptr, nullptr};
+  int vocStreams = 3;
+  // CUDA graphs of whole chunk steps: a step's ~130 launches (and the fork / join above) are captured once per distinct
+  // (ready count, buffer set) on an engine-owned stream and replayed with one cudaGraphLaunch on the caller's stream.  The ready
+  // list itself is NOT baked in: kernels read the slot ids from the device buffer the graph was captured with (slot indirection).
+  struct StepGraph { int n; const void* ids; const void* chunk; void* wav; void* mel; void* tok; cudaGraphExec_t exec; uint64_t launches; uint64_t last_use; };
+  std::vector<StepGraph> stepGraphs;
+  std::vector<StepGraph> stepSeen;       // keys met once (the first eager run doubles as warm-up of attributes / tensor maps)
+  cudaStream_t graphStream = nullptr;
+  int graphMode = 0;                     // 0 off, 1 on
+  uint64_t graphClock = 0, graphReplays = 0;
 
   const WeightSlot* W(const std::string& name) const {
     auto it = windex.find(name);
@@ -588,6 +603,13 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->hWav2, (size_t)S * e->vL[c.voc_n_ups])); TRY(dalloc(e, &e->hMel2, (size_t)S * seg * c.n_mels));
   TRY(dalloc(e, &e->hTok2, (size_t)S * seg));
   CONAN_CUDA_OK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+  { const char* v = getenv("CONAN_VOC_STREAMS"); if (v) e->vocStreams = std::max(1, std::min(3, atoi(v))); }
+  for (int i = 0; i < 2; ++i) CONAN_CUDA_OK(cudaStreamCreateWithFlags(&e->branchStream[i], cudaStreamNonBlocking));
+  CONAN_CUDA_OK(cudaStreamCreateWithFlags(&e->graphStream, cudaStreamNonBlocking));
+  e->graphMode = e->cfg.step_graphs;
+  { const char* v = getenv("CONAN_STEP_GRAPH"); if (v) e->graphMode = atoi(v) != 0; }
+  CONAN_CUDA_OK(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) CONAN_CUDA_OK(cudaEventCreateWithFlags(&e->evBranch[i], cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     CONAN_CUDA_OK(cudaEventCreateWithFlags(&e->evCompute[i], cudaEventDisableTiming));
     CONAN_CUDA_OK(cudaEventCreateWithFlags(&e->evCopy[i], cudaEventDisableTiming));
@@ -876,8 +898,18 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
       f.out_scale = 1.0f / (float)c.voc_n_res; f.slope = sl;
       TRY(run_fused(e, f, st));
     }
+    // per-conv path: branch r runs on stream bs (fork / join around the scale; the running sum orders the branches' last convs)
+    // (only on the fp16 fast path: the fp32 / split paths share the residual scratch vXR between branches)
+    const bool multi = !e->vFused[i] && e->vocStreams > 1 && c.voc_n_res > 1 && c.voc_n_res <= 4 && !e->profiling && from_ctx &&
+                       e->vXA[i].is_half == 1;
+    if (multi) {
+      CONAN_CUDA_OK(cudaEventRecord(e->evFork, st));
+      for (int q = 0; q < e->vocStreams - 1; ++q) CONAN_CUDA_OK(cudaStreamWaitEvent(e->branchStream[q], e->evFork, 0));
+    }
     for (int r = 0; r < c.voc_n_res && !e->vFused[i]; ++r) {
       const int k = c.voc_res_kernels[r];
+      const int lane = multi ? r % e->vocStreams : 0;
+      cudaStream_t bs = lane == 0 ? st : e->branchStream[lane - 1];
       std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
       const float* xj = e->vXS;
       for (int j = 0; j < c.voc_n_dil; ++j) {
@@ -885,7 +917,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
         auto p1 = conv_on_ctx(e, in1, k, c.voc_res_dilations[j], e->P(q + "c1." + std::to_string(j) + ".w"),
                               e->F(q + "c1." + std::to_string(j) + ".b"), C, n);
         out2_ctx(p1, e->vC2[i][r][j], ACT_LRELU, sl);
-        TRY(run_conv(e, p1, st, e->cfg.voc_use_tensor_cores != 0));
+        TRY(run_conv(e, p1, bs, e->cfg.voc_use_tensor_cores != 0));
         auto p2 = conv_on_ctx(e, e->vC2[i][r][j], k, 1, e->P(q + "c2." + std::to_string(j) + ".w"),
                               e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
         if (from_ctx) {
@@ -912,9 +944,13 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
           p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)
           if (r == c.voc_n_res - 1) out2_ctx(p2, next, ACT_LRELU, sl);
         }
-        TRY(run_conv(e, p2, st, e->cfg.voc_use_tensor_cores != 0));
+        const bool last_conv = j + 1 == c.voc_n_dil;
+        if (multi && last_conv && r > 0) CONAN_CUDA_OK(cudaStreamWaitEvent(bs, e->evBranch[r - 1], 0));   // the running sum of branch r - 1
+        TRY(run_conv(e, p2, bs, e->cfg.voc_use_tensor_cores != 0));
+        if (multi && last_conv) CONAN_CUDA_OK(cudaEventRecord(e->evBranch[r], bs));
       }
     }
+    if (multi) CONAN_CUDA_OK(cudaStreamWaitEvent(st, e->evBranch[c.voc_n_res - 1], 0));               // join (the chain of sums implies every branch)
   }
   const int Lw = e->vL[c.voc_n_ups];
   TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half ? 1 : 0, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
@@ -1119,6 +1155,11 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
 void conan_engine_destroy(conan_engine_t* e) {
   if (!e) return;
   if (e->copyStream) { cudaStreamSynchronize(e->copyStream); cudaStreamDestroy(e->copyStream); }
+  for (int i = 0; i < 2; ++i) if (e->branchStream[i]) { cudaStreamSynchronize(e->branchStream[i]); cudaStreamDestroy(e->branchStream[i]); }
+  for (auto& g : e->stepGraphs) cudaGraphExecDestroy(g.exec);
+  if (e->graphStream) cudaStreamDestroy(e->graphStream);
+  if (e->evFork) cudaEventDestroy(e->evFork);
+  for (int i = 0; i < 4; ++i) if (e->evBranch[i]) cudaEventDestroy(e->evBranch[i]);
   for (int i = 0; i < 2; ++i) { if (e->evCompute[i]) cudaEventDestroy(e->evCompute[i]); if (e->evCopy[i]) cudaEventDestroy(e->evCopy[i]); }
   for (void* p : e->allocs) cudaFree(p);
   delete e;
@@ -1169,6 +1210,7 @@ int conan_engine_finalize(conan_engine_t* e) {
 
 size_t conan_engine_state_bytes(const conan_engine_t* e) { return e ? e->state_bytes : 0; }
 uint64_t conan_engine_launch_count(const conan_engine_t*) { return g_launches.load(); }
+uint64_t conan_engine_graph_replays(const conan_engine_t* e) { return e ? e->graphReplays : 0; }
 
 int conan_slots_reset(conan_engine_t* e, int n, const int32_t* slots_host, int parts, void* stream) {
   if (check_ready(e)) return 1;
@@ -1259,14 +1301,69 @@ int conan_vocoder_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, co
   return vocoder_step(e, n, slot_ids_dev, mel_dev, wav_out_dev, (cudaStream_t)stream);
 }
 
+static int step_eager(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* wav_out_dev, float* mel_out_dev,
+                      int32_t* tokens_out_dev, cudaStream_t st) {
+  TRY(emformer_step(e, n, slot_ids_dev, chunk_dev, nullptr, nullptr, tokens_out_dev, st));
+  TRY(decoder_step(e, n, slot_ids_dev, nullptr, mel_out_dev, st));
+  TRY(vocoder_step(e, n, slot_ids_dev, nullptr, wav_out_dev, st));
+  return 0;
+}
+
 int conan_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* wav_out_dev, float* mel_out_dev,
                int32_t* tokens_out_dev, void* stream) {
   if (check_ready(e)) return 1;
   if (n < 0 || n > e->S || !slot_ids_dev || !chunk_dev || !wav_out_dev) { set_error("bad arguments to conan_step"); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
-  TRY(emformer_step(e, n, slot_ids_dev, chunk_dev, nullptr, nullptr, tokens_out_dev, st));
-  TRY(decoder_step(e, n, slot_ids_dev, nullptr, mel_out_dev, st));
-  TRY(vocoder_step(e, n, slot_ids_dev, nullptr, wav_out_dev, st));
+  if (!e->graphMode || e->profiling || n == 0) return step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, st);
+  auto same = [&](const conan_engine::StepGraph& g) {
+    return g.n == n && g.ids == slot_ids_dev && g.chunk == chunk_dev && g.wav == wav_out_dev && g.mel == mel_out_dev && g.tok == tokens_out_dev;
+  };
+  ++e->graphClock;
+  for (auto& g : e->stepGraphs)
+    if (same(g)) {
+      g.last_use = e->graphClock;
+      CONAN_CUDA_OK(cudaGraphLaunch(g.exec, st));
+      count_launch((int)g.launches);
+      ++e->graphReplays;
+      return 0;
+    }
+  bool seen = false;
+  for (auto& g : e->stepSeen) seen = seen || same(g);
+  if (!seen) {
+    // first time with this (ready count, buffers): run eagerly (sets kernel attributes, fills the tensor-map cache)
+    if (e->stepSeen.size() >= 64) e->stepSeen.erase(e->stepSeen.begin());
+    e->stepSeen.push_back(conan_engine::StepGraph{n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, nullptr, 0, 0});
+    return step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, st);
+  }
+  // second time: capture on the engine's stream (the caller's may be the legacy default stream, which cannot capture), instantiate,
+  // and replay on the caller's stream from now on
+  cudaGraph_t graph = nullptr;
+  const uint64_t l0 = g_launches.load();
+  CONAN_CUDA_OK(cudaStreamBeginCapture(e->graphStream, cudaStreamCaptureModeThreadLocal));
+  const int rc = step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, e->graphStream);
+  cudaError_t ce = cudaStreamEndCapture(e->graphStream, &graph);
+  const uint64_t nl = g_launches.load() - l0;
+  g_launches.fetch_sub(nl);                              // nothing has run yet
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    e->graphMode = 0;                                    // capture is not possible in this process: stay on eager launches
+    return step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, st);
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { (void)cudaGetLastError(); e->graphMode = 0; return step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, st); }
+  if (e->stepGraphs.size() >= 32) {                      // bounded: drop the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < e->stepGraphs.size(); ++i) if (e->stepGraphs[i].last_use < e->stepGraphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(e->stepGraphs[lru].exec);
+    e->stepGraphs.erase(e->stepGraphs.begin() + lru);
+  }
+  e->stepGraphs.push_back(conan_engine::StepGraph{n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, exec, nl, e->graphClock});
+  CONAN_CUDA_OK(cudaGraphLaunch(exec, st));
+  count_launch((int)nl);
+  ++e->graphReplays;
   return 0;
 }
 

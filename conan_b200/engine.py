@@ -23,7 +23,7 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
                 voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None,
                 voc_residual_from_ctx: Optional[bool] = None, voc_fuse_resblocks: Optional[bool] = None,
                 lin_fuse_ffn: Optional[bool] = None, ses_tensor_cores: Optional[bool] = None,
-                emformer_memory_size: Optional[int] = None) -> _lib.ConanConfig:
+                emformer_memory_size: Optional[int] = None, step_graphs: bool = True) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -84,6 +84,7 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     # torchaudio Emformer max_memory_size: the reference never passes it (modules/Emformer/emformer.py:14-22 -> 0); an
     # `emformer_memory_size` hparam / argument enables the memory bank for checkpoints trained with one
     cfg.emformer_memory_size = int(hp.get("emformer_memory_size", 0) if emformer_memory_size is None else emformer_memory_size)
+    cfg.step_graphs = int(bool(step_graphs))
     return cfg
 
 
@@ -165,6 +166,10 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.conan_engine_launch_count(self.h))
+
+    @property
+    def graph_replays(self) -> int:
+        return int(self.lib.conan_engine_graph_replays(self.h))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -93,7 +93,9 @@ typedef struct conan_config {
                                      12.8 GFLOP per session) on tcgen05 with split-fp16 operands; 0: fp32 FFMA */
   int32_t emformer_memory_size;   /* torchaudio Emformer max_memory_size M (0 in the reference config, modules/Emformer/emformer.py:14-22):
                                      M > 0 keeps a bank of the last M memory vectors per layer and stream and adds the summary query */
-  int32_t reserved[2];
+  int32_t step_graphs;            /* 1: conan_step / conan_step_host* replay a CUDA graph of the whole chunk step (captured once per distinct
+                                     ready count and buffer set; the slot ids stay an indirection read from the device buffer) */
+  int32_t reserved[1];
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */
@@ -187,6 +189,9 @@ CONAN_API int conan_step_host_wait(conan_engine_t* eng, int ticket);
 
 /* kernels launched by this engine since creation (bench.py's gpu_launches claim) */
 CONAN_API uint64_t conan_engine_launch_count(const conan_engine_t* eng);
+
+/* chunk steps served by replaying a captured CUDA graph since creation (0 when step_graphs is off) */
+CONAN_API uint64_t conan_engine_graph_replays(const conan_engine_t* eng);
 
 /* Per-launch CUDA-event timing of the conv engines (measurement only: events are recorded on the
  * launching stream around every conv launch while enabled).  category 0 = FFMA, 1 = tcgen05 ring kernel

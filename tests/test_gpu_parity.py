@@ -128,6 +128,10 @@ TC_SHAPES = [
     (64, 64, 11, 5, 640, 2), (64, 64, 3, 1, 640, 1),
     (32, 32, 3, 1, 1280, 2), (32, 32, 11, 5, 1280, 1), (32, 32, 7, 3, 1280, 3),
     (256, 640, 10, 1, 32, 6), (128, 256, 8, 1, 160, 2), (64, 64, 4, 1, 640, 2), (512, 2048, 16, 1, 4, 40),
+    # enough 256-row tiles for the CTA-pair kernel (tcgen05.mma.cta_group::2): BN = 256 and BN = 128, odd and even tile counts,
+    # a stream count that leaves the last tile partly empty
+    (256, 256, 3, 1, 32, 601), (256, 256, 7, 3, 32, 596), (128, 128, 11, 1, 160, 121), (512, 2048, 16, 1, 4, 2100),
+    (256, 640, 10, 1, 32, 700),
 ]
 
 
@@ -604,6 +608,45 @@ def test_end_to_end_vs_reference_golden(which, name, request, golden_dir):
     assert sa >= SNR_MIN_DB
     if which in ("eng_fp32", "eng_split"):          # fp32-grade engines: CUDA-core fp32, and split-fp16 on the tensor cores
         assert np.abs(wav - d["wav"]).max() < 2e-4
+
+
+def test_step_graph_replay_is_bitwise_equal_to_eager_launches(state_dicts):
+    """A chunk step replayed from its CUDA graph (captured at the second step with the same ready count and buffers) must equal
+    the eager launch sequence bit for bit, while the CONTENT of the slot-id buffer changes from step to step (slot indirection:
+    the graph bakes in pointers and grids, not which streams are ready) and the ready count changes in between."""
+    outs = {}
+    for graphs in (False, True):
+        eng = _engine(state_dicts, step_graphs=graphs)
+        S = 6
+        ref = torch.stack([synth.synth_mel(40, 300 + s) for s in range(S)])
+        src = torch.stack([synth.synth_mel(4 * 9 + 2, 400 + s) for s in range(S)])
+        eng.reset_slots(list(range(S)))
+        eng.open_sessions(list(range(S)), ref.cuda())
+        ids4 = eng.ids_tensor([0, 1, 2, 3])
+        ids2 = eng.ids_tensor([4, 5])
+        ch4, ch2 = torch.empty(4, 6, 80, device="cuda"), torch.empty(2, 6, 80, device="cuda")
+        w4, m4, t4 = torch.empty(4, 1280, device="cuda"), torch.empty(4, 4, 80, device="cuda"), torch.empty(4, 4, dtype=torch.int32, device="cuda")
+        w2, m2, t2 = torch.empty(2, 1280, device="cuda"), torch.empty(2, 4, 80, device="cuda"), torch.empty(2, 4, dtype=torch.int32, device="cuda")
+        got = []
+        order = [[0, 1, 2, 3], [3, 2, 1, 0], [1, 3, 0, 2]]
+        for step in range(9):
+            perm = order[step % 3]
+            ids4.copy_(torch.tensor(perm, dtype=torch.int32))                  # same buffer, new ready list
+            ch4.copy_(src[perm, step * 4:step * 4 + 6])
+            eng.step(ids4, ch4, w4, m4, t4)
+            inv = torch.tensor([perm.index(s) for s in range(4)])
+            got.append((w4.cpu()[inv], m4.cpu()[inv], t4.cpu()[inv]))
+            if step % 2 == 0:                                                  # another ready count in between
+                k = step // 2
+                ch2.copy_(src[4:6, k * 4:k * 4 + 6])
+                eng.step(ids2, ch2, w2, m2, t2)
+                got.append((w2.cpu(), m2.cpu(), t2.cpu()))
+        assert (eng.graph_replays > 0) == graphs
+        outs[graphs] = got
+        eng.close()
+    for a, b in zip(outs[False], outs[True]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
 
 
 def test_step_host_equals_device_step(eng_tc):
