@@ -111,8 +111,9 @@ def traffic(src, dst):
         n = d["name"]
         key = ("resblock_fused_kernel" if "resblock_fused" in n else "ffn_fused_kernel" if "ffn_fused" in n else
                "conv_window_tc_kernel" if "conv_window_tc" in n else
-               # the vocoder layers run the <128, 64, 3, ...> variants; every other variant is a split-fp16 Emformer / Conan GEMM
-               ("conv_gemm_tc_kernel (" if re.search(r"<\(?i?n?t?\)?128, \(?i?n?t?\)?64, \(?i?n?t?\)?3,", n) else "conv_gemm_tc_kernel, split")
+               # fp16-operand vocoder layers: the CTA-pair kernel (conv_gemm_tc2_kernel) and the single-CTA ring variants whose last
+               # template argument (SP, four-tile split stages) is 0; SP = 1 marks a split-fp16 Emformer / Conan GEMM
+               ("conv_gemm_tc_kernel (" if ("conv_gemm_tc2" in n or re.search(r"0\)?>", n.split("(")[0] if "<" in n.split("(")[0] else n)) else "conv_gemm_tc_kernel, split")
                if "conv_gemm_tc" in n else
                "conv_gemm_ffma_kernel" if "conv_gemm_ffma" in n else None)
         if key is None:
