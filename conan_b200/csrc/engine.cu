@@ -56,7 +56,9 @@ struct conan_engine {
   bool finalized = false;
   std::vector<void*> allocs;
   size_t state_bytes = 0;
-  int S = 0, tp_max = 0;
+  int S = 0, tp_max = 0;     // S: slots allocated = max_slots + kPadSlots
+  int Su = 0;                // slots the caller may use (cfg.max_slots); the rest pad ready lists to graph bucket sizes
+  int* padIds = nullptr;     // device: ids of the pad slots
   bool lin_tc = false;       // Emformer / Conan contractions on tcgen05 with split-fp16 operands
   bool ses_tc = false;       // session setup: the style encoder's ConvBlocks (95 % of the setup FLOPs) on tcgen05, split-fp16 operands
   int DP = 0, QP = 0, LP = 0;   // (padded) Emformer model dim, QKV width, logits width
@@ -289,6 +291,10 @@ inline int fused_weight_copies() {        // CONAN_FUSED_WCOPIES=1..16 (A/B of t
   static int n = [] { const char* v = getenv("CONAN_FUSED_WCOPIES"); int x = v ? atoi(v) : 8; return x < 1 ? 1 : (x > kFusedWeightCopies ? kFusedWeightCopies : x); }();
   return n;
 }
+// Ready lists of the host entry points are padded to a multiple of kStepBucket with dedicated pad slots (distinct ids past
+// max_slots, inputs = whatever the staging buffer holds, outputs dropped), so a serving loop whose ready count changes every
+// step replays a handful of captured graphs instead of capturing one per distinct count.
+constexpr int kStepBucket = 8, kPadSlots = kStepBucket - 1;
 constexpr float kSplitWeightScale = 1024.f;      // split weights are packed as 2^10 * W (keeps W_lo out of the fp16 subnormals)
 
 // ---- conv parameter builders (all compact: stream i of the ready list, no slot indirection) -----
@@ -597,6 +603,12 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->qSlots, (size_t)SB));
   // ---- host-call staging
   TRY(dalloc(e, &e->hIds, (size_t)S)); TRY(dalloc(e, &e->hIdsSmall, (size_t)S));
+  {
+    int pad[kPadSlots];
+    for (int i = 0; i < kPadSlots; ++i) pad[i] = e->Su + i;
+    TRY(dalloc(e, &e->padIds, (size_t)kPadSlots));
+    CONAN_CUDA_OK(cudaMemcpy(e->padIds, pad, sizeof(pad), cudaMemcpyHostToDevice));
+  }
   TRY(dalloc(e, &e->hChunk, (size_t)S * rows * D));
   TRY(dalloc(e, &e->hWav, (size_t)S * e->vL[c.voc_n_ups])); TRY(dalloc(e, &e->hMel, (size_t)S * seg * c.n_mels));
   TRY(dalloc(e, &e->hTok, (size_t)S * seg));
@@ -1088,10 +1100,10 @@ int session_open_batch(conan_engine* e, int n, const int* slots_host, const floa
 // A ready list handed over in HOST memory is checked before it reaches the device: an out-of-range id would be an
 // out-of-bounds read / write of resident state, a duplicate would make two CTAs race on one stream's K/V ring and history.
 int check_ids_host(conan_engine* e, int n, const int32_t* ids, const char* who) {
-  e->idSeen.assign((size_t)e->S, 0);
+  e->idSeen.assign((size_t)e->Su, 0);
   for (int i = 0; i < n; ++i) {
     const int s = ids[i];
-    if (s < 0 || s >= e->S) { set_error(std::string(who) + ": slot id " + std::to_string(s) + " out of range [0, " + std::to_string(e->S) + ")"); return 1; }
+    if (s < 0 || s >= e->Su) { set_error(std::string(who) + ": slot id " + std::to_string(s) + " out of range [0, " + std::to_string(e->Su) + ")"); return 1; }
     if (e->idSeen[s]) { set_error(std::string(who) + ": slot id " + std::to_string(s) + " appears twice in one step"); return 1; }
     e->idSeen[s] = 1;
   }
@@ -1142,7 +1154,8 @@ int conan_engine_create(const conan_config_t* cfg, conan_engine_t** out) {
   CONAN_CUDA_OK(cudaSetDevice(cfg->device));
   conan_engine* e = new conan_engine();
   e->cfg = *cfg;
-  e->S = cfg->max_slots;
+  e->Su = cfg->max_slots;
+  e->S = cfg->max_slots + kPadSlots;
   e->tp_max = (cfg->max_ref_frames - 1) / 4 + 1;
   e->lin_tc = cfg->lin_use_tensor_cores != 0;
   e->ses_tc = cfg->ses_use_tensor_cores != 0;
@@ -1205,6 +1218,26 @@ int conan_engine_finalize(conan_engine_t* e) {
   }
   CONAN_CUDA_OK(cudaDeviceSynchronize());
   e->finalized = true;
+  {
+    // the pad slots get a real (dummy) session so that every kernel sees a well-formed stream in them: 8 reference frames of a
+    // constant spectrum; their outputs are never returned
+    const int T = std::min(8, e->cfg.max_ref_frames), M = e->cfg.n_mels;
+    std::vector<float> ref((size_t)kPadSlots * T * M);
+    for (size_t i = 0; i < ref.size(); ++i) ref[i] = -3.0f + 0.01f * (float)(i % 7);
+    std::vector<int> pad(kPadSlots);
+    for (int i = 0; i < kPadSlots; ++i) pad[i] = e->Su + i;
+    float* dref = nullptr;
+    CONAN_CUDA_OK(cudaMalloc(&dref, ref.size() * sizeof(float)));
+    CONAN_CUDA_OK(cudaMemcpy(dref, ref.data(), ref.size() * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = 0;
+    for (int g = 0; g < kPadSlots && !rc; g += e->SB) {
+      const int nb = std::min(e->SB, kPadSlots - g);
+      rc = session_open_batch(e, nb, pad.data() + g, dref + (size_t)g * T * M, T, nullptr);
+    }
+    cudaError_t ce = cudaDeviceSynchronize();
+    cudaFree(dref);
+    if (rc || ce != cudaSuccess) { if (!rc) set_error(std::string("pad-slot session setup: ") + cudaGetErrorString(ce)); e->finalized = false; return 1; }
+  }
   return 0;
 }
 
@@ -1215,8 +1248,8 @@ uint64_t conan_engine_graph_replays(const conan_engine_t* e) { return e ? e->gra
 int conan_slots_reset(conan_engine_t* e, int n, const int32_t* slots_host, int parts, void* stream) {
   if (check_ready(e)) return 1;
   if (n <= 0) return 0;
-  if (n > e->S) { set_error("more slots than max_slots"); return 1; }
-  for (int i = 0; i < n; ++i) if (slots_host[i] < 0 || slots_host[i] >= e->S) { set_error("slot id out of range"); return 1; }
+  if (n > e->Su) { set_error("more slots than max_slots"); return 1; }
+  for (int i = 0; i < n; ++i) if (slots_host[i] < 0 || slots_host[i] >= e->Su) { set_error("slot id out of range"); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
   CONAN_CUDA_OK(cudaMemcpyAsync(e->hIdsSmall, slots_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
   if (parts & 1) TRY(launch_zero_slots(e->zeroEmf, e->nZeroEmf, n, e->hIdsSmall, st));
@@ -1231,7 +1264,7 @@ int conan_session_open(conan_engine_t* e, int n, const int32_t* slots_host, cons
   if (check_ready(e)) return 1;
   if (n <= 0) return 0;
   if (ref_frames < 1 || ref_frames > e->cfg.max_ref_frames) { set_error("ref_frames outside [1, max_ref_frames]"); return 1; }
-  for (int i = 0; i < n; ++i) if (slots_host[i] < 0 || slots_host[i] >= e->S) { set_error("slot id out of range"); return 1; }
+  for (int i = 0; i < n; ++i) if (slots_host[i] < 0 || slots_host[i] >= e->Su) { set_error("slot id out of range"); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < n; g += e->SB) {
     int nb = std::min(e->SB, n - g);
@@ -1245,7 +1278,7 @@ int conan_session_open(conan_engine_t* e, int n, const int32_t* slots_host, cons
 int conan_emformer_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* enc_out_dev,
                         float* logits_out_dev, int32_t* tokens_out_dev, void* stream) {
   if (check_ready(e)) return 1;
-  if (n < 0 || n > e->S || !slot_ids_dev || !chunk_dev) { set_error("bad arguments to conan_emformer_step"); return 1; }
+  if (n < 0 || n > e->Su || !slot_ids_dev || !chunk_dev) { set_error("bad arguments to conan_emformer_step"); return 1; }
   return emformer_step(e, n, slot_ids_dev, chunk_dev, enc_out_dev, logits_out_dev, tokens_out_dev, (cudaStream_t)stream);
 }
 
@@ -1255,7 +1288,7 @@ int conan_emformer_forward(conan_engine_t* e, int n, const int32_t* slots_host, 
   if (n <= 0) return 0;
   const conan_config_t& c = e->cfg;
   const int seg = c.segment, rc = c.right_context, D = c.emformer_dim, T = frames - rc;
-  if (n > e->S || !slots_host || !input_dev || T < 1) { set_error("bad arguments to conan_emformer_forward (needs frames > right_context)"); return 1; }
+  if (n > e->Su || !slots_host || !input_dev || T < 1) { set_error("bad arguments to conan_emformer_forward (needs frames > right_context)"); return 1; }
   if (check_ids_host(e, n, slots_host, "conan_emformer_forward")) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   CONAN_CUDA_OK(cudaMemcpyAsync(e->hIds, slots_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1291,13 +1324,13 @@ int conan_emformer_forward(conan_engine_t* e, int n, const int32_t* slots_host, 
 
 int conan_decoder_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const int32_t* tokens_dev, float* mel_out_dev, void* stream) {
   if (check_ready(e)) return 1;
-  if (n < 0 || n > e->S || !slot_ids_dev || !tokens_dev) { set_error("bad arguments to conan_decoder_step"); return 1; }
+  if (n < 0 || n > e->Su || !slot_ids_dev || !tokens_dev) { set_error("bad arguments to conan_decoder_step"); return 1; }
   return decoder_step(e, n, slot_ids_dev, tokens_dev, mel_out_dev, (cudaStream_t)stream);
 }
 
 int conan_vocoder_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* mel_dev, float* wav_out_dev, void* stream) {
   if (check_ready(e)) return 1;
-  if (n < 0 || n > e->S || !slot_ids_dev || !mel_dev || !wav_out_dev) { set_error("bad arguments to conan_vocoder_step"); return 1; }
+  if (n < 0 || n > e->Su || !slot_ids_dev || !mel_dev || !wav_out_dev) { set_error("bad arguments to conan_vocoder_step"); return 1; }
   return vocoder_step(e, n, slot_ids_dev, mel_dev, wav_out_dev, (cudaStream_t)stream);
 }
 
@@ -1309,11 +1342,26 @@ static int step_eager(conan_engine_t* e, int n, const int32_t* slot_ids_dev, con
   return 0;
 }
 
+static int step_graphed(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* wav_out_dev, float* mel_out_dev,
+                        int32_t* tokens_out_dev, cudaStream_t st);
+
 int conan_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* wav_out_dev, float* mel_out_dev,
                int32_t* tokens_out_dev, void* stream) {
   if (check_ready(e)) return 1;
-  if (n < 0 || n > e->S || !slot_ids_dev || !chunk_dev || !wav_out_dev) { set_error("bad arguments to conan_step"); return 1; }
-  cudaStream_t st = (cudaStream_t)stream;
+  if (n < 0 || n > e->Su || !slot_ids_dev || !chunk_dev || !wav_out_dev) { set_error("bad arguments to conan_step"); return 1; }
+  return step_graphed(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, (cudaStream_t)stream);
+}
+
+// pads a ready list staged in hIds to the next multiple of kStepBucket with the pad slots (graph mode only); returns the padded count
+static int pad_ready_list(conan_engine_t* e, int n, cudaStream_t st) {
+  if (!e->graphMode || n == 0) return n;
+  const int np = std::min((n + kStepBucket - 1) / kStepBucket * kStepBucket, e->S);
+  if (np > n) cudaMemcpyAsync(e->hIds + n, e->padIds, (size_t)(np - n) * sizeof(int), cudaMemcpyDeviceToDevice, st);
+  return np;
+}
+
+static int step_graphed(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const float* chunk_dev, float* wav_out_dev, float* mel_out_dev,
+                        int32_t* tokens_out_dev, cudaStream_t st) {
   if (!e->graphMode || e->profiling || n == 0) return step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, st);
   auto same = [&](const conan_engine::StepGraph& g) {
     return g.n == n && g.ids == slot_ids_dev && g.chunk == chunk_dev && g.wav == wav_out_dev && g.mel == mel_out_dev && g.tok == tokens_out_dev;
@@ -1370,7 +1418,7 @@ int conan_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const floa
 int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
                     float* mel_out_host, int32_t* tokens_out_host, void* stream) {
   if (check_ready(e)) return 1;
-  if (n < 0 || n > e->S || !slot_ids_host || !chunk_host || !wav_out_host) { set_error("bad arguments to conan_step_host"); return 1; }
+  if (n < 0 || n > e->Su || !slot_ids_host || !chunk_host || !wav_out_host) { set_error("bad arguments to conan_step_host"); return 1; }
   if (e->ticketPending[0] || e->ticketPending[1]) {
     // the synchronous call shares output set 0 with the pipelined one: its result copy may still be in flight
     set_error("conan_step_host: pipelined steps are in flight; call conan_step_host_wait first");
@@ -1382,7 +1430,8 @@ int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, cons
   const size_t rows = c.segment + c.right_context, Lw = e->vL[c.voc_n_ups];
   CONAN_CUDA_OK(cudaMemcpyAsync(e->hIds, slot_ids_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
   CONAN_CUDA_OK(cudaMemcpyAsync(e->hChunk, chunk_host, (size_t)n * rows * c.emformer_dim * 4, cudaMemcpyHostToDevice, st));
-  TRY(conan_step(e, n, e->hIds, e->hChunk, e->hWav, mel_out_host ? e->hMel : nullptr, tokens_out_host ? e->hTok : nullptr, stream));
+  const int np = pad_ready_list(e, n, st);
+  TRY(step_graphed(e, np, e->hIds, e->hChunk, e->hWav, mel_out_host ? e->hMel : nullptr, tokens_out_host ? e->hTok : nullptr, st));
   CONAN_CUDA_OK(cudaMemcpyAsync(wav_out_host, e->hWav, (size_t)n * Lw * 4, cudaMemcpyDeviceToHost, st));
   if (mel_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out_host, e->hMel, (size_t)n * c.segment * c.n_mels * 4, cudaMemcpyDeviceToHost, st));
   if (tokens_out_host) CONAN_CUDA_OK(cudaMemcpyAsync(tokens_out_host, e->hTok, (size_t)n * c.segment * 4, cudaMemcpyDeviceToHost, st));
@@ -1393,7 +1442,7 @@ int conan_step_host(conan_engine_t* e, int n, const int32_t* slot_ids_host, cons
 int conan_step_host_submit(conan_engine_t* e, int n, const int32_t* slot_ids_host, const float* chunk_host, float* wav_out_host,
                            float* mel_out_host, int32_t* tokens_out_host, void* stream, int* ticket) {
   if (check_ready(e)) return 1;
-  if (n < 0 || n > e->S || !slot_ids_host || !chunk_host || !wav_out_host || !ticket) { set_error("bad arguments to conan_step_host_submit"); return 1; }
+  if (n < 0 || n > e->Su || !slot_ids_host || !chunk_host || !wav_out_host || !ticket) { set_error("bad arguments to conan_step_host_submit"); return 1; }
   const conan_config_t& c = e->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   const int b = (int)(e->submitCount & 1);
@@ -1405,7 +1454,8 @@ int conan_step_host_submit(conan_engine_t* e, int n, const int32_t* slot_ids_hos
   CONAN_CUDA_OK(cudaMemcpyAsync(e->hChunk, chunk_host, (size_t)n * rows * c.emformer_dim * 4, cudaMemcpyHostToDevice, st));
   // output set b was last read by the copy of ticket b two submits ago: that copy has been waited for by the caller
   // (ticketPending[b] is clear), so the step may overwrite it
-  TRY(conan_step(e, n, e->hIds, e->hChunk, dWav, mel_out_host ? dMel : nullptr, tokens_out_host ? dTok : nullptr, stream));
+  const int np = pad_ready_list(e, n, st);
+  TRY(step_graphed(e, np, e->hIds, e->hChunk, dWav, mel_out_host ? dMel : nullptr, tokens_out_host ? dTok : nullptr, st));
   CONAN_CUDA_OK(cudaEventRecord(e->evCompute[b], st));
   CONAN_CUDA_OK(cudaStreamWaitEvent(e->copyStream, e->evCompute[b], 0));
   CONAN_CUDA_OK(cudaMemcpyAsync(wav_out_host, dWav, (size_t)n * Lw * 4, cudaMemcpyDeviceToHost, e->copyStream));
@@ -1453,7 +1503,7 @@ int conan_engine_profile_read(conan_engine_t* e, int category, double* ms, uint6
 
 int conan_debug_read(conan_engine_t* e, const char* name, int slot, float* out_dev, size_t capacity, size_t* numel, void* stream) {
   if (check_ready(e)) return 1;
-  if (slot < 0 || slot >= e->S) { set_error("slot id out of range"); return 1; }
+  if (slot < 0 || slot >= e->Su) { set_error("slot id out of range"); return 1; }
   const conan_config_t& c = e->cfg;
   const void* src = nullptr; size_t cnt = 0;
   std::string nm(name ? name : "");
