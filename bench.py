@@ -680,7 +680,7 @@ def run_b200(args):
     NPROF = 2
     for i in range(NPROF):
         rig.step()
-    prof = {cat: eng.profile_read(cat) for cat in range(6)}
+    prof = {cat: eng.profile_read(cat) for cat in range(7)}
     eng.set_profiling(False)
 
     e2e_ms, e2e_sync_ms = allmax(e2e_ms, e2e_sync_ms)
@@ -695,7 +695,8 @@ def run_b200(args):
                  2: ("conv_window_tc_kernel (tcgen05, persistent, weights resident, one input window per tile: vocoder scales 2-3)", "hbm"),
                  3: ("conv_gemm_tc_kernel, split-fp16 operands (Emformer / Conan linear + conv contractions, 3 MMAs per product)", "tensor"),
                  4: ("resblock_fused_kernel (tcgen05, one HiFi-GAN residual block = six convs per launch, activations in shared memory: vocoder scales 2-3)", "tensor"),
-                 5: ("ffn_fused_kernel (tcgen05, Emformer 80 -> 2048 -> 80 feed-forward in one launch, split-fp16 operands, hidden activation in shared memory)", "tensor")}
+                 5: ("ffn_fused_kernel (tcgen05, Emformer 80 -> 2048 -> 80 feed-forward in one launch, split-fp16 operands, hidden activation in shared memory)", "tensor"),
+                 6: ("block_fused_kernel (tcgen05, Conan decoder residual block body / aligner feed-forward: two GEMMs per launch, split-fp16 operands)", "tensor")}
         roofs = {}
         for cat, (ms, nl, fl, by) in prof.items():
             if nl == 0:

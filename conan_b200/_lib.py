@@ -30,7 +30,7 @@ class ConanConfig(C.Structure):
         ("voc_res_dilations", C.c_int32 * 8), ("voc_n_dil", C.c_int32),
         ("voc_precision", C.c_int32), ("voc_use_tensor_cores", C.c_int32), ("voc_group", C.c_int32),
         ("voc_residual_from_ctx", C.c_int32), ("lin_use_tensor_cores", C.c_int32), ("voc_fuse_resblocks", C.c_int32), ("lin_fuse_ffn", C.c_int32),
-        ("ses_use_tensor_cores", C.c_int32), ("emformer_memory_size", C.c_int32), ("step_graphs", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("ses_use_tensor_cores", C.c_int32), ("emformer_memory_size", C.c_int32), ("step_graphs", C.c_int32), ("lin_fuse_blocks", C.c_int32),
     ]
 
 

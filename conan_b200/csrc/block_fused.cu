@@ -1,0 +1,318 @@
+// Two-GEMM residual block of the Conan chunk path as ONE tcgen05 kernel with fp32-grade split-fp16 operands:
+//
+//   h = act(scale * (conv_k(x) + b1))        GEMM1: K1 = k taps x C1 channels  ->  hidden (chunks of 128)
+//   y = W2 . h                               GEMM2: hidden -> N2 = 256, accumulated in TMEM across the hidden chunks of the CTA
+//
+// covering (a) the decoder's CausalResidualBlock body: causal conv k5 256 -> 512, x 5^-1/2, erf-GELU, 1x1 512 -> 256
+// (modules/commons/conv.py:127-178) and (b) the aligner layer's feed-forward 256 -> 2048 ReLU -> 256
+// (modules/Conan/prosody_util.py:108-127).  As separate launches the hidden tensor makes a round trip through HBM as a split
+// fp16 pair and the second GEMM is one more deep, launch-bound kernel; here it stays in shared memory in exactly the swizzled
+// K-major layout GEMM2 reads (same construction as ffn_fused.cu, which does this for the Emformer's 96-wide rows).
+//
+// A CTA owns a 128-row tile of (stream, time) rows and a slice of the hidden dimension.  GEMM1's operands are streamed: one ring
+// slot (32 KB) per (tap, 32-channel block) holds A_hi, A_lo (TMA boxes {32 ch, TT rows, 128/TT streams} of the compact context
+// buffer at row offset = tap) and W1_hi, W1_lo, and feeds the three MMA groups A_hi W_hi + A_hi W_lo + A_lo W_hi.  GEMM2's weight
+// tiles (256 x 64, hi and lo) go through the same ring.  acc1 is double-buffered in TMEM (2 x 128 columns) next to acc2 (256
+// columns).  Each CTA writes its partial y * 2^-10 to P[fs][row][256]; the LayerNorm that follows sums the partials with b2 and
+// the residual (deterministic, no atomics).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace conan {
+
+namespace {
+
+constexpr int BF_THREADS = 384;        // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 4..11: epilogue
+constexpr int BF_EPI = 256;
+constexpr int BF_N2 = 256;
+constexpr int BF_CH = 128;             // hidden chunk
+constexpr int BF_SLOTS = 4;
+constexpr int BF_SLOT_BYTES = 32768;   // GEMM1: A_hi | A_lo | W1_hi | W1_lo (8 KB each, 32-wide k-block); GEMM2: one 256 x 64 W2 tile
+constexpr int BF_T8 = 8192;
+constexpr int BF_H_TILE = TILE_M * 128;                        // 128 rows x 64 halfs (128-byte swizzle)
+constexpr int BF_OFF_W = 0;
+constexpr int BF_OFF_H = BF_SLOTS * BF_SLOT_BYTES;             // 131072
+constexpr int BF_OFF_BAR = BF_OFF_H + 4 * BF_H_TILE;           // 196608
+constexpr int BF_SMEM = BF_OFF_BAR + 1024 + 1024;
+
+struct BfArgs {
+  int n_streams, L, TT, C1, k, row0, lo_slot_off;
+  int hidden, n_chunks, FS;
+  int K1;                       // k * C1
+  const float* b1;
+  float scale1; int act;
+  float* P; long long M;        // [FS][M][256]
+  float acc_scale;
+};
+
+__global__ void __launch_bounds__(BF_THREADS, 1)
+block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                   const __grid_constant__ CUtensorMap tmW2, BfArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BF_OFF_BAR);
+  uint64_t* acc1_full = bars;              // [2]
+  uint64_t* acc1_empty = bars + 2;         // [2]
+  uint64_t* h_full = bars + 4;             // [1]
+  uint64_t* h_empty = bars + 5;            // [1]
+  uint64_t* acc2_full = bars + 6;          // [1]
+  uint64_t* w_full = bars + 8;             // [SLOTS]
+  uint64_t* w_empty = w_full + BF_SLOTS;   // [SLOTS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + BF_SLOTS);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / a.FS, fs = blockIdx.x - mt * a.FS;
+  const int c_begin = (a.n_chunks * fs) / a.FS, c_end = (a.n_chunks * (fs + 1)) / a.FS, nc = c_end - c_begin;
+  const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
+  const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
+  const int kb1 = a.K1 / 32;                // GEMM1 k-blocks per chunk
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    mbar_init(h_full, BF_EPI); mbar_init(h_empty, 1); mbar_init(acc2_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], BF_EPI); }
+    for (int s = 0; s < BF_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer, in the order the MMA warp consumes:
+    // G1(0), then per chunk [G1(c+1)], G2(c)
+    int s = 0;
+    uint32_t ph = 1;
+    auto g1 = [&](int c) {
+      const int f0 = (c_begin + c) * BF_CH;
+      int j = 0, c0 = 0;
+      for (int kb = 0; kb < kb1; ++kb) {
+        mbar_wait_warp(&w_empty[s], ph);
+        if (elect_one_sync()) {
+          uint8_t* d = smem + BF_OFF_W + s * BF_SLOT_BYTES;
+          mbar_expect_tx(&w_full[s], 4 * BF_T8);
+          tma_load_3d(d, &tmX, &w_full[s], c0, a.row0 + t0 + j, stream0);                          // A_hi: box {32, TT, NS}
+          tma_load_3d(d + BF_T8, &tmX, &w_full[s], c0, a.row0 + t0 + j, stream0 + a.lo_slot_off);  // A_lo
+          tma_load_2d(d + 2 * BF_T8, &tmW1, &w_full[s], kb * 32, f0);                              // W1_hi: box {32, 128}
+          tma_load_2d(d + 3 * BF_T8, &tmW1, &w_full[s], a.K1 + kb * 32, f0);                       // W1_lo
+        }
+        if (++s == BF_SLOTS) { s = 0; ph ^= 1; }
+        c0 += 32;
+        if (c0 == a.C1) { c0 = 0; ++j; }
+      }
+    };
+    auto g2 = [&](int c) {
+      const int f0 = (c_begin + c) * BF_CH;
+      for (int t = 0; t < 4; ++t) {                          // (kb2, hi | lo): W2 tiles of 256 output rows x 64 hidden columns
+        const int kb2 = t >> 1, lo = t & 1;
+        mbar_wait_warp(&w_empty[s], ph);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&w_full[s], BF_SLOT_BYTES);
+          tma_load_2d(smem + BF_OFF_W + s * BF_SLOT_BYTES, &tmW2, &w_full[s], lo * a.hidden + f0 + kb2 * 64, 0);
+        }
+        if (++s == BF_SLOTS) { s = 0; ph ^= 1; }
+      }
+    };
+    g1(0);
+    for (int c = 0; c < nc; ++c) {
+      if (c + 1 < nc) g1(c + 1);
+      g2(c);
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (warp-uniform, one elected lane issues)
+    constexpr uint32_t idesc1 = make_idesc<BF_CH>();
+    constexpr uint32_t idesc2 = make_idesc<BF_N2>();
+    const uint32_t s32 = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 0;
+    auto g1 = [&](int c) {
+      const int b = c & 1;
+      mbar_wait_warp(&acc1_empty[b], ((c >> 1) & 1) ^ 1);           // epilogue 1 of chunk c-2 has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(b * BF_CH);
+      for (int kb = 0; kb < kb1; ++kb) {
+        mbar_wait_warp(&w_full[s], ph);
+        tc_fence_after();
+        const uint32_t d = s32 + BF_OFF_W + s * BF_SLOT_BYTES;
+        const uint64_t a_hi = make_smem_desc<64>(d), a_lo = make_smem_desc<64>(d + BF_T8);
+        const uint64_t w_hi = make_smem_desc<64>(d + 2 * BF_T8), w_lo = make_smem_desc<64>(d + 3 * BF_T8);
+        tc_mma_f16_tap<2>(tacc, a_hi, w_hi, idesc1, kb == 0 ? 1u : 0u);
+        tc_mma_f16_tap<2>(tacc, a_hi, w_lo, idesc1, 0u);
+        tc_mma_f16_tap<2>(tacc, a_lo, w_hi, idesc1, 0u);
+        if (elect_one_sync()) tc_commit(&w_empty[s]);
+        if (++s == BF_SLOTS) { s = 0; ph ^= 1; }
+      }
+      if (elect_one_sync()) tc_commit(&acc1_full[b]);
+    };
+    auto g2 = [&](int c) {
+      mbar_wait_warp(h_full, c & 1);                                 // epilogue 1 of chunk c has written h (hi, lo)
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + 256u;
+#pragma unroll
+      for (int kb2 = 0; kb2 < 2; ++kb2) {
+        const uint64_t h_hi = make_smem_desc<128>(s32 + BF_OFF_H + (0 * 2 + kb2) * BF_H_TILE);
+        const uint64_t h_lo = make_smem_desc<128>(s32 + BF_OFF_H + (1 * 2 + kb2) * BF_H_TILE);
+        // slot t = 2 kb2: W2_hi, slot 2 kb2 + 1: W2_lo.  Products: h_hi W_hi, h_lo W_hi (same slot), then h_hi W_lo.
+        mbar_wait_warp(&w_full[s], ph);
+        tc_fence_after();
+        const uint64_t w_hi = make_smem_desc<128>(s32 + BF_OFF_W + s * BF_SLOT_BYTES);
+        tc_mma_f16_tap<4>(tacc, h_hi, w_hi, idesc2, (c == 0 && kb2 == 0) ? 1u : 0u);
+        tc_mma_f16_tap<4>(tacc, h_lo, w_hi, idesc2, 0u);
+        if (elect_one_sync()) tc_commit(&w_empty[s]);
+        if (++s == BF_SLOTS) { s = 0; ph ^= 1; }
+        mbar_wait_warp(&w_full[s], ph);
+        tc_fence_after();
+        const uint64_t w_lo = make_smem_desc<128>(s32 + BF_OFF_W + s * BF_SLOT_BYTES);
+        tc_mma_f16_tap<4>(tacc, h_hi, w_lo, idesc2, 0u);
+        if (elect_one_sync()) tc_commit(&w_empty[s]);
+        if (++s == BF_SLOTS) { s = 0; ph ^= 1; }
+      }
+      if (elect_one_sync()) tc_commit(h_empty);                      // h may be overwritten once these MMAs have read it
+    };
+    g1(0);
+    for (int c = 0; c < nc; ++c) {
+      if (c + 1 < nc) g1(c + 1);
+      g2(c);
+    }
+    if (elect_one_sync()) tc_commit(acc2_full);
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue warps: wg 0 / 1 = hidden columns 0-63 / 64-127
+    const int wg = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const bool gelu = a.act == ACT_GELU;
+    for (int c = 0; c < nc; ++c) {
+      const int b = c & 1;
+      const float* b1 = a.b1 + (long long)(c_begin + c) * BF_CH + wg * 64;
+      mbar_wait_lane0(&acc1_full[b], (c >> 1) & 1, 0);
+      mbar_wait_lane0(h_empty, (c & 1) ^ 1, 0);                      // GEMM2 of chunk c-1 has finished reading h
+      tc_fence_after();
+      uint8_t* hhi = smem + BF_OFF_H + (0 * 2 + wg) * BF_H_TILE + r * 128;
+      uint8_t* hlo = smem + BF_OFF_H + (1 * 2 + wg) * BF_H_TILE + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t acc[16];
+        tc_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(b * BF_CH + wg * 64 + ch * 16), acc);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          __half2 hi[4], lo[4];
+          const float4 ba = *reinterpret_cast<const float4*>(b1 + ch * 16 + h8 * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(b1 + ch * 16 + h8 * 8 + 4);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float x = fmaf(__uint_as_float(acc[h8 * 8 + u]), a.acc_scale, bv[u]) * a.scale1;
+            v[u] = gelu ? 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)) : fmaxf(x, 0.f);     // warp-uniform branch
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            hi[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+            const float2 hf = __half22float2(hi[u]);
+            lo[u] = __floats2half2_rn(v[2 * u] - hf.x, v[2 * u + 1] - hf.y);
+          }
+          const uint32_t chunk = (uint32_t)((ch * 2 + h8) ^ (r & 7)) << 4;      // 128-byte swizzle on a 1024-aligned tile
+          *reinterpret_cast<uint4*>(hhi + chunk) = *reinterpret_cast<uint4*>(hi);
+          *reinterpret_cast<uint4*>(hlo + chunk) = *reinterpret_cast<uint4*>(lo);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(h_full);
+      mbar_arrive(&acc1_empty[b]);
+    }
+    // ---- final: partial y rows of this hidden slice (wg 0 / 1 = output columns 0-127 / 128-255)
+    mbar_wait_lane0(acc2_full, 0, 0);
+    tc_fence_after();
+    const int stream = stream0 + r / a.TT, t = t0 + r % a.TT;
+    const bool valid = stream < a.n_streams;
+    float* prow = a.P + ((long long)fs * a.M + (long long)stream * a.L + t) * BF_N2 + wg * 128;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t acc[16];
+      tc_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(256 + wg * 128 + ch * 16), acc);
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<float4*>(prow + ch * 16 + 4 * u) =
+              make_float4(__uint_as_float(acc[4 * u]) * a.acc_scale, __uint_as_float(acc[4 * u + 1]) * a.acc_scale,
+                          __uint_as_float(acc[4 * u + 2]) * a.acc_scale, __uint_as_float(acc[4 * u + 3]) * a.acc_scale);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+int pick_tt_bf(int L) {
+  for (int tt = 128; tt >= 1; tt >>= 1)
+    if (L % tt == 0) return tt;
+  return 0;
+}
+
+}  // namespace
+
+bool block_fused_eligible(int C1, int k, int hidden, int N2, int L) {
+  return C1 % 32 == 0 && k >= 1 && hidden % BF_CH == 0 && hidden >= BF_CH && N2 == BF_N2 && pick_tt_bf(L) > 0;
+}
+
+int block_fused_split(int n_streams, int L, int hidden, long long max_partial_rows) {
+  // hidden-dimension split: row tiles x split ~ one wave of CTAs (one CTA per SM: the kernel uses all of TMEM), bounded by the
+  // hidden chunks and by the partial-output buffer (max_partial_rows rows of 256 floats)
+  const int TT = pick_tt_bf(L), NS = TILE_M / TT;
+  const int mt = ((n_streams + NS - 1) / NS) * (L / TT);
+  const long long rows = (long long)n_streams * L;
+  int fs = std::max(1, num_sms() / std::max(mt, 1));
+  fs = std::min(fs, hidden / BF_CH);
+  fs = (int)std::min<long long>(fs, std::max<long long>(1, max_partial_rows / std::max<long long>(rows, 1)));
+  return std::min(fs, 16);
+}
+
+int launch_block_fused(const BlockFusedParams& p, cudaStream_t st) {
+  if (!block_fused_eligible(p.C1, p.k, p.hidden, p.N2, p.L)) { set_error("block_fused: shape not eligible"); return 1; }
+  if (p.n_streams <= 0) return 0;
+  const int TT = pick_tt_bf(p.L), NS = TILE_M / TT;
+  const int mt = ((p.n_streams + NS - 1) / NS) * (p.L / TT);
+  if (p.FS < 1 || p.FS > p.hidden / BF_CH) { set_error("block_fused: bad hidden split"); return 1; }
+  const int K1 = p.k * p.C1;
+  CUtensorMap tmX, tmW1, tmW2;
+  if (get_tensor_map(&tmX, p.x, 3, (unsigned long long)p.C1, (unsigned long long)p.x_rows, (unsigned long long)(p.lo_slot_off + p.n_slots),
+                     (unsigned long long)p.C1 * 2, (unsigned long long)p.x_slot_stride * 2, 32, TT, NS, 64))
+    return 1;
+  if (get_tensor_map(&tmW1, p.w1, 2, (unsigned long long)3 * K1, (unsigned long long)p.hidden, 1, (unsigned long long)3 * K1 * 2, 0, 32, BF_CH, 1, 64)) return 1;
+  if (get_tensor_map(&tmW2, p.w2, 2, (unsigned long long)3 * p.hidden, BF_N2, 1, (unsigned long long)3 * p.hidden * 2, 0, 64, BF_N2, 1, 128)) return 1;
+  BfArgs a;
+  a.n_streams = p.n_streams; a.L = p.L; a.TT = TT; a.C1 = p.C1; a.k = p.k; a.row0 = p.row0; a.lo_slot_off = (int)p.lo_slot_off;
+  a.hidden = p.hidden; a.n_chunks = p.hidden / BF_CH; a.FS = p.FS; a.K1 = K1; a.b1 = p.b1; a.scale1 = p.scale1; a.act = p.act;
+  a.P = p.partials; a.M = (long long)p.n_streams * p.L; a.acc_scale = p.acc_scale;
+  static DeviceOnce once;
+  if (device_once(once, nullptr, [&](int*) {
+        cudaError_t e = cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+        return 0;
+      }))
+    return 1;
+  block_fused_kernel<<<mt * p.FS, BF_THREADS, BF_SMEM, st>>>(tmX, tmW1, tmW2, a);
+  CONAN_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace conan

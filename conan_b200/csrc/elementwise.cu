@@ -22,16 +22,18 @@ __global__ void layernorm_kernel(LnArgs a) {
   int slot = slot_of(a.slot_ids, i);
   const float* x = reinterpret_cast<const float*>(a.in.base) + (long long)slot * a.in.slot_stride +
                    (long long)(a.in.row0 + t) * a.in.row_stride;
-  float xs[4];                                    // partial-sum mode: the row (C <= 128) is assembled once, in registers
+  float xs[8];                                    // partial-sum mode: the row (C <= 256) is assembled once, in registers
   if (a.part) {
     const long long row = (long long)i * a.L + t;
+    const float pmask = a.part_mask ? a.part_mask[row] : 1.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int c = lane + 32 * q;
       float v = 0.f;
       if (c < a.C) {
         for (int p = 0; p < a.n_part; ++p) v += a.part[p * a.part_stride + row * a.part_ld + c];
-        v += a.part_bias[c] + a.part_res[row * a.part_res_ld + c];
+        v = (v + a.part_bias[c] + a.part_res[row * a.part_res_ld + c]) * pmask;
+        if (a.part_out) a.part_out[row * a.part_out_ld + c] = v;
       }
       xs[q] = v;
     }

@@ -68,6 +68,7 @@ struct conan_engine {
   Ctx eXN, eATT, eFN, eHF;   // GEMM operands (fp32 or split fp16)
   std::vector<float> postTapsHost;                 // host copy of conv_post's taps + bias (kernel-parameter fast path)
   bool ffnFused = false; float* eFFP = nullptr;    // fused FFN: partial outputs [split][rows][DP]
+  bool blockFused = false; float* bfP = nullptr; long long bfRows = 0;   // fused Conan blocks: partial outputs [split][rows][256]
   std::vector<float*> eRing;
   // generic step (memory bank M > 0, summary query, partial segments): its own work buffers with seg + rc + 1 rows per stream
   int eM = 0;                                   // max_memory_size
@@ -418,6 +419,33 @@ int ln_rows(const float* in, int in_rows, int in_ld, int in_row0, RowView out, c
 
 #define TRY(x) do { if ((x) != 0) return 1; } while (0)
 
+// profiling category 6: fused two-GEMM Conan block (decoder residual block body / aligner feed-forward)
+int run_block(const conan_engine* e, const BlockFusedParams& f, cudaStream_t st) {
+  if (!e->profiling) return launch_block_fused(f, st);
+  conan_engine::ProfRec r;
+  r.cat = 6;
+  const double rows = (double)f.n_streams * f.L;
+  r.flops = 2.0 * rows * f.hidden * ((double)f.k * f.C1 + f.N2);
+  r.bytes = rows * f.C1 * 4.0 + (double)f.hidden * (f.k * f.C1 + f.N2) * 4.0 + (double)f.FS * rows * f.N2 * 4.0;
+  CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
+  CONAN_CUDA_OK(cudaEventRecord(r.a, st));
+  int rc = launch_block_fused(f, st);
+  CONAN_CUDA_OK(cudaEventRecord(r.b, st));
+  e->prof.push_back(r);
+  return rc;
+}
+
+BlockFusedParams block_on_ctx(const conan_engine* e, const Ctx& in, int k, const void* w1, const float* b1, int hidden, float scale1, int act,
+                              const void* w2, int n) {
+  BlockFusedParams f;
+  memset(&f, 0, sizeof(f));
+  f.x = in.p; f.x_slot_stride = in.slot_stride(); f.x_rows = in.rows(); f.n_slots = e->S; f.lo_slot_off = e->S;
+  f.C1 = in.C; f.k = k; f.row0 = in.H - (k - 1); f.L = in.L; f.n_streams = n;
+  f.w1 = w1; f.b1 = b1; f.hidden = hidden; f.scale1 = scale1; f.act = act; f.w2 = w2; f.N2 = 256;
+  f.partials = e->bfP; f.FS = block_fused_split(n, in.L, hidden, e->bfRows); f.acc_scale = 1.f / kSplitWeightScale;
+  return f;
+}
+
 // ============================================================================ allocation
 int allocate_state(conan_engine* e) {
   const conan_config_t& c = e->cfg;
@@ -464,6 +492,10 @@ int allocate_state(conan_engine* e) {
   TRY(alloc_ctx(e, &e->cO1, 0, seg, 0, H, lt)); TRY(alloc_ctx(e, &e->cHF, 0, seg, 0, 2048, lt));
   TRY(alloc_ctx(e, &e->cPROS[0], 0, seg, 0, H, lt)); TRY(alloc_ctx(e, &e->cPROS[1], 0, seg, 0, H, lt));
   TRY(alloc_ctx(e, &e->cDECH, 0, seg, 0, 2 * H, lt));
+  static const int fuse_blocks_env = [] { const char* v = getenv("CONAN_FUSE_BLOCKS"); return v ? atoi(v) : -1; }();
+  e->blockFused = e->lin_tc && (fuse_blocks_env < 0 ? c.lin_fuse_blocks != 0 : fuse_blocks_env != 0) && H == 256 && block_fused_eligible(H, c.dec_kernel, 2 * H, H, seg) &&
+                  block_fused_eligible(H, 1, 2048, H, seg);
+  if (e->blockFused) { e->bfRows = (long long)4 * S * seg; TRY(dalloc(e, &e->bfP, (size_t)e->bfRows * H)); }
   TRY(dalloc(e, &e->dX0, (size_t)S * seg * H)); TRY(dalloc(e, &e->dQ, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dT1, (size_t)S * seg * H)); TRY(dalloc(e, &e->dO1, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dT2, (size_t)S * seg * H));
@@ -817,14 +849,29 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
     TRY(run_conv(e, o, st, tc));
     TRY(ln_rows(e->dT1, seg, H, 0, e->cO1.new_rows(), e->F(a + "norm1.g"), e->F(a + "norm1.b"), H, seg, n, st, nullptr, nullptr, 0,
                 nullptr, nullptr, view_f32(e->dO1, (long long)seg * H, H)));
+    if (e->blockFused) {
+      // feed-forward 256 -> 2048 ReLU -> 256 in one kernel; the LayerNorm sums its partials with b2 and the residual
+      auto f = block_on_ctx(e, e->cO1, 1, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, 1.f, ACT_RELU, e->P(a + "ffn2.w"), n);
+      TRY(run_block(e, f, st));
+      LnArgs ln;
+      ln.in = RowView{(void*)e->dO1, (long long)seg * H, H, 0, 0, 0};
+      ln.out = e->cPROS[l].new_rows(); ln.out2 = view_f32(e->dPROS[l], (long long)seg * H, H);
+      ln.gamma = e->F(a + "norm2.g"); ln.beta = e->F(a + "norm2.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n; ln.slot_ids = nullptr;
+      ln.premask = nullptr; ln.premask_slot_stride = 0; ln.postmask = nullptr; ln.postmask_slot_stride = 0;
+      ln.write_mask = nullptr; ln.write_mask_slot_stride = 0; ln.write_mask2 = nullptr;
+      ln.part = e->bfP; ln.n_part = f.FS; ln.part_stride = (long long)n * seg * H; ln.part_ld = H;
+      ln.part_bias = e->F(a + "ffn2.b"); ln.part_res = e->dO1; ln.part_res_ld = H;
+      TRY(launch_layernorm(ln, st));
+    } else {
     auto f1 = conv_on_ctx(e, e->cO1, 1, 1, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, n);
-    out2_ctx(f1, e->cHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
-    TRY(run_conv(e, f1, st, tc));
-    auto f2 = conv_on_ctx(e, e->cHF, 1, 1, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n);
-    out_rows(f2, e->dT2, seg, H); res_rows(f2, e->dO1, seg, H);
-    TRY(run_conv(e, f2, st, tc));
-    TRY(ln_rows(e->dT2, seg, H, 0, e->cPROS[l].new_rows(), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st, nullptr, nullptr, 0,
-                nullptr, nullptr, view_f32(e->dPROS[l], (long long)seg * H, H)));
+      out2_ctx(f1, e->cHF, ACT_NONE, 0.f); f1.act = ACT_RELU;
+      TRY(run_conv(e, f1, st, tc));
+      auto f2 = conv_on_ctx(e, e->cHF, 1, 1, e->P(a + "ffn2.w"), e->F(a + "ffn2.b"), H, n);
+      out_rows(f2, e->dT2, seg, H); res_rows(f2, e->dO1, seg, H);
+      TRY(run_conv(e, f2, st, tc));
+      TRY(ln_rows(e->dT2, seg, H, 0, e->cPROS[l].new_rows(), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st, nullptr, nullptr, 0,
+                  nullptr, nullptr, view_f32(e->dPROS[l], (long long)seg * H, H)));
+    }
     cur = e->dPROS[l]; curc = &e->cPROS[l];
   }
   TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, nullptr, seg, H, st));  // Conan.py:168
@@ -837,20 +884,57 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
   }
   TRY(launch_pitch(e->dUVH, e->F("conan.uv.ln.g"), e->F("conan.uv.ln.b"), e->F("conan.uv.lin.w"), e->F("conan.uv.lin.b"), tok,
                    c.silent_token, e->F("conan.pitch_embed"), e->dPINP, e->dDECX, e->dUVP, n, nullptr, seg, 128, H, st));
-  for (int b = 0; b < c.dec_blocks; ++b)
-    for (int s = 0; s < 2; ++s) {
-      std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
-      TRY(ln_rows(e->dDECX, seg, H, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, st, nullptr, nullptr, seg,
-                  s == 0 ? e->dMASKB : nullptr, (b == 0 && s == 0) ? e->dMASK0 : nullptr));
-      auto p = conv_on_ctx(e, e->cD[b][s], c.dec_kernel, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, n);
-      out2_ctx(p, e->cDECH, ACT_NONE, 0.f); p.scale = 1.0f / sqrtf((float)c.dec_kernel); p.act = ACT_GELU;
-      TRY(run_conv(e, p, st, tc));
-      auto w = conv_on_ctx(e, e->cDECH, 1, 1, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n);
-      out_rows(w, e->dDECX, seg, H); res_rows(w, e->dDECX, seg, H); w.rowmask = e->dMASKB; w.mask_slot_stride = seg;
-      TRY(run_conv(e, w, st, tc));
-    }
-  TRY(ln_rows(e->dDECX, seg, H, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, st,
-              e->dMASK0, e->dMASK0, seg));
+  if (e->blockFused) {
+    // per residual block body: LayerNorm -> ONE kernel (causal conv k5 -> x 5^-1/2 -> GELU -> 1x1); the next LayerNorm assembles
+    // x = (x + y + b2) * nonpadding from the kernel's partial outputs, writes it back as the residual stream and normalises it
+    int fs_prev = 0; std::string d_prev;
+    auto ln_assemble = [&](LnArgs& ln) {
+      if (!fs_prev) return;
+      ln.part = e->bfP; ln.n_part = fs_prev; ln.part_stride = (long long)n * seg * H; ln.part_ld = H;
+      ln.part_bias = e->F(d_prev + "pw.b"); ln.part_res = e->dDECX; ln.part_res_ld = H;
+      ln.part_mask = e->dMASKB; ln.part_out = e->dDECX; ln.part_out_ld = H;
+    };
+    for (int b = 0; b < c.dec_blocks; ++b)
+      for (int s = 0; s < 2; ++s) {
+        std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
+        LnArgs ln;
+        ln.in = RowView{(void*)e->dDECX, (long long)seg * H, H, 0, 0, 0};
+        ln.out = e->cD[b][s].new_rows(); ln.out2 = RowView{};
+        ln.gamma = e->F(d + "ln.g"); ln.beta = e->F(d + "ln.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n; ln.slot_ids = nullptr;
+        ln.premask = nullptr; ln.premask_slot_stride = seg; ln.postmask = nullptr; ln.postmask_slot_stride = seg;
+        ln.write_mask = s == 0 ? e->dMASKB : nullptr; ln.write_mask_slot_stride = seg;
+        ln.write_mask2 = (b == 0 && s == 0) ? e->dMASK0 : nullptr;
+        ln_assemble(ln);
+        TRY(launch_layernorm(ln, st));
+        auto f = block_on_ctx(e, e->cD[b][s], c.dec_kernel, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, 1.0f / sqrtf((float)c.dec_kernel),
+                              ACT_GELU, e->P(d + "pw.w"), n);
+        TRY(run_block(e, f, st));
+        fs_prev = f.FS; d_prev = d;
+      }
+    LnArgs ln;
+    ln.in = RowView{(void*)e->dDECX, (long long)seg * H, H, 0, 0, 0};
+    ln.out = e->cP.new_rows(); ln.out2 = RowView{};
+    ln.gamma = e->F("conan.dec.last_norm.g"); ln.beta = e->F("conan.dec.last_norm.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n;
+    ln.slot_ids = nullptr; ln.premask = e->dMASK0; ln.premask_slot_stride = seg; ln.postmask = e->dMASK0; ln.postmask_slot_stride = seg;
+    ln.write_mask = nullptr; ln.write_mask_slot_stride = seg; ln.write_mask2 = nullptr;
+    ln_assemble(ln);
+    TRY(launch_layernorm(ln, st));
+  } else {
+    for (int b = 0; b < c.dec_blocks; ++b)
+      for (int s = 0; s < 2; ++s) {
+        std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
+        TRY(ln_rows(e->dDECX, seg, H, 0, e->cD[b][s].new_rows(), e->F(d + "ln.g"), e->F(d + "ln.b"), H, seg, n, st, nullptr, nullptr, seg,
+                    s == 0 ? e->dMASKB : nullptr, (b == 0 && s == 0) ? e->dMASK0 : nullptr));
+        auto p = conv_on_ctx(e, e->cD[b][s], c.dec_kernel, 1, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, n);
+        out2_ctx(p, e->cDECH, ACT_NONE, 0.f); p.scale = 1.0f / sqrtf((float)c.dec_kernel); p.act = ACT_GELU;
+        TRY(run_conv(e, p, st, tc));
+        auto w = conv_on_ctx(e, e->cDECH, 1, 1, e->P(d + "pw.w"), e->F(d + "pw.b"), H, n);
+        out_rows(w, e->dDECX, seg, H); res_rows(w, e->dDECX, seg, H); w.rowmask = e->dMASKB; w.mask_slot_stride = seg;
+        TRY(run_conv(e, w, st, tc));
+      }
+    TRY(ln_rows(e->dDECX, seg, H, 0, e->cP.new_rows(), e->F("conan.dec.last_norm.g"), e->F("conan.dec.last_norm.b"), H, seg, n, st,
+                e->dMASK0, e->dMASK0, seg));
+  }
   {
     auto p = conv_on_ctx(e, e->cP, c.dec_post_kernel, 1, e->P("conan.dec.post.w"), e->F("conan.dec.post.b"), H, n);
     out_rows(p, e->dPOST, seg, H); p.rowmask = e->dMASK0; p.mask_slot_stride = seg;

@@ -39,9 +39,12 @@ struct LnArgs {
   float* write_mask; int write_mask_slot_stride;     // mask[slot, t] = (sum_c |x| > 0) of the raw input
   float* write_mask2;                                // optional second copy (same stride)
   // optional: the input row is  sum_p part[p][row][c] + part_bias[c] + part_res[row][c]  instead of `in` (the fused FFN kernel
-  // leaves one partial per hidden-dimension slice; compact rows, C <= 128)
+  // and the fused residual-block kernel leave one partial per hidden-dimension slice; compact rows, C <= 256)
   const float* part = nullptr; int n_part = 0; long long part_stride = 0; int part_ld = 0;
   const float* part_bias = nullptr; const float* part_res = nullptr; int part_res_ld = 0;
+  // (C <= 256) optionally the assembled row is multiplied by part_mask[row] (the residual block's nonpadding mask) and written
+  // back as the new fp32 residual stream part_out[row][c] before it is normalised
+  const float* part_mask = nullptr; float* part_out = nullptr; int part_out_ld = 0;
   // optional chained second LayerNorm over the first one's output y (C <= 128): out3 = LN2(y) -- the next Emformer layer's
   // input norm applied in the same pass as this layer's output norm
   const float* gamma2 = nullptr; const float* beta2 = nullptr; RowView out3;
@@ -138,6 +141,20 @@ struct FfnFusedParams {
 bool ffn_fused_eligible(int K, int hidden, int N);
 int ffn_fused_split(int M);
 int launch_ffn_fused(const FfnFusedParams& p, cudaStream_t st);
+
+// fused two-GEMM residual block (block_fused.cu): partial y = W2 . act(scale * (conv_k(x) + b1)), split-fp16 operands
+struct BlockFusedParams {
+  const void* x; long long x_slot_stride; int x_rows; int n_slots; long long lo_slot_off;   // split context [2 planes][slots][x_rows][C1], compact
+  int C1, k, row0, L, n_streams;                     // taps read rows row0 + t + j, j < k
+  const void* w1; const float* b1; int hidden;       // [hidden][3*k*C1] fp16 (x 2^10), [hidden] fp32
+  float scale1; int act;                             // ACT_GELU (exact erf) or ACT_RELU
+  const void* w2; int N2;                            // [256][3*hidden] fp16 (x 2^10)
+  float* partials; int FS;                           // [FS][n_streams*L][256] fp32
+  float acc_scale;
+};
+bool block_fused_eligible(int C1, int k, int hidden, int N2, int L);
+int block_fused_split(int n_streams, int L, int hidden, long long max_partial_rows);
+int launch_block_fused(const BlockFusedParams& p, cudaStream_t st);
 
 // log-mel front-end: |DFT| -> Slaney mel -> log10 -> clip, one CTA per frame (spec from the conv-GEMM engine)
 int launch_logmel(const float* spec, int ld, int bins, const float* basis_t, int n_mels, float eps, float vmin, float vmax,

@@ -23,7 +23,8 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
                 voc_tensor_cores: bool = True, voc_group: int = 0, lin_tensor_cores: Optional[bool] = None,
                 voc_residual_from_ctx: Optional[bool] = None, voc_fuse_resblocks: Optional[bool] = None,
                 lin_fuse_ffn: Optional[bool] = None, ses_tensor_cores: Optional[bool] = None,
-                emformer_memory_size: Optional[int] = None, step_graphs: bool = True) -> _lib.ConanConfig:
+                emformer_memory_size: Optional[int] = None, step_graphs: bool = True,
+                lin_fuse_blocks: Optional[bool] = None) -> _lib.ConanConfig:
     """Builds the native config from reference-style hparams dicts (the keys the hot path reads,
     SURVEY.md section 5)."""
     hp = {**DEFAULT_HP, **{k: v for k, v in (hp or {}).items() if v is not None}}
@@ -85,6 +86,7 @@ def make_config(hp: Optional[Dict] = None, voc_hp: Optional[Dict] = None, *, max
     # `emformer_memory_size` hparam / argument enables the memory bank for checkpoints trained with one
     cfg.emformer_memory_size = int(hp.get("emformer_memory_size", 0) if emformer_memory_size is None else emformer_memory_size)
     cfg.step_graphs = int(bool(step_graphs))
+    cfg.lin_fuse_blocks = int(bool(cfg.lin_use_tensor_cores) if lin_fuse_blocks is None else (bool(lin_fuse_blocks) and bool(cfg.lin_use_tensor_cores)))
     return cfg
 
 
@@ -99,7 +101,7 @@ def _packed_weights(sd_conan, sd_emformer, sd_voc, cfg):
     """pack_engine_weights memoised on the state-dict objects and the config fields the packing depends on (a process that
     builds several engines over the same checkpoints -- bench.py's sweeps, the test suite -- packs them once)."""
     key = (id(sd_conan), id(sd_emformer), id(sd_voc), cfg.voc_precision, cfg.voc_use_tensor_cores, cfg.lin_use_tensor_cores,
-           cfg.lin_fuse_ffn, cfg.ses_use_tensor_cores, cfg.max_ref_frames, cfg.emformer_layers, cfg.right_context)
+           cfg.lin_fuse_ffn, cfg.ses_use_tensor_cores, cfg.lin_fuse_blocks, cfg.max_ref_frames, cfg.emformer_layers, cfg.right_context)
     hit = _PACK_CACHE.get(key)
     if hit is None or hit[0] is not sd_conan:
         if len(_PACK_CACHE) >= 4:
@@ -278,7 +280,8 @@ class Engine:
         _lib.check(self.lib.conan_engine_set_profiling(self.h, int(enabled)), "set_profiling")
 
     def profile_read(self, category: int):
-        """category 0 FFMA, 1 tcgen05 ring (fp16), 2 tcgen05 window, 3 tcgen05 ring (split fp16)
+        """category 0 FFMA, 1 tcgen05 ring (fp16), 2 tcgen05 window, 3 tcgen05 ring (split fp16), 4 fused residual block,
+        5 fused Emformer FFN, 6 fused Conan block
         -> (ms, launches, algorithmic flops, algorithmic bytes)."""
         ms, n, fl, by = C.c_double(), C.c_uint64(), C.c_double(), C.c_double()
         _lib.check(self.lib.conan_engine_profile_read(self.h, category, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)), "profile_read")

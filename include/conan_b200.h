@@ -95,7 +95,8 @@ typedef struct conan_config {
                                      M > 0 keeps a bank of the last M memory vectors per layer and stream and adds the summary query */
   int32_t step_graphs;            /* 1: conan_step / conan_step_host* replay a CUDA graph of the whole chunk step (captured once per distinct
                                      ready count and buffer set; the slot ids stay an indirection read from the device buffer) */
-  int32_t reserved[1];
+  int32_t lin_fuse_blocks;        /* 1: the decoder's residual block body (conv k5 -> GELU -> 1x1) and the aligner's feed-forward run as one
+                                     tcgen05 kernel each, hidden activation in shared memory (needs lin_use_tensor_cores) */
 } conan_config_t;
 
 /* dtype codes for conan_engine_bind_weight */
@@ -196,7 +197,8 @@ CONAN_API uint64_t conan_engine_graph_replays(const conan_engine_t* eng);
 /* Per-launch CUDA-event timing of the conv engines (measurement only: events are recorded on the
  * launching stream around every conv launch while enabled).  category 0 = FFMA, 1 = tcgen05 ring kernel
  * (fp16 operands), 2 = tcgen05 window kernel, 3 = tcgen05 ring kernel with split-fp16 operands, 4 = fused
- * residual-block kernel (six convs per launch), 5 = fused feed-forward kernel (two GEMMs per launch).
+ * residual-block kernel (six convs per launch), 5 = fused Emformer feed-forward kernel, 6 = fused Conan block kernel
+ * (decoder residual block body / aligner feed-forward: two GEMMs per launch).
  * profile_read synchronises the device and returns the summed kernel time, launch count, algorithmic
  * FLOPs (2*M*N*K) and algorithmic HBM bytes since profiling was (re-)enabled. */
 CONAN_API int conan_engine_set_profiling(conan_engine_t* eng, int enabled);

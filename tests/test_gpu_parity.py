@@ -610,6 +610,37 @@ def test_end_to_end_vs_reference_golden(which, name, request, golden_dir):
         assert np.abs(wav - d["wav"]).max() < 2e-4
 
 
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+def test_conan_fused_blocks_match_per_gemm_path(state_dicts):
+    """block_fused_kernel (decoder residual block body: conv k5 -> x 5^-1/2 -> GELU -> 1x1; aligner feed-forward 256 -> 2048 -> 256,
+    hidden activation in shared memory, partial outputs summed by the next LayerNorm) against the same split-fp16 arithmetic run
+    GEMM by GEMM, and against the oracle: 12 chunks (longer than the decoder's receptive field), streams that do not fill a tile."""
+    from oracle.incremental import ConanOracle
+    B, T = 5, 48
+    ref = torch.stack([synth.synth_mel(40 + 3 * s, 510 + s)[:40] for s in range(B)])
+    tokens = torch.randint(0, 100, (B, T), generator=torch.Generator().manual_seed(3))
+    tokens[:, 5:9] = 57                                                     # silent token: forced unvoiced frames
+    o = ConanOracle(state_dicts[0])
+    with torch.no_grad():
+        o.open(ref)
+        mel_o = torch.cat([o.step(tokens[:, i:i + 4]) for i in range(0, T, 4)], 1)
+    mels = {}
+    for fuse in (False, True):
+        eng = _engine(state_dicts, lin_fuse_blocks=fuse)
+        assert bool(eng.cfg.lin_fuse_blocks) == fuse
+        slots = [6, 1, 4, 0, 3]
+        eng.reset_slots(slots)
+        eng.open_sessions(slots, ref.cuda())
+        ids = eng.ids_tensor(slots)
+        l0 = eng.launch_count
+        mels[fuse] = torch.cat([eng.decoder_step(ids, tokens[:, i:i + 4].to(torch.int32).contiguous().cuda()).cpu() for i in range(0, T, 4)], 1)
+        launches = (eng.launch_count - l0) // (T // 4)
+        print("fused" if fuse else "per-GEMM", "Conan chunk step:", launches, "launches, mel max-abs vs oracle", (mels[fuse] - mel_o).abs().max().item())
+        eng.close()
+    assert (mels[True] - mel_o).abs().max().item() <= MEL_TOL
+    assert (mels[True] - mels[False]).abs().max().item() < 2e-4
+
+
 def test_step_graph_replay_is_bitwise_equal_to_eager_launches(state_dicts):
     """A chunk step replayed from its CUDA graph (captured at the second step with the same ready count and buffers) must equal
     the eager launch sequence bit for bit, while the CONTENT of the slot-id buffer changes from step to step (slot indirection:
