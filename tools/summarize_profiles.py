@@ -110,6 +110,7 @@ def traffic(src, dst):
     for d in byid.values():
         n = d["name"]
         key = ("resblock_fused_kernel" if "resblock_fused" in n else "ffn_fused_kernel" if "ffn_fused" in n else
+               "block_fused_kernel" if "block_fused" in n else
                "conv_window_tc_kernel" if "conv_window_tc" in n else
                # fp16-operand vocoder layers: the CTA-pair kernel (conv_gemm_tc2_kernel) and the single-CTA ring variants whose last
                # template argument (SP, four-tile split stages) is 0; SP = 1 marks a split-fp16 Emformer / Conan GEMM
