@@ -318,7 +318,13 @@ def leg_scheduler(rig, K, seconds=3.0):
     dt = time.perf_counter() - t0
     lock = {"api": "ChunkScheduler.push_many / submit / collect (two steps in flight)", "steps": n_steps, "seconds": dt,
             "ms_per_step": dt / n_steps * 1e3, "value": S * n_steps / dt * CHUNK_S, "clock": "host wall clock"}
-    # ---- (b) real time, jittered arrivals
+    # ---- (b) real time, jittered arrivals.  Start-up warm-up first, as a server would do it: the step graphs of the small
+    # ready-count buckets are captured on a second engine-less pass over throw-away steps (the streams' state is zeroed again)
+    warm = ChunkScheduler(eng, S)
+    warm.warm(max_batch=96)
+    del warm
+    eng.reset_slots(rig.slots, 1 | 2 | 4)
+    sch.recv[:] = sch.pos[:] = sch.total[:] = 0
     rng = np.random.default_rng(0)
     n_ev = int(seconds / CHUNK_S)
     phase = rng.uniform(0, CHUNK_S, S)

@@ -121,6 +121,28 @@ class ChunkScheduler:
         self._flip = 0
         self._inflight: Deque[Tuple[int, int, np.ndarray, np.ndarray, np.ndarray, int]] = deque()
 
+    def warm(self, max_batch: int = 64, full: bool = False):
+        """Start-up warm-up of a serving loop: runs throw-away steps for every ready-count bucket (multiples of 8) up to
+        `max_batch` (and the full size with full=True), through both pipelined buffer sets, so that the engine has captured its
+        CUDA graphs before the first real chunk arrives (a capture costs a few ms -- fine at start-up, a p99 outlier in service).
+        Must run before any session is opened; the slots it touched are reset."""
+        if self.streams:
+            raise RuntimeError("warm() must run before sessions are opened")
+        sizes = sorted(set(list(range(8, min(max_batch, self.S) + 1, 8)) + ([self.S] if full else [])))
+        pipelined = hasattr(self.eng, "step_host_submit")
+        for n in sizes:
+            slots = np.arange(n, dtype=np.int32)
+            for rep in range(6 if pipelined else 3):                 # eager run, capture, replay -- per buffer set
+                b = self._stage[rep & 1]
+                b["chunk"][:n] = -3.0
+                b["slots"][:n] = slots
+                if pipelined:
+                    self.eng.step_host_wait(self.eng.step_host_submit(b["slots"][:n], b["chunk"][:n], b["wav"][:n], b["mel"][:n], b["tok"][:n]))
+                else:
+                    self.eng.step_host(b["slots"][:n], b["chunk"][:n], b["wav"][:n], b["mel"][:n], b["tok"][:n])
+        if sizes:
+            self.eng.reset_slots(list(range(max(sizes))))
+
     # ------------------------------------------------------------------ session admission
     def open(self, ref_mel) -> int:
         return self.open_many([ref_mel])[0]

@@ -312,6 +312,18 @@ def test_scheduler_vectorised_lockstep_and_pipelined_stepping():
             sch.push_many(slots, src[:, :4])                           # nobody consumes: back-pressure
 
 
+def test_scheduler_warm_up_touches_every_bucket_and_resets():
+    for eng in (FakeEngine(), PipelinedFakeEngine()):
+        sch = ChunkScheduler(eng, 40)
+        sch.warm(max_batch=24, full=True)
+        sizes = sorted({len(c[0]) for c in eng.calls})
+        assert sizes == [8, 16, 24, 40] and eng.resets[-1] == list(range(40))
+        sid = sch.open(np.zeros((8, 80), np.float32))
+        with pytest.raises(RuntimeError):
+            sch.warm()
+        sch.close(sid)
+
+
 def test_scheduler_failed_admission_releases_slots():
     class Rejecting(FakeEngine):
         def open_sessions(self, slots, ref):
