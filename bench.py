@@ -250,7 +250,7 @@ class Rig:
 
 def _short_window(rig, K, seconds, warm=3):
     """warm-up, one K-step probe, then K-step blocks for ~`seconds`: dict(ms_per_step, latency, value, steps)."""
-    for _ in range(warm + (2 * rig.n_pool if rig.cfg.step_graphs else 0)):
+    for _ in range(warm + (4 * rig.n_pool if rig.cfg.step_graphs else 0)):
         rig.step()
     rig.torch.cuda.synchronize(rig.dev)
     _, probe = rig.timed(K)
@@ -269,6 +269,8 @@ def leg_sweep(local, sds, sizes, K):
             rig = Rig(S, local, sds)
             r = _short_window(rig, K, 1.5)
             r["session_open_ms_total"] = rig.session_ms
+            if S == 8192:            # config 5 at N = 1 as a SERVICE: 8192 real-time streams with jittered arrivals on one GPU
+                r["realtime_jittered"] = realtime_leg(rig, 3.0, warm_batch=256)
             rig.close()
         except Exception as ex:          # e.g. out of memory at the largest size: report, keep the line
             r = {"streams_resident": S, "error": str(ex)[:200]}
@@ -281,50 +283,39 @@ def leg_sweep(local, sds, sizes, K):
             "note": "every run allocates S slots, opens S sessions and steps all S streams; latency = device time of one packed step"}
 
 
-def leg_scheduler(rig, K, seconds=3.0):
-    """ChunkScheduler in the measured loop: (a) lock-step pipelined throughput through push_many / submit / collect,
-    (b) real time with jittered arrivals: arrival-to-wav latency through step_packed."""
+def _adopt_sessions(rig):
+    """A ChunkScheduler over the rig's already opened sessions: slot i <-> stream i (session setup is measured separately)."""
+    from conan_b200.scheduler import ChunkScheduler
+    sch = ChunkScheduler(rig.eng, rig.S)
+    sch.free = []
+    for slot in range(rig.S):
+        sch._activate(slot, slot)
+    sch._next_id = rig.S
+    rig.eng.reset_slots(rig.slots, 1 | 2 | 4)        # zero the stream state; the session caches stay
+    return sch
+
+
+def _frame_pool(S, P=16):
     import numpy as np
     from conan_b200 import synth
+    pool = np.stack([synth.synth_mel(SEG * P, 500 + s).numpy() for s in range(32)])                   # [32, 4P, 80]
+    return np.ascontiguousarray(np.tile(pool, (S // 32 + 1, 1, 1))[:S].reshape(S, P, SEG, MELS))
+
+
+def realtime_leg(rig, seconds=3.0, warm_batch=96):
+    """Every stream delivers 4 frames per 80 ms of WALL CLOCK at its own phase with exponential jitter; the loop ingests what has
+    arrived, runs one packed step for whatever is ready (ChunkScheduler.step_packed: results on the host) and records, per
+    stream-chunk, the time from the arrival that completed the chunk to its wav being on the host."""
+    import numpy as np
     from conan_b200.scheduler import ChunkScheduler
     eng, S = rig.eng, rig.S
-    sch = ChunkScheduler(eng, S)
-    # adopt the rig's already opened sessions: slot i <-> stream i (session setup is measured separately)
-    sch.free = []
-    for slot in range(S):
-        sch._activate(slot, slot)
-    sch._next_id = S
-    eng.reset_slots(rig.slots, 1 | 2 | 4)        # zero the stream state; the session caches stay
-    P = 16
-    pool = np.stack([synth.synth_mel(SEG * P, 500 + s).numpy() for s in range(32)])                   # [32, 4P, 80]
-    pool = np.ascontiguousarray(np.tile(pool, (S // 32 + 1, 1, 1))[:S].reshape(S, P, SEG, MELS))
-    slots = np.arange(S)
-    # ---- (a) lock-step, pipelined
-    sch.push_many(slots, np.ascontiguousarray(pool[:, 0, :2]))          # prime the look-ahead (rc = 2 frames)
-    t_list, prev = [], None
-    n_steps = 0
-    t0 = time.perf_counter()
-    while True:
-        sch.push_many(slots, pool[:, n_steps % P])
-        t = sch.submit()
-        if prev is not None:
-            sch.collect(prev)
-        prev = t
-        n_steps += 1
-        if n_steps >= 3 * K and time.perf_counter() - t0 > min(seconds, 2.0):
-            break
-    sch.collect(prev)
-    rig.torch.cuda.synchronize(rig.dev)
-    dt = time.perf_counter() - t0
-    lock = {"api": "ChunkScheduler.push_many / submit / collect (two steps in flight)", "steps": n_steps, "seconds": dt,
-            "ms_per_step": dt / n_steps * 1e3, "value": S * n_steps / dt * CHUNK_S, "clock": "host wall clock"}
-    # ---- (b) real time, jittered arrivals.  Start-up warm-up first, as a server would do it: the step graphs of the small
-    # ready-count buckets are captured on a second engine-less pass over throw-away steps (the streams' state is zeroed again)
+    # start-up warm-up, as a server would do it: the step graphs of the ready-count buckets are captured on throw-away steps
     warm = ChunkScheduler(eng, S)
-    warm.warm(max_batch=96)
+    warm.warm(max_batch=warm_batch)
     del warm
-    eng.reset_slots(rig.slots, 1 | 2 | 4)
-    sch.recv[:] = sch.pos[:] = sch.total[:] = 0
+    sch = _adopt_sessions(rig)
+    P = 16
+    pool = _frame_pool(S, P)
     rng = np.random.default_rng(0)
     n_ev = int(seconds / CHUNK_S)
     phase = rng.uniform(0, CHUNK_S, S)
@@ -356,13 +347,42 @@ def leg_scheduler(rig, K, seconds=3.0):
         batch_sizes.append(len(r))
     total = time.perf_counter() - t0
     lat = np.sort(np.concatenate(lat)) * 1e3
-    rt = {"api": "ChunkScheduler.push_many / step_packed (synchronous, results on the host)", "streams": S, "seconds": total,
-          "arrival_model": "every stream delivers 4 frames per 80 ms of wall clock, uniform phase, exponential jitter (mean 4 ms)",
-          "chunk_steps": int(len(lat)), "engine_calls": len(batch_sizes), "mean_batch": float(np.mean(batch_sizes)),
-          "arrival_to_wav_ms": {"p50": float(lat[len(lat) // 2]), "p99": float(lat[int(len(lat) * 0.99)]), "max": float(lat[-1]),
-                                "samples": int(len(lat))},
-          "kept_up": bool(total < seconds + 0.25)}
-    return {"lockstep_pipelined": lock, "realtime_jittered": rt}
+    return {"api": "ChunkScheduler.push_many / step_packed (synchronous, results on the host)", "streams": S, "seconds": total,
+            "arrival_model": "every stream delivers 4 frames per 80 ms of wall clock, uniform phase, exponential jitter (mean 4 ms)",
+            "chunk_steps": int(len(lat)), "engine_calls": len(batch_sizes), "mean_batch": float(np.mean(batch_sizes)),
+            "max_batch": int(np.max(batch_sizes)),
+            "arrival_to_wav_ms": {"p50": float(lat[len(lat) // 2]), "p99": float(lat[int(len(lat) * 0.99)]), "max": float(lat[-1]),
+                                  "samples": int(len(lat))},
+            "kept_up": bool(total < seconds + 0.25), "graph_replays_total": eng.graph_replays}
+
+
+def leg_scheduler(rig, K, seconds=3.0):
+    """ChunkScheduler in the measured loop: (a) lock-step pipelined throughput through push_many / submit / collect,
+    (b) real time with jittered arrivals: arrival-to-wav latency through step_packed."""
+    import numpy as np
+    S = rig.S
+    sch = _adopt_sessions(rig)
+    P = 16
+    pool = _frame_pool(S, P)
+    slots = np.arange(S)
+    sch.push_many(slots, np.ascontiguousarray(pool[:, 0, :2]))          # prime the look-ahead (rc = 2 frames)
+    prev, n_steps = None, 0
+    t0 = time.perf_counter()
+    while True:
+        sch.push_many(slots, pool[:, n_steps % P])
+        t = sch.submit()
+        if prev is not None:
+            sch.collect(prev)
+        prev = t
+        n_steps += 1
+        if n_steps >= 3 * K and time.perf_counter() - t0 > min(seconds, 2.0):
+            break
+    sch.collect(prev)
+    rig.torch.cuda.synchronize(rig.dev)
+    dt = time.perf_counter() - t0
+    lock = {"api": "ChunkScheduler.push_many / submit / collect (two steps in flight)", "steps": n_steps, "seconds": dt,
+            "ms_per_step": dt / n_steps * 1e3, "value": S * n_steps / dt * CHUNK_S, "clock": "host wall clock"}
+    return {"lockstep_pipelined": lock, "realtime_jittered": realtime_leg(rig, seconds)}
 
 
 def leg_session(rig, K):
@@ -609,7 +629,7 @@ def run_b200(args):
         rig.step()
     # untimed priming beyond the W warm-up steps: a chunk step is captured as a CUDA graph the second time its (ready count,
     # buffer set) is seen, and the input pool rotates over n_pool device buffers
-    n_prime = 2 * rig.n_pool if cfg.step_graphs else 0
+    n_prime = 4 * rig.n_pool if cfg.step_graphs else 0       # (a ready count above 256 is captured at its 4th sighting)
     for _ in range(n_prime):
         rig.step()
     sync_all()

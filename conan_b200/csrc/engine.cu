@@ -296,6 +296,11 @@ inline int fused_weight_copies() {        // CONAN_FUSED_WCOPIES=1..16 (A/B of t
 // max_slots, inputs = whatever the staging buffer holds, outputs dropped), so a serving loop whose ready count changes every
 // step replays a handful of captured graphs instead of capturing one per distinct count.
 constexpr int kStepBucket = 8, kPadSlots = kStepBucket - 1;
+// Ready counts up to kGraphSmallN are padded to a bucket and captured the second time a bucket is met (at most 32 buckets: the
+// graph cache holds them all).  Larger ready counts are not padded and are captured only once the very same count keeps coming
+// back (lock-step serving); a large count that changes from step to step is launched eagerly -- at that size the launches are
+// hidden behind the kernels anyway, and capturing a graph per distinct count would thrash the cache.
+constexpr int kGraphSmallN = 256, kGraphBigSightings = 3;
 constexpr float kSplitWeightScale = 1024.f;      // split weights are packed as 2^10 * W (keeps W_lo out of the fp16 subnormals)
 
 // ---- conv parameter builders (all compact: stream i of the ready list, no slot indirection) -----
@@ -1438,7 +1443,7 @@ int conan_step(conan_engine_t* e, int n, const int32_t* slot_ids_dev, const floa
 
 // pads a ready list staged in hIds to the next multiple of kStepBucket with the pad slots (graph mode only); returns the padded count
 static int pad_ready_list(conan_engine_t* e, int n, cudaStream_t st) {
-  if (!e->graphMode || n == 0) return n;
+  if (!e->graphMode || n == 0 || n > kGraphSmallN) return n;
   const int np = std::min((n + kStepBucket - 1) / kStepBucket * kStepBucket, e->S);
   if (np > n) cudaMemcpyAsync(e->hIds + n, e->padIds, (size_t)(np - n) * sizeof(int), cudaMemcpyDeviceToDevice, st);
   return np;
@@ -1459,12 +1464,14 @@ static int step_graphed(conan_engine_t* e, int n, const int32_t* slot_ids_dev, c
       ++e->graphReplays;
       return 0;
     }
-  bool seen = false;
-  for (auto& g : e->stepSeen) seen = seen || same(g);
-  if (!seen) {
-    // first time with this (ready count, buffers): run eagerly (sets kernel attributes, fills the tensor-map cache)
-    if (e->stepSeen.size() >= 64) e->stepSeen.erase(e->stepSeen.begin());
-    e->stepSeen.push_back(conan_engine::StepGraph{n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, nullptr, 0, 0});
+  uint64_t sightings = 0;
+  for (auto& g : e->stepSeen) if (same(g)) sightings = ++g.launches;           // (launches doubles as the sighting counter here)
+  if (sightings < (uint64_t)(n <= kGraphSmallN ? 2 : 1 + kGraphBigSightings)) {
+    // not met often enough yet: run eagerly (the first run also sets kernel attributes and fills the tensor-map cache)
+    if (!sightings) {
+      if (e->stepSeen.size() >= 64) e->stepSeen.erase(e->stepSeen.begin());
+      e->stepSeen.push_back(conan_engine::StepGraph{n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, nullptr, 1, 0});
+    }
     return step_eager(e, n, slot_ids_dev, chunk_dev, wav_out_dev, mel_out_dev, tokens_out_dev, st);
   }
   // second time: capture on the engine's stream (the caller's may be the legacy default stream, which cannot capture), instantiate,

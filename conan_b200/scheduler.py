@@ -132,7 +132,8 @@ class ChunkScheduler:
         pipelined = hasattr(self.eng, "step_host_submit")
         for n in sizes:
             slots = np.arange(n, dtype=np.int32)
-            for rep in range(6 if pipelined else 3):                 # eager run, capture, replay -- per buffer set
+            reps = 3 if n <= 256 else 5                               # eager run(s), capture, replay -- per buffer set
+            for rep in range(2 * reps if pipelined else reps):
                 b = self._stage[rep & 1]
                 b["chunk"][:n] = -3.0
                 b["slots"][:n] = slots

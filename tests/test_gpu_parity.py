@@ -371,6 +371,25 @@ def test_emformer_view_forward_matches_streaming_inference(state_dicts, eng_tc):
     assert torch.equal(torch.cat(toks, 1), out[:, :36].argmax(-1).cpu())
 
 
+def test_emformer_encoder_bits_do_not_depend_on_the_batch(eng_tc):
+    """The split of the fused feed-forward's hidden dimension is a constant, so a stream's encoder rows (not only its argmax
+    tokens) are bit-identical whether it shares the launch with 70 other streams or runs alone."""
+    eng = eng_tc
+    S = 8
+    src = torch.stack([synth.synth_mel(14, 830 + s) for s in range(S)])
+    eng.reset_slots(list(range(S)))
+    ids = eng.ids_tensor(list(range(S)))
+    together = []
+    for pos in (0, 4, 8):
+        _, enc, _ = eng.emformer_step(ids, src[:, pos:pos + 6].contiguous().cuda(), want_enc=True)
+        together.append(enc.cpu())
+    eng.reset_slots([5])
+    one = eng.ids_tensor([5])
+    for k, pos in enumerate((0, 4, 8)):
+        _, enc, _ = eng.emformer_step(one, src[2:3, pos:pos + 6].contiguous().cuda(), want_enc=True)
+        assert torch.equal(enc.cpu()[0], together[k][2])
+
+
 # ------------------------------------------------------------------------------------------
 # Conan main model
 # ------------------------------------------------------------------------------------------
