@@ -524,9 +524,23 @@ struct Smem2Layout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES;
 };
 
+// Up to kMaxGroup INDEPENDENT convolutions of the same shape (the three MRF branches of a vocoder scale: kernel sizes 3 / 7 / 11 on
+// the same rows) run as one launch: the tile space is the concatenation of the problems' tile spaces, longest K first, so a
+// launch's prologue, cluster barriers, first TMA round trip and last-tile epilogue are paid once per group instead of once per conv
+// and the short-K problem's tiles fill the tail of the long one's.
+constexpr int kMaxGroup = 3;
+struct TcProb { int k, dil, row0, kblocks; TcEpi e; };
+struct TcGroup {
+  CUtensorMap tmA[kMaxGroup], tmW[kMaxGroup];
+  TcProb prob[kMaxGroup];
+  int n_prob;
+  TcArgs a;                  // shared shape: n_streams, L, TT, cin, cout, n_tiles, m_tiles, num_tiles (per problem)
+};
+
 template <int BN, int STAGES, int ES, int OCC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * ES, OCC)
-conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcArgs a) {
+conv_gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
+  const TcArgs& a = g.a;
   using SL = Smem2Layout<BN, STAGES>;
   constexpr int BK = 64, SWZ = 128;
   constexpr int TMEM_COLS = 2 * BN;                    // two accumulators: MMAs of tile i+1 overlap the epilogue of tile i
@@ -538,7 +552,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * SL::STAGE_BYTES + 256);
-  stage_bias(s_bias, a.e.bias, a.cout);
+  for (int pi = 0; pi < g.n_prob; ++pi) stage_bias(s_bias + pi * a.cout, g.prob[pi].e.bias, a.cout);
+  const int total_tiles = g.n_prob * a.num_tiles;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -546,8 +561,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int NS = TILE_M / a.TT, TPS = a.L / a.TT;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int pi = 0; pi < g.n_prob; ++pi) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA[pi]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmW[pi]) : "memory");
+    }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * 128 * ES); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -565,20 +582,22 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================================================================== TMA producer (both CTAs: own A rows, own half of B)
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = cluster_id; tile < a.num_tiles; tile += n_clusters) {
+    for (int gt = cluster_id; gt < total_tiles; gt += n_clusters) {
+      const int pi = gt / a.num_tiles, tile = gt - pi * a.num_tiles;
+      const TcProb& pr = g.prob[pi];
       const int nt = tile % a.n_tiles;
       int mt = (tile / a.n_tiles) * 2 + rank;
       if (mt >= a.m_tiles) mt = a.m_tiles - 1;             // odd tile count: the peer computes a duplicate that its epilogue drops
       const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
       int j = 0, c0 = 0;
-      for (int kb = 0; kb < a.kblocks; ++kb) {
+      for (int kb = 0; kb < pr.kblocks; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * SL::STAGE_BYTES;
         uint8_t* sb = sa + SL::A_BYTES;
         if (elect_one_sync()) {
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * SL::STAGE_BYTES);
-          tma_load_3d_2sm(sa, &tmA, &full_bar[s], c0, a.row0 + t0 + j * a.dil, stream0);      // box {64, TT, NS}
-          tma_load_2d_2sm(sb, &tmW, &full_bar[s], kb * BK, nt * BN + rank * (BN / 2));            // box {64, BN / 2}
+          tma_load_3d_2sm(sa, &g.tmA[pi], &full_bar[s], c0, pr.row0 + t0 + j * pr.dil, stream0);     // box {64, TT, NS}
+          tma_load_2d_2sm(sb, &g.tmW[pi], &full_bar[s], kb * BK, nt * BN + rank * (BN / 2));           // box {64, BN / 2}
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
         c0 += BK;
@@ -591,13 +610,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t idesc = make_idesc<BN, 256>();
       int it = 0, s = 0;
       uint32_t ph = 0;
-      for (int tile = cluster_id; tile < a.num_tiles; tile += n_clusters, ++it) {
+      for (int gt = cluster_id; gt < total_tiles; gt += n_clusters, ++it) {
+        const int kblocks = g.prob[gt / a.num_tiles].kblocks;
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[ab], aph ^ 1);                  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
-        for (int kb = 0; kb < a.kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
@@ -620,12 +640,13 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int r = quarter * 32 + lane;
     const int q = r / a.TT, tt = r - q * a.TT;
     int it = 0;
-    for (int tile = cluster_id; tile < a.num_tiles; tile += n_clusters, ++it) {
+    for (int gt = cluster_id; gt < total_tiles; gt += n_clusters, ++it) {
+      const int pi = gt / a.num_tiles, tile = gt - pi * a.num_tiles;
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * 2 + rank;
       const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
-      epilogue_rows<BNE, false>(a.e, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + cpart * BNE),
+      epilogue_rows<BNE, false>(g.prob[pi].e, s_bias + pi * a.cout, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + cpart * BNE),
                                 nt * BN + cpart * BNE, mt < a.m_tiles && stream < a.n_streams, stream, t, &acc_full[ab], aph);
       tc_fence_before();
       mbar_arrive_leader(&acc_empty[ab]);
@@ -917,7 +938,7 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, lon
 }
 
 template <int BN, int STAGES, int ES, int OCC = 1>
-int launch_pair_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, long long m_tiles, cudaStream_t st) {
+int launch_pair_variant(const TcGroup& g0, long long m_tiles, cudaStream_t st) {
   using SL = Smem2Layout<BN, STAGES>;
   static_assert(OCC * 2 * BN <= 512, "TMEM columns of the co-resident CTAs");
   auto kern = conv_gemm_tc2_kernel<BN, STAGES, ES, OCC>;
@@ -930,13 +951,21 @@ int launch_pair_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a
         return 0;
       }))
     return 1;
-  a.m_tiles = (int)m_tiles;
-  a.num_tiles = (int)(((m_tiles + 1) / 2) * a.n_tiles);                  // tiles of 256 rows x BN columns
-  const int clusters = std::min(a.num_tiles, (num_sms() / 2) * OCC);     // persistent: OCC CTA pairs per TPC
-  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "pair<%d,%d,%d,%d> tiles %d clusters %d\n", BN, STAGES, ES, OCC, a.num_tiles, clusters);
-  kern<<<2 * clusters, threads, SL::TOTAL, st>>>(tmA, tmW, a);           // cluster dims (2, 1, 1) are compiled into the kernel
+  TcGroup g = g0;
+  g.a.m_tiles = (int)m_tiles;
+  g.a.num_tiles = (int)(((m_tiles + 1) / 2) * g.a.n_tiles);              // tiles of 256 rows x BN columns, per problem
+  const int clusters = std::min(g.n_prob * g.a.num_tiles, (num_sms() / 2) * OCC);     // persistent: OCC CTA pairs per TPC
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "pair<%d,%d,%d,%d> problems %d tiles %d clusters %d\n", BN, STAGES, ES, OCC, g.n_prob, g.a.num_tiles, clusters);
+  kern<<<2 * clusters, threads, SL::TOTAL, st>>>(g);                     // cluster dims (2, 1, 1) are compiled into the kernel
   CONAN_CHECK_LAUNCH();
   return 0;
+}
+
+int pair_mode();
+int launch_pair_group(const TcGroup& g, int bn2, long long m_tiles, cudaStream_t st) {
+  if (bn2 == 256) return pair_mode() == 4 ? launch_pair_variant<256, 5, 4>(g, m_tiles, st) : launch_pair_variant<256, 5, 2>(g, m_tiles, st);
+  // 128 output channels: two pairs per TPC (3 stages each), so one pair's epilogue runs under the other's MMAs
+  return pair_mode() == 3 ? launch_pair_variant<128, 6, 2>(g, m_tiles, st) : launch_pair_variant<128, 3, 2, 2>(g, m_tiles, st);
 }
 
 int pair_mode() {
@@ -1102,9 +1131,10 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
       a.n_tiles = p.cout / bn2;
       if (get_tensor_map(&tmW, p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, bn2 / 2, 1, BK * 2))
         return 1;
-      if (bn2 == 256) return pair_mode() == 4 ? launch_pair_variant<256, 5, 4>(tmA, tmW, a, m_tiles, st) : launch_pair_variant<256, 5, 2>(tmA, tmW, a, m_tiles, st);
-      // 128 output channels: two pairs per TPC (3 stages each), so one pair's epilogue runs under the other's MMAs
-      return pair_mode() == 3 ? launch_pair_variant<128, 6, 2>(tmA, tmW, a, m_tiles, st) : launch_pair_variant<128, 3, 2, 2>(tmA, tmW, a, m_tiles, st);
+      TcGroup g;
+      g.n_prob = 1; g.tmA[0] = tmA; g.tmW[0] = tmW; g.a = a;
+      g.prob[0] = TcProb{p.k, p.dil, p.row0, a.kblocks, a.e};
+      return launch_pair_group(g, bn2, m_tiles, st);
     }
   }
   if (BK == 64) {
@@ -1136,6 +1166,49 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
   if (BN == 128) return launch_variant<128, 32, 3>(tmA, tmW, a, m_tiles, st);
   if (BN == 64) return launch_variant<64, 32, 3>(tmA, tmW, a, m_tiles, st);
   return launch_variant<32, 32, 3>(tmA, tmW, a, m_tiles, st);
+}
+
+// Up to three independent convs of one shape as ONE launch of the CTA-pair kernel.  Returns -1 (nothing launched) when the group
+// does not qualify: the caller then launches the convs one by one.
+int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t st) {
+  if (G < 2 || G > kMaxGroup || !pair_mode()) return -1;
+  const conan_conv_params_t& p0 = ps[0];
+  for (int i = 0; i < G; ++i) {
+    const conan_conv_params_t& p = ps[i];
+    if (!conv_gemm_tc_eligible(p) || window_eligible(p) || p.x_split || p.cin % 64 != 0 || p.cout % 128 != 0) return -1;
+    if (p.cin != p0.cin || p.cout != p0.cout || p.L != p0.L || p.n_streams != p0.n_streams || p.n_slots != p0.n_slots) return -1;
+  }
+  if (p0.n_streams <= 0) return 0;
+  if (G * p0.cout > 2048) return -1;                                      // bias staging area
+  const int BK = 64, TT = pick_tt(p0.L), NS = TILE_M / TT;
+  const int bn2 = (p0.cout % 256 == 0) ? 256 : (pair_mode() >= 2 ? 128 : 0);
+  if (!bn2) return -1;
+  const long long m_tiles = (long long)((p0.n_streams + NS - 1) / NS) * (p0.L / TT);
+  static const long long min_tiles = [] { const char* e = getenv("CONAN_TC_2CTA_MIN"); return e ? atoll(e) : -1LL; }();
+  if (((m_tiles + 1) / 2) * (p0.cout / bn2) < (min_tiles >= 0 ? min_tiles : (long long)num_sms() / 2)) return -1;
+  // longest K first: the short problem's tiles fill the tail of the long one's
+  int order[kMaxGroup] = {0, 1, 2};
+  std::sort(order, order + G, [&](int x, int y) { return ps[x].k > ps[y].k; });
+  TcGroup g;
+  g.n_prob = G;
+  for (int i = 0; i < G; ++i) {
+    const conan_conv_params_t& p = ps[order[i]];
+    const int Ktot = p.k * p.cin;
+    if (get_tensor_map(&g.tmA[i], p.x, 3, (unsigned long long)p.cin, (unsigned long long)p.x_rows, (unsigned long long)p.n_slots,
+                       (unsigned long long)p.x_row_stride * 2, (unsigned long long)p.x_slot_stride * 2, BK, TT, TILE_M / TT, BK * 2))
+      return 1;
+    if (get_tensor_map(&g.tmW[i], p.w, 2, (unsigned long long)Ktot, (unsigned long long)p.cout, 1, (unsigned long long)Ktot * 2, 0, BK, bn2 / 2, 1, BK * 2))
+      return 1;
+    TcEpi e{p.bias, p.scale, p.act, p.slope, p.res, p.res_slot_stride, p.res_row_stride, p.rowmask, p.mask_slot_stride,
+            p.out_scale, p.y, p.y_slot_stride, p.y_row_stride, p.y_row0, p.accumulate, (__half*)p.y2, p.y2_slot_stride,
+            p.y2_row_stride, p.y2_row0, p.act2, p.slope2, p.acc_scale == 0.f ? 1.f : p.acc_scale, p.y2_split ? p.y2_lo_off : 0,
+            p.res_is_half, p.res_inv_slope, (const __half*)p.res2, p.res2_slot_stride, p.res2_row_stride, p.y_is_half};
+    g.prob[i] = TcProb{p.k, p.dil, p.row0, Ktot / BK, e};
+  }
+  TcArgs& a = g.a;
+  a.n_streams = p0.n_streams; a.L = p0.L; a.TT = TT; a.cin = p0.cin; a.k = 0; a.dil = 0; a.cout = p0.cout; a.row0 = 0;
+  a.kblocks = 0; a.n_tiles = p0.cout / bn2; a.nseg = 1; a.lo_slot_off = 0; a.e = g.prob[0].e;
+  return launch_pair_group(g, bn2, m_tiles, st);
 }
 
 }  // namespace conan

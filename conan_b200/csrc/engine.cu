@@ -337,6 +337,8 @@ void out2_ctx(conan_conv_params_t& p, const Ctx& c, int act2, float slope2) {
 }
 void res_rows(conan_conv_params_t& p, const float* r, int L, int C) { p.res = r; p.res_slot_stride = (long long)L * C; p.res_row_stride = C; }
 
+#define TRY_RC(x) do { if ((x) != 0) return 1; } while (0)
+
 int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t st, bool allow_tc = false) {
   const bool tc = allow_tc && conv_gemm_tc_eligible(p);
   if (p.x_split && !tc) { set_error("internal: split-fp16 operand on a shape the tcgen05 engine cannot run"); return 1; }
@@ -361,6 +363,30 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
   int rc = tc ? launch_conv_gemm_tc(p, st) : launch_conv_gemm_ffma(p, st);
   CONAN_CUDA_OK(cudaEventRecord(r.b, st));
   e->prof.push_back(r);
+  return rc;
+}
+
+// G independent convs of one shape: one grouped launch of the CTA-pair kernel where they qualify, else one launch each
+int run_conv_group(const conan_engine* e, const conan_conv_params_t* ps, int G, cudaStream_t st) {
+  conan_engine::ProfRec r;
+  if (e->profiling) {
+    r.cat = 1; r.flops = 0; r.bytes = 0;
+    for (int i = 0; i < G; ++i) {
+      const conan_conv_params_t& p = ps[i];
+      const double rows_out = (double)p.n_streams * p.L;
+      r.flops += 2.0 * rows_out * p.cout * p.k * p.cin;
+      r.bytes += (double)p.n_streams * (p.L + (p.k - 1) * p.dil) * p.cin * 2.0 + (double)p.cout * p.k * p.cin * 2.0 + rows_out * p.cout * 2.0 * 2.0;
+    }
+    CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
+    CONAN_CUDA_OK(cudaEventRecord(r.a, st));
+  }
+  const int rc = launch_conv_gemm_tc_group(ps, G, st);
+  if (rc < 0) {                                   // not a group for the pair kernel: launch them one by one (profiled individually)
+    if (e->profiling) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (int i = 0; i < G; ++i) TRY_RC(run_conv(e, ps[i], st, true));
+    return 0;
+  }
+  if (e->profiling) { CONAN_CUDA_OK(cudaEventRecord(r.b, st)); e->prof.push_back(r); }
   return rc;
 }
 
@@ -999,59 +1025,82 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
       f.out_scale = 1.0f / (float)c.voc_n_res; f.slope = sl;
       TRY(run_fused(e, f, st));
     }
-    // per-conv path: branch r runs on stream bs (fork / join around the scale; the running sum orders the branches' last convs)
-    // (only on the fp16 fast path: the fp32 / split paths share the residual scratch vXR between branches)
-    const bool multi = !e->vFused[i] && e->vocStreams > 1 && c.voc_n_res > 1 && c.voc_n_res <= 4 && !e->profiling && from_ctx &&
-                       e->vXA[i].is_half == 1;
-    if (multi) {
-      CONAN_CUDA_OK(cudaEventRecord(e->evFork, st));
-      for (int q = 0; q < e->vocStreams - 1; ++q) CONAN_CUDA_OK(cudaStreamWaitEvent(e->branchStream[q], e->evFork, 0));
-    }
-    for (int r = 0; r < c.voc_n_res && !e->vFused[i]; ++r) {
-      const int k = c.voc_res_kernels[r];
-      const int lane = multi ? r % e->vocStreams : 0;
-      cudaStream_t bs = lane == 0 ? st : e->branchStream[lane - 1];
+    // per-conv path.  The three MRF branches are independent chains until their outputs are summed, so the j-th conv of every branch
+    // goes out as ONE grouped launch of the CTA-pair kernel (launch_conv_gemm_tc_group) where the layer qualifies; only the last conv of
+    // each branch stays a launch of its own (the running sum orders them).  Without grouping the branches run on three streams.
+    static const int group_env = [] { const char* v = getenv("CONAN_VOC_GROUP"); return v ? atoi(v) : 1; }();
+    const bool fast16 = from_ctx && e->vXA[i].is_half == 1;
+    const bool grouped = !e->vFused[i] && group_env && fast16 && c.voc_n_res > 1 && c.voc_n_res <= 3 && e->cfg.voc_use_tensor_cores;
+    const bool multi = !e->vFused[i] && !grouped && e->vocStreams > 1 && c.voc_n_res > 1 && c.voc_n_res <= 4 && !e->profiling && fast16;
+    auto make_p1 = [&](int r, int j) {
+      const Ctx& in1 = (j == 0) ? e->vXA[i] : e->vC1[i][r][j];
       std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
-      const float* xj = e->vXS;
-      for (int j = 0; j < c.voc_n_dil; ++j) {
-        const Ctx& in1 = (j == 0) ? e->vXA[i] : e->vC1[i][r][j];
-        auto p1 = conv_on_ctx(e, in1, k, c.voc_res_dilations[j], e->P(q + "c1." + std::to_string(j) + ".w"),
-                              e->F(q + "c1." + std::to_string(j) + ".b"), C, n);
-        out2_ctx(p1, e->vC2[i][r][j], ACT_LRELU, sl);
-        TRY(run_conv(e, p1, bs, e->cfg.voc_use_tensor_cores != 0));
-        auto p2 = conv_on_ctx(e, e->vC2[i][r][j], k, 1, e->P(q + "c2." + std::to_string(j) + ".w"),
-                              e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
-        if (from_ctx) {
-          p2.res = (const float*)in1.at_row(in1.H); p2.res_slot_stride = in1.slot_stride(); p2.res_row_stride = C;
-          p2.res_is_half = in1.is_half ? 1 : 0; p2.res_inv_slope = 1.0f / sl;
-        } else {
-          res_rows(p2, xj, L, C);
-        }
-        if (j + 1 < c.voc_n_dil) {
-          if (!from_ctx) { float* xn = e->vXR[j & 1]; out_rows(p2, xn, L, C); xj = xn; }
-          out2_ctx(p2, e->vC1[i][r][j + 1], ACT_LRELU, sl);
-        } else if (from_ctx && e->vXA[i].is_half == 1) {
-          // MRF average (hifigan_causal.py:324-329) with the running sum carried in fp16: resblock 0 writes it, 1 adds to it,
-          // the last one only reads it and emits lrelu(sum / 3) into the next layer's context
-          if (r > 0) { p2.res2 = e->vSUMh; p2.res2_slot_stride = (long long)L * C; p2.res2_row_stride = C; p2.res2_is_half = 1; }
-          if (r < c.voc_n_res - 1) {
-            p2.y = (float*)e->vSUMh; p2.y_slot_stride = (long long)L * C; p2.y_row_stride = C; p2.y_row0 = 0; p2.y_is_half = 1;
-          } else {
-            p2.out_scale = 1.0f / (float)c.voc_n_res;
-            out2_ctx(p2, next, ACT_LRELU, sl);
-          }
-        } else {
-          out_rows(p2, e->vSUM, L, C);
-          p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)
-          if (r == c.voc_n_res - 1) out2_ctx(p2, next, ACT_LRELU, sl);
-        }
-        const bool last_conv = j + 1 == c.voc_n_dil;
-        if (multi && last_conv && r > 0) CONAN_CUDA_OK(cudaStreamWaitEvent(bs, e->evBranch[r - 1], 0));   // the running sum of branch r - 1
-        TRY(run_conv(e, p2, bs, e->cfg.voc_use_tensor_cores != 0));
-        if (multi && last_conv) CONAN_CUDA_OK(cudaEventRecord(e->evBranch[r], bs));
+      auto p1 = conv_on_ctx(e, in1, c.voc_res_kernels[r], c.voc_res_dilations[j], e->P(q + "c1." + std::to_string(j) + ".w"),
+                            e->F(q + "c1." + std::to_string(j) + ".b"), C, n);
+      out2_ctx(p1, e->vC2[i][r][j], ACT_LRELU, sl);
+      return p1;
+    };
+    const float* xj_of[4] = {e->vXS, e->vXS, e->vXS, e->vXS};
+    auto make_p2 = [&](int r, int j) {
+      const Ctx& in1 = (j == 0) ? e->vXA[i] : e->vC1[i][r][j];
+      std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
+      auto p2 = conv_on_ctx(e, e->vC2[i][r][j], c.voc_res_kernels[r], 1, e->P(q + "c2." + std::to_string(j) + ".w"),
+                            e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
+      if (from_ctx) {
+        p2.res = (const float*)in1.at_row(in1.H); p2.res_slot_stride = in1.slot_stride(); p2.res_row_stride = C;
+        p2.res_is_half = in1.is_half ? 1 : 0; p2.res_inv_slope = 1.0f / sl;
+      } else {
+        res_rows(p2, xj_of[r], L, C);
       }
+      if (j + 1 < c.voc_n_dil) {
+        if (!from_ctx) { float* xn = e->vXR[j & 1]; out_rows(p2, xn, L, C); xj_of[r] = xn; }
+        out2_ctx(p2, e->vC1[i][r][j + 1], ACT_LRELU, sl);
+      } else if (fast16) {
+        // MRF average (hifigan_causal.py:324-329) with the running sum carried in fp16: resblock 0 writes it, 1 adds to it,
+        // the last one only reads it and emits lrelu(sum / 3) into the next layer's context
+        if (r > 0) { p2.res2 = e->vSUMh; p2.res2_slot_stride = (long long)L * C; p2.res2_row_stride = C; p2.res2_is_half = 1; }
+        if (r < c.voc_n_res - 1) {
+          p2.y = (float*)e->vSUMh; p2.y_slot_stride = (long long)L * C; p2.y_row_stride = C; p2.y_row0 = 0; p2.y_is_half = 1;
+        } else {
+          p2.out_scale = 1.0f / (float)c.voc_n_res;
+          out2_ctx(p2, next, ACT_LRELU, sl);
+        }
+      } else {
+        out_rows(p2, e->vSUM, L, C);
+        p2.out_scale = 1.0f / (float)c.voc_n_res; p2.accumulate = r > 0;                  // MRF average (hifigan_causal.py:324-329)
+        if (r == c.voc_n_res - 1) out2_ctx(p2, next, ACT_LRELU, sl);
+      }
+      return p2;
+    };
+    if (grouped) {
+      conan_conv_params_t ps[4];
+      for (int j = 0; j < c.voc_n_dil; ++j) {
+        for (int r = 0; r < c.voc_n_res; ++r) ps[r] = make_p1(r, j);
+        TRY(run_conv_group(e, ps, c.voc_n_res, st));
+        for (int r = 0; r < c.voc_n_res; ++r) ps[r] = make_p2(r, j);
+        if (j + 1 < c.voc_n_dil) TRY(run_conv_group(e, ps, c.voc_n_res, st));
+        else for (int r = 0; r < c.voc_n_res; ++r) TRY(run_conv(e, ps[r], st, true));          // the running sum orders these
+      }
+    } else if (!e->vFused[i]) {
+      if (multi) {
+        CONAN_CUDA_OK(cudaEventRecord(e->evFork, st));
+        for (int q = 0; q < e->vocStreams - 1; ++q) CONAN_CUDA_OK(cudaStreamWaitEvent(e->branchStream[q], e->evFork, 0));
+      }
+      for (int r = 0; r < c.voc_n_res; ++r) {
+        const int lane = multi ? r % e->vocStreams : 0;
+        cudaStream_t bs = lane == 0 ? st : e->branchStream[lane - 1];
+        for (int j = 0; j < c.voc_n_dil; ++j) {
+          auto p1 = make_p1(r, j);
+          TRY(run_conv(e, p1, bs, e->cfg.voc_use_tensor_cores != 0));
+          auto p2 = make_p2(r, j);
+          const bool last_conv = j + 1 == c.voc_n_dil;
+          if (multi && last_conv && r > 0) CONAN_CUDA_OK(cudaStreamWaitEvent(bs, e->evBranch[r - 1], 0));   // the running sum of branch r - 1
+          TRY(run_conv(e, p2, bs, e->cfg.voc_use_tensor_cores != 0));
+          if (multi && last_conv) CONAN_CUDA_OK(cudaEventRecord(e->evBranch[r], bs));
+        }
+      }
+      if (multi) CONAN_CUDA_OK(cudaStreamWaitEvent(st, e->evBranch[c.voc_n_res - 1], 0));             // join (the chain of sums implies every branch)
     }
-    if (multi) CONAN_CUDA_OK(cudaStreamWaitEvent(st, e->evBranch[c.voc_n_res - 1], 0));               // join (the chain of sums implies every branch)
   }
   const int Lw = e->vL[c.voc_n_ups];
   TRY(launch_conv_post_tanh(e->vPOST.p, e->vPOST.is_half ? 1 : 0, e->vPOST.slot_stride(), e->vPOST.C, e->vPOST.H - 6, Lw, e->vPOST.C, 7,
