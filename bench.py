@@ -667,7 +667,7 @@ def run_b200(args):
     np_chunks = [h.numpy() for h in h_chunks]
     np_out = [tuple(t.numpy() for t in o) for o in h_out]
     Ke = max(3, min(K, 20))
-    for i in range(2):
+    for i in range(6):                           # untimed: a ready count above 256 is captured as a graph at its 4th sighting
         eng.step_host(slots, np_chunks[i % n_pool], *np_out[0])
     sync_all()
     # (a) synchronous plugin call, one step at a time
@@ -683,7 +683,7 @@ def run_b200(args):
     e2e_api = "conan_step_host_submit / conan_step_host_wait (two steps in flight: result copy of step i under the compute of step i+1)"
     n_e2e = max(Ke, int(args.e2e_seconds * 1e3 / max(burst_ms / K, 1e-3)))
     try:
-        for i in range(2):                       # untimed: first use of the engine's copy stream and events
+        for i in range(10):                      # untimed: first use of the engine's copy stream and events, graph capture per buffer set
             eng.step_host_wait(eng.step_host_submit(slots, np_chunks[i % 2], *np_out[i % 2]))
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
