@@ -23,11 +23,17 @@ __device__ __forceinline__ int slot_of(const int* slot_ids, int i) { return slot
 constexpr int EMF_MAX_KEYS = 64;   // rc + lc + seg = 56 at the reference config
 constexpr int EMF_MAX_ROWS = 8;
 
+// FIXED: the reference configuration (segment 4, right context 2, left context 50, ring 56 rows, D = 80, 8 heads; LDQ = row stride of
+// qkv) as compile-time constants.  With run-time shapes 45 % of this kernel's instructions were index arithmetic (IMAD / IADD3 / LEA /
+// ISETP / IABS: strides, divisions and modulos by parameters) and it ran issue-bound; the generic instantiation stays for other configs.
+template <bool FIXED, int LDQ>
 __global__ void __launch_bounds__(256, 4)
 emformer_attention_kernel(const float* __restrict__ qkv, float* __restrict__ ring, const int* __restrict__ past_len,
-                          RowView att, const int* __restrict__ slot_ids, int seg, int rc, int lc,
-                          int ring_rows, int D, int heads, int ldq, EmfAttnEpilogue ep, int fused) {
+                          RowView att, const int* __restrict__ slot_ids, int seg_, int rc_, int lc_,
+                          int ring_rows_, int D_, int heads_, int ldq_, EmfAttnEpilogue ep, int fused) {
   extern __shared__ float sm[];
+  const int seg = FIXED ? 4 : seg_, rc = FIXED ? 2 : rc_, lc = FIXED ? 50 : lc_, ring_rows = FIXED ? 56 : ring_rows_;
+  const int D = FIXED ? 80 : D_, heads = FIXED ? 8 : heads_, ldq = FIXED ? LDQ : ldq_;
   const int rows = seg + rc;
   const int slot = slot_of(slot_ids, blockIdx.x);
   const int past = past_len[slot];
@@ -340,17 +346,25 @@ int launch_emformer_attention(const float* qkv, float* kv_ring, const int* past_
   if (ring_rows < lc + seg) { set_error("emformer_attention: ring too short"); return 1; }
   if (ep && (size_t)D * D + (size_t)(seg + rc) * D > (size_t)2 * (rc + lc + seg) * (D + 1)) { set_error("emformer_attention: fused tail does not fit in the K/V staging area"); return 1; }
   size_t sh = ((size_t)2 * (rc + lc + seg) * (D + 1) + (size_t)(seg + rc) * D) * sizeof(float);
-  static DeviceOnce once;
-  if (device_once(once, nullptr, [&](int*) {
-        cudaError_t e = cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(emformer_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-        return 0;
-      }))
-    return 1;
   if (sh > 96 * 1024) { set_error("emformer_attention: shared memory above 96 KB"); return 1; }
-  emformer_attention_kernel<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv,
-                                                ep ? *ep : EmfAttnEpilogue{}, ep ? 1 : 0);
+  const bool fixed = seg == 4 && rc == 2 && lc == 50 && ring_rows == 56 && D == 80 && heads == 8 && (ld_qkv == 256 || ld_qkv == 240);
+  auto launch = [&](auto kern) -> int {
+    static DeviceOnce once;                       // (one per instantiation: the lambda's operator() is a template)
+    if (device_once(once, nullptr, [&](int*) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+          return 0;
+        }))
+      return 1;
+    kern<<<n, 256, sh, st>>>(qkv, kv_ring, past_len, att, slot_ids, seg, rc, lc, ring_rows, D, heads, ld_qkv, ep ? *ep : EmfAttnEpilogue{}, ep ? 1 : 0);
+    return 0;
+  };
+  int rc_l;
+  if (fixed && ld_qkv == 256) rc_l = launch(emformer_attention_kernel<true, 256>);
+  else if (fixed) rc_l = launch(emformer_attention_kernel<true, 240>);
+  else rc_l = launch(emformer_attention_kernel<false, 0>);
+  if (rc_l) return 1;
   CONAN_CHECK_LAUNCH();
   return 0;
 }
