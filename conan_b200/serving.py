@@ -127,7 +127,6 @@ class StreamServer:
         pcm = np.asarray(pcm, dtype=np.float32).reshape(-1)
         room_frames = self._room(sid)
         # samples we may take without producing more frames than there is room for
-        have = 0 if s.pcm is None else s.pcm.shape[0]
         max_new = max(0, (s.frames_made + room_frames) * fe.hop + fe.n_fft - fe.pad - s.pcm_received - 1) if not final else pcm.shape[0]
         take = min(pcm.shape[0], max_new)
         if take < pcm.shape[0]:

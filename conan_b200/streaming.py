@@ -19,7 +19,7 @@ import torch
 
 from . import audio, ckpt, synth
 from .frontend import GpuLogMel
-from .engine import Engine, PARTS_ALL, PARTS_CONAN, PARTS_EMFORMER, PARTS_VOCODER, make_config
+from .engine import Engine, PARTS_CONAN, PARTS_EMFORMER, PARTS_VOCODER, make_config
 from .hparams import hparams, set_hparams
 from .scheduler import ChunkScheduler
 
