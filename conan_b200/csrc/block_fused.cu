@@ -48,8 +48,17 @@ struct BfArgs {
   float scale1; int act;
   float* P; long long M;        // [FS][M][256]
   float acc_scale;
+  // cluster reduction (CL = true): out[row][c] = (sum over the 4 hidden slices + b2[c] + res[row][c]) * mask[row]
+  float* out; const float* res; const float* b2; const float* mask; int ld;
 };
 
+// CL: the 4 CTAs that hold the hidden slices of one row tile form a thread-block cluster; each parks its partial y tile in its own
+// shared memory (the operand ring is dead by then), and CTA q of the cluster sums rows [32 q, 32 q + 32) of the four tiles through
+// distributed shared memory, in slice order (deterministic), adds bias and residual, applies the row mask and writes the finished rows:
+// no partial tensors in HBM and no partial-summing pass in the LayerNorm that follows.
+constexpr int BF_YLD = 260;            // floats per parked row (256 + 4: conflict-free float4 rows)
+
+template <bool CL>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmW2, BfArgs a) {
@@ -240,11 +249,18 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int stream = stream0 + r / a.TT, t = t0 + r % a.TT;
     const bool valid = stream < a.n_streams;
     float* prow = a.P + ((long long)fs * a.M + (long long)stream * a.L + t) * BF_N2 + wg * 128;
+    float* yrow = reinterpret_cast<float*>(smem) + r * BF_YLD + wg * 128;      // CL: parked tile [128][BF_YLD] over the dead ring / h area
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
       uint32_t acc[16];
       tc_ld_32x32b_x16(tmem_base + lane_base + (uint32_t)(256 + wg * 128 + ch * 16), acc);
-      if (valid) {
+      if (CL) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<float4*>(yrow + ch * 16 + 4 * u) =
+              make_float4(__uint_as_float(acc[4 * u]) * a.acc_scale, __uint_as_float(acc[4 * u + 1]) * a.acc_scale,
+                          __uint_as_float(acc[4 * u + 2]) * a.acc_scale, __uint_as_float(acc[4 * u + 3]) * a.acc_scale);
+      } else if (valid) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           *reinterpret_cast<float4*>(prow + ch * 16 + 4 * u) =
@@ -258,6 +274,40 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+  if (CL) {
+    cluster_sync_all();                          // every slice's tile is parked (release / acquire over the cluster)
+    if (warp >= 4) {
+      // CTA `fs` of the cluster finishes rows [32 fs, 32 fs + 32): warp w -> 4 rows, lane -> 8 columns
+      const int w = warp - 4;
+      const float* base = reinterpret_cast<const float*>(smem);
+      uint32_t src[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) src[q] = dsmem_addr(base, (uint32_t)q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = fs * 32 + w * 4 + i;
+        const int stream = stream0 + r / a.TT, t = t0 + r % a.TT;
+        if (stream >= a.n_streams) continue;                        // warp-uniform
+        const long long row = (long long)stream * a.L + t;
+        const uint32_t off = (uint32_t)((r * BF_YLD + lane * 8) * 4);
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                               // slice order: the sum does not depend on which CTA finishes when
+          const float4 u0 = dsmem_ld_f4(src[q] + off), u1 = dsmem_ld_f4(src[q] + off + 16);
+          s0.x += u0.x; s0.y += u0.y; s0.z += u0.z; s0.w += u0.w;
+          s1.x += u1.x; s1.y += u1.y; s1.z += u1.z; s1.w += u1.w;
+        }
+        const float m = a.mask ? a.mask[row] : 1.f;
+        const float4 b0 = *reinterpret_cast<const float4*>(a.b2 + lane * 8), b1 = *reinterpret_cast<const float4*>(a.b2 + lane * 8 + 4);
+        const float4 r0 = *reinterpret_cast<const float4*>(a.res + row * a.ld + lane * 8);
+        const float4 r1 = *reinterpret_cast<const float4*>(a.res + row * a.ld + lane * 8 + 4);
+        float* o = a.out + row * a.ld + lane * 8;
+        *reinterpret_cast<float4*>(o) = make_float4((s0.x + b0.x + r0.x) * m, (s0.y + b0.y + r0.y) * m, (s0.z + b0.z + r0.z) * m, (s0.w + b0.w + r0.w) * m);
+        *reinterpret_cast<float4*>(o + 4) = make_float4((s1.x + b1.x + r1.x) * m, (s1.y + b1.y + r1.y) * m, (s1.z + b1.z + r1.z) * m, (s1.w + b1.w + r1.w) * m);
+      }
+    }
+    cluster_sync_all();                          // no CTA may exit while a partner still reads its tile
   }
 }
 
@@ -299,15 +349,33 @@ int launch_block_fused(const BlockFusedParams& p, cudaStream_t st) {
   a.n_streams = p.n_streams; a.L = p.L; a.TT = TT; a.C1 = p.C1; a.k = p.k; a.row0 = p.row0; a.lo_slot_off = (int)p.lo_slot_off;
   a.hidden = p.hidden; a.n_chunks = p.hidden / BF_CH; a.FS = p.FS; a.K1 = K1; a.b1 = p.b1; a.scale1 = p.scale1; a.act = p.act;
   a.P = p.partials; a.M = (long long)p.n_streams * p.L; a.acc_scale = p.acc_scale;
-  static DeviceOnce once;
-  if (device_once(once, nullptr, [&](int*) {
-        cudaError_t e = cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
-        return 0;
-      }))
-    return 1;
-  block_fused_kernel<<<mt * p.FS, BF_THREADS, BF_SMEM, st>>>(tmX, tmW1, tmW2, a);
+  a.out = p.out; a.res = p.res; a.b2 = p.b2; a.mask = p.mask; a.ld = p.ld;
+  const bool cl = p.out != nullptr;
+  if (cl && (p.FS != 4 || !p.res || !p.b2 || p.ld % 4 != 0)) { set_error("block_fused: the cluster reduction needs 4 hidden slices, a residual and a bias"); return 1; }
+  static_assert(TILE_M * BF_YLD * 4 <= BF_OFF_BAR, "parked tile must fit below the barriers");
+  auto setup = [&](auto kern, DeviceOnce& once) -> int {
+    return device_once(once, nullptr, [&](int*) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 1; }
+      return 0;
+    });
+  };
+  static DeviceOnce once_plain, once_cl;
+  if (!cl) {
+    if (setup(block_fused_kernel<false>, once_plain)) return 1;
+    block_fused_kernel<false><<<mt * p.FS, BF_THREADS, BF_SMEM, st>>>(tmX, tmW1, tmW2, a);
+  } else {
+    if (setup(block_fused_kernel<true>, once_cl)) return 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(mt * p.FS)); cfg.blockDim = dim3(BF_THREADS); cfg.dynamicSmemBytes = BF_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, block_fused_kernel<true>, tmX, tmW1, tmW2, a);
+    if (e != cudaSuccess) { set_error(std::string("cudaLaunchKernelEx(block_fused, cluster 4): ") + cudaGetErrorString(e)); return 1; }
+  }
   CONAN_CHECK_LAUNCH();
   return 0;
 }

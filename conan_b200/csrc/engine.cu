@@ -69,6 +69,7 @@ struct conan_engine {
   std::vector<float> postTapsHost;                 // host copy of conv_post's taps + bias (kernel-parameter fast path)
   bool ffnFused = false; float* eFFP = nullptr;    // fused FFN: partial outputs [split][rows][DP]
   bool blockFused = false; float* bfP = nullptr; long long bfRows = 0;   // fused Conan blocks: partial outputs [split][rows][256]
+  bool blockCluster = true;      // fused Conan blocks sum their hidden slices through distributed shared memory (cluster of 4 CTAs)
   std::vector<float*> eRing;
   // generic step (memory bank M > 0, summary query, partial segments): its own work buffers with seg + rc + 1 rows per stream
   int eM = 0;                                   // max_memory_size
@@ -527,6 +528,7 @@ int allocate_state(conan_engine* e) {
   e->blockFused = e->lin_tc && (fuse_blocks_env < 0 ? c.lin_fuse_blocks != 0 : fuse_blocks_env != 0) && H == 256 && block_fused_eligible(H, c.dec_kernel, 2 * H, H, seg) &&
                   block_fused_eligible(H, 1, 2048, H, seg);
   if (e->blockFused) { e->bfRows = (long long)4 * S * seg; TRY(dalloc(e, &e->bfP, (size_t)e->bfRows * H)); }
+  { const char* v = getenv("CONAN_BLOCK_CLUSTER"); if (v) e->blockCluster = atoi(v) != 0; }
   TRY(dalloc(e, &e->dX0, (size_t)S * seg * H)); TRY(dalloc(e, &e->dQ, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dT1, (size_t)S * seg * H)); TRY(dalloc(e, &e->dO1, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dT2, (size_t)S * seg * H));
@@ -883,7 +885,15 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
     if (e->blockFused) {
       // feed-forward 256 -> 2048 ReLU -> 256 in one kernel; the LayerNorm sums its partials with b2 and the residual
       auto f = block_on_ctx(e, e->cO1, 1, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, 1.f, ACT_RELU, e->P(a + "ffn2.w"), n);
+      const bool cl = e->blockCluster && f.FS == 4;
+      if (cl) { f.out = e->dT2; f.res = e->dO1; f.b2 = e->F(a + "ffn2.b"); f.mask = nullptr; f.ld = H; }   // finished rows, summed in-cluster
       TRY(run_block(e, f, st));
+      if (cl) {
+        TRY(ln_rows(e->dT2, seg, H, 0, e->cPROS[l].new_rows(), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st, nullptr, nullptr, 0,
+                    nullptr, nullptr, view_f32(e->dPROS[l], (long long)seg * H, H)));
+        cur = e->dPROS[l]; curc = &e->cPROS[l];
+        continue;
+      }
       LnArgs ln;
       ln.in = RowView{(void*)e->dO1, (long long)seg * H, H, 0, 0, 0};
       ln.out = e->cPROS[l].new_rows(); ln.out2 = view_f32(e->dPROS[l], (long long)seg * H, H);
@@ -920,7 +930,7 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
     // x = (x + y + b2) * nonpadding from the kernel's partial outputs, writes it back as the residual stream and normalises it
     int fs_prev = 0; std::string d_prev;
     auto ln_assemble = [&](LnArgs& ln) {
-      if (!fs_prev) return;
+      if (!fs_prev || e->blockCluster) return;       // cluster mode: the kernel already wrote the finished residual stream
       ln.part = e->bfP; ln.n_part = fs_prev; ln.part_stride = (long long)n * seg * H; ln.part_ld = H;
       ln.part_bias = e->F(d_prev + "pw.b"); ln.part_res = e->dDECX; ln.part_res_ld = H;
       ln.part_mask = e->dMASKB; ln.part_out = e->dDECX; ln.part_out_ld = H;
@@ -939,6 +949,8 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
         TRY(launch_layernorm(ln, st));
         auto f = block_on_ctx(e, e->cD[b][s], c.dec_kernel, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, 1.0f / sqrtf((float)c.dec_kernel),
                               ACT_GELU, e->P(d + "pw.w"), n);
+        if (e->blockCluster && f.FS == 4) { f.out = e->dDECX; f.res = e->dDECX; f.b2 = e->F(d + "pw.b"); f.mask = e->dMASKB; f.ld = H; }
+        else if (e->blockCluster) { set_error("internal: fused decoder block without 4 hidden slices"); return 1; }
         TRY(run_block(e, f, st));
         fs_prev = f.FS; d_prev = d;
       }

@@ -151,6 +151,9 @@ struct BlockFusedParams {
   const void* w2; int N2;                            // [256][3*hidden] fp16 (x 2^10)
   float* partials; int FS;                           // [FS][n_streams*L][256] fp32
   float acc_scale;
+  // cluster reduction (out != nullptr, FS == 4): the four slices of a row tile are summed through distributed shared memory and the
+  // kernel writes finished rows  out[row][c] = (y + b2[c] + res[row][c]) * mask[row]  (row stride ld; mask may be null; out may be res)
+  float* out; const float* res; const float* b2; const float* mask; int ld;
 };
 bool block_fused_eligible(int C1, int k, int hidden, int N2, int L);
 int block_fused_split(int n_streams, int L, int hidden, long long max_partial_rows);
