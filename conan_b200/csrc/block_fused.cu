@@ -50,6 +50,11 @@ struct BfArgs {
   float acc_scale;
   // cluster reduction (CL = true): out[row][c] = (sum over the 4 hidden slices + b2[c] + res[row][c]) * mask[row]
   float* out; const float* res; const float* b2; const float* mask; int ld;
+  // optional LayerNorm of the finished rows, fused into the cluster epilogue (the reducing warp holds whole rows):
+  //   wmask[row] = (sum_c |x| > 0);  y = ((x * pre - mean) * rstd * g + b) * post  ->  ln_out (GEMM operand rows) [, ln_out2 fp32]
+  const float* ln_g; const float* ln_b; float ln_eps;
+  RowView ln_out; float* ln_out2; int ln_out2_ld;
+  const float* ln_pre; const float* ln_post; float* ln_wmask;
 };
 
 // CL: the 4 CTAs that hold the hidden slices of one row tile form a thread-block cluster; each parks its partial y tile in its own
@@ -303,8 +308,36 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const float4 r0 = *reinterpret_cast<const float4*>(a.res + row * a.ld + lane * 8);
         const float4 r1 = *reinterpret_cast<const float4*>(a.res + row * a.ld + lane * 8 + 4);
         float* o = a.out + row * a.ld + lane * 8;
-        *reinterpret_cast<float4*>(o) = make_float4((s0.x + b0.x + r0.x) * m, (s0.y + b0.y + r0.y) * m, (s0.z + b0.z + r0.z) * m, (s0.w + b0.w + r0.w) * m);
-        *reinterpret_cast<float4*>(o + 4) = make_float4((s1.x + b1.x + r1.x) * m, (s1.y + b1.y + r1.y) * m, (s1.z + b1.z + r1.z) * m, (s1.w + b1.w + r1.w) * m);
+        float v[8] = {(s0.x + b0.x + r0.x) * m, (s0.y + b0.y + r0.y) * m, (s0.z + b0.z + r0.z) * m, (s0.w + b0.w + r0.w) * m,
+                      (s1.x + b1.x + r1.x) * m, (s1.y + b1.y + r1.y) * m, (s1.z + b1.z + r1.z) * m, (s1.w + b1.w + r1.w) * m};
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        if (a.ln_g) {                                               // warp-uniform: the LayerNorm that consumes these rows
+          if (a.ln_wmask) {
+            float sabs = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sabs += fabsf(v[u]);
+            sabs = warp_sum(sabs);
+            if (lane == 0) a.ln_wmask[row] = sabs > 0.f ? 1.f : 0.f;
+          }
+          const float pm = a.ln_pre ? a.ln_pre[row] : 1.f;
+          float sm1 = 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { v[u] *= pm; sm1 += v[u]; }
+          const float mean = warp_sum(sm1) * (1.f / BF_N2);
+          float sq = 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const float d = v[u] - mean; sq += d * d; }
+          const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / BF_N2) + a.ln_eps);
+          const float post = a.ln_post ? a.ln_post[row] : 1.f;
+          const long long oo = (long long)stream * a.ln_out.slot_stride + (long long)(a.ln_out.row0 + t) * a.ln_out.row_stride + lane * 8;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float y = ((v[u] - mean) * rstd * a.ln_g[lane * 8 + u] + a.ln_b[lane * 8 + u]) * post;
+            store_view(a.ln_out, oo + u, y);
+            if (a.ln_out2) a.ln_out2[row * a.ln_out2_ld + lane * 8 + u] = y;
+          }
+        }
       }
     }
     cluster_sync_all();                          // no CTA may exit while a partner still reads its tile
@@ -350,6 +383,9 @@ int launch_block_fused(const BlockFusedParams& p, cudaStream_t st) {
   a.hidden = p.hidden; a.n_chunks = p.hidden / BF_CH; a.FS = p.FS; a.K1 = K1; a.b1 = p.b1; a.scale1 = p.scale1; a.act = p.act;
   a.P = p.partials; a.M = (long long)p.n_streams * p.L; a.acc_scale = p.acc_scale;
   a.out = p.out; a.res = p.res; a.b2 = p.b2; a.mask = p.mask; a.ld = p.ld;
+  a.ln_g = p.ln_g; a.ln_b = p.ln_b; a.ln_eps = p.ln_eps; a.ln_out = p.ln_out; a.ln_out2 = p.ln_out2; a.ln_out2_ld = p.ln_out2_ld;
+  a.ln_pre = p.ln_pre; a.ln_post = p.ln_post; a.ln_wmask = p.ln_wmask;
+  if (p.ln_g && !p.out) { set_error("block_fused: the fused LayerNorm needs the cluster reduction"); return 1; }
   const bool cl = p.out != nullptr;
   if (cl && (p.FS != 4 || !p.res || !p.b2 || p.ld % 4 != 0)) { set_error("block_fused: the cluster reduction needs 4 hidden slices, a residual and a bias"); return 1; }
   static_assert(TILE_M * BF_YLD * 4 <= BF_OFF_BAR, "parked tile must fit below the barriers");

@@ -886,11 +886,14 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
       // feed-forward 256 -> 2048 ReLU -> 256 in one kernel; the LayerNorm sums its partials with b2 and the residual
       auto f = block_on_ctx(e, e->cO1, 1, e->P(a + "ffn1.w"), e->F(a + "ffn1.b"), 2048, 1.f, ACT_RELU, e->P(a + "ffn2.w"), n);
       const bool cl = e->blockCluster && f.FS == 4;
-      if (cl) { f.out = e->dT2; f.res = e->dO1; f.b2 = e->F(a + "ffn2.b"); f.mask = nullptr; f.ld = H; }   // finished rows, summed in-cluster
+      if (cl) {
+        // finished rows, summed in-cluster, and norm2 applied by the reducing warps: operand rows for the next GEMM + an fp32 copy
+        f.out = e->dT2; f.res = e->dO1; f.b2 = e->F(a + "ffn2.b"); f.mask = nullptr; f.ld = H;
+        f.ln_g = e->F(a + "norm2.g"); f.ln_b = e->F(a + "norm2.b"); f.ln_eps = 1e-5f;
+        f.ln_out = e->cPROS[l].new_rows(); f.ln_out2 = e->dPROS[l]; f.ln_out2_ld = H;
+      }
       TRY(run_block(e, f, st));
       if (cl) {
-        TRY(ln_rows(e->dT2, seg, H, 0, e->cPROS[l].new_rows(), e->F(a + "norm2.g"), e->F(a + "norm2.b"), H, seg, n, st, nullptr, nullptr, 0,
-                    nullptr, nullptr, view_f32(e->dPROS[l], (long long)seg * H, H)));
         cur = e->dPROS[l]; curc = &e->cPROS[l];
         continue;
       }
@@ -935,33 +938,52 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
       ln.part_bias = e->F(d_prev + "pw.b"); ln.part_res = e->dDECX; ln.part_res_ld = H;
       ln.part_mask = e->dMASKB; ln.part_out = e->dDECX; ln.part_out_ld = H;
     };
+    const bool fold = e->blockCluster;               // cluster mode: every LayerNorm but the first is applied by the previous block kernel
     for (int b = 0; b < c.dec_blocks; ++b)
       for (int s = 0; s < 2; ++s) {
         std::string d = "conan.dec." + std::to_string(b) + "." + std::to_string(s) + ".";
-        LnArgs ln;
-        ln.in = RowView{(void*)e->dDECX, (long long)seg * H, H, 0, 0, 0};
-        ln.out = e->cD[b][s].new_rows(); ln.out2 = RowView{};
-        ln.gamma = e->F(d + "ln.g"); ln.beta = e->F(d + "ln.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n; ln.slot_ids = nullptr;
-        ln.premask = nullptr; ln.premask_slot_stride = seg; ln.postmask = nullptr; ln.postmask_slot_stride = seg;
-        ln.write_mask = s == 0 ? e->dMASKB : nullptr; ln.write_mask_slot_stride = seg;
-        ln.write_mask2 = (b == 0 && s == 0) ? e->dMASK0 : nullptr;
-        ln_assemble(ln);
-        TRY(launch_layernorm(ln, st));
+        if (!fold || (b == 0 && s == 0)) {
+          LnArgs ln;
+          ln.in = RowView{(void*)e->dDECX, (long long)seg * H, H, 0, 0, 0};
+          ln.out = e->cD[b][s].new_rows(); ln.out2 = RowView{};
+          ln.gamma = e->F(d + "ln.g"); ln.beta = e->F(d + "ln.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n; ln.slot_ids = nullptr;
+          ln.premask = nullptr; ln.premask_slot_stride = seg; ln.postmask = nullptr; ln.postmask_slot_stride = seg;
+          ln.write_mask = s == 0 ? e->dMASKB : nullptr; ln.write_mask_slot_stride = seg;
+          ln.write_mask2 = (b == 0 && s == 0) ? e->dMASK0 : nullptr;
+          ln_assemble(ln);
+          TRY(launch_layernorm(ln, st));
+        }
         auto f = block_on_ctx(e, e->cD[b][s], c.dec_kernel, e->P(d + "conv.w"), e->F(d + "conv.b"), 2 * H, 1.0f / sqrtf((float)c.dec_kernel),
                               ACT_GELU, e->P(d + "pw.w"), n);
         if (e->blockCluster && f.FS == 4) { f.out = e->dDECX; f.res = e->dDECX; f.b2 = e->F(d + "pw.b"); f.mask = e->dMASKB; f.ld = H; }
         else if (e->blockCluster) { set_error("internal: fused decoder block without 4 hidden slices"); return 1; }
+        if (fold) {
+          // the LayerNorm that consumes this block's output: the next block's input norm (its mask is taken at s == 0), or last_norm
+          const bool last = b == c.dec_blocks - 1 && s == 1;
+          f.ln_eps = 1e-5f;
+          if (!last) {
+            const int nb = s == 0 ? b : b + 1, ns = s == 0 ? 1 : 0;
+            std::string dn = "conan.dec." + std::to_string(nb) + "." + std::to_string(ns) + ".";
+            f.ln_g = e->F(dn + "ln.g"); f.ln_b = e->F(dn + "ln.b"); f.ln_out = e->cD[nb][ns].new_rows();
+            f.ln_wmask = ns == 0 ? e->dMASKB : nullptr;
+          } else {
+            f.ln_g = e->F("conan.dec.last_norm.g"); f.ln_b = e->F("conan.dec.last_norm.b"); f.ln_out = e->cP.new_rows();
+            f.ln_pre = e->dMASK0; f.ln_post = e->dMASK0;
+          }
+        }
         TRY(run_block(e, f, st));
         fs_prev = f.FS; d_prev = d;
       }
-    LnArgs ln;
-    ln.in = RowView{(void*)e->dDECX, (long long)seg * H, H, 0, 0, 0};
-    ln.out = e->cP.new_rows(); ln.out2 = RowView{};
-    ln.gamma = e->F("conan.dec.last_norm.g"); ln.beta = e->F("conan.dec.last_norm.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n;
-    ln.slot_ids = nullptr; ln.premask = e->dMASK0; ln.premask_slot_stride = seg; ln.postmask = e->dMASK0; ln.postmask_slot_stride = seg;
-    ln.write_mask = nullptr; ln.write_mask_slot_stride = seg; ln.write_mask2 = nullptr;
-    ln_assemble(ln);
-    TRY(launch_layernorm(ln, st));
+    if (!fold) {
+      LnArgs ln;
+      ln.in = RowView{(void*)e->dDECX, (long long)seg * H, H, 0, 0, 0};
+      ln.out = e->cP.new_rows(); ln.out2 = RowView{};
+      ln.gamma = e->F("conan.dec.last_norm.g"); ln.beta = e->F("conan.dec.last_norm.b"); ln.eps = 1e-5f; ln.C = H; ln.L = seg; ln.n = n;
+      ln.slot_ids = nullptr; ln.premask = e->dMASK0; ln.premask_slot_stride = seg; ln.postmask = e->dMASK0; ln.postmask_slot_stride = seg;
+      ln.write_mask = nullptr; ln.write_mask_slot_stride = seg; ln.write_mask2 = nullptr;
+      ln_assemble(ln);
+      TRY(launch_layernorm(ln, st));
+    }
   } else {
     for (int b = 0; b < c.dec_blocks; ++b)
       for (int s = 0; s < 2; ++s) {

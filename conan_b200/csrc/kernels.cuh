@@ -154,6 +154,11 @@ struct BlockFusedParams {
   // cluster reduction (out != nullptr, FS == 4): the four slices of a row tile are summed through distributed shared memory and the
   // kernel writes finished rows  out[row][c] = (y + b2[c] + res[row][c]) * mask[row]  (row stride ld; mask may be null; out may be res)
   float* out; const float* res; const float* b2; const float* mask; int ld;
+  // optional (cluster mode): the LayerNorm that consumes the finished rows, applied by the reducing warp:
+  //   ln_wmask[row] = (sum_c |x| > 0);  y = ((x * ln_pre[row] - mean) * rstd * ln_g + ln_b) * ln_post[row]  ->  ln_out [, ln_out2 fp32]
+  const float* ln_g; const float* ln_b; float ln_eps;
+  RowView ln_out; float* ln_out2; int ln_out2_ld;
+  const float* ln_pre; const float* ln_post; float* ln_wmask;
 };
 bool block_fused_eligible(int C1, int k, int hidden, int N2, int L);
 int block_fused_split(int n_streams, int L, int hidden, long long max_partial_rows);
