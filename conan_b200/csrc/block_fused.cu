@@ -54,7 +54,7 @@ struct BfArgs {
   //   wmask[row] = (sum_c |x| > 0);  y = ((x * pre - mean) * rstd * g + b) * post  ->  ln_out (GEMM operand rows) [, ln_out2 fp32]
   const float* ln_g; const float* ln_b; float ln_eps;
   RowView ln_out; float* ln_out2; int ln_out2_ld;
-  const float* ln_pre; const float* ln_post; float* ln_wmask;
+  const float* ln_pre; const float* ln_post; float* ln_wmask; const float* ln_add;
 };
 
 // CL: the 4 CTAs that hold the hidden slices of one row tile form a thread-block cluster; each parks its partial y tile in its own
@@ -333,7 +333,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const long long oo = (long long)stream * a.ln_out.slot_stride + (long long)(a.ln_out.row0 + t) * a.ln_out.row_stride + lane * 8;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const float y = ((v[u] - mean) * rstd * a.ln_g[lane * 8 + u] + a.ln_b[lane * 8 + u]) * post;
+            float y = ((v[u] - mean) * rstd * a.ln_g[lane * 8 + u] + a.ln_b[lane * 8 + u]) * post;
+            if (a.ln_add) y += a.ln_add[row * a.ld + lane * 8 + u];
             store_view(a.ln_out, oo + u, y);
             if (a.ln_out2) a.ln_out2[row * a.ln_out2_ld + lane * 8 + u] = y;
           }
@@ -384,7 +385,7 @@ int launch_block_fused(const BlockFusedParams& p, cudaStream_t st) {
   a.P = p.partials; a.M = (long long)p.n_streams * p.L; a.acc_scale = p.acc_scale;
   a.out = p.out; a.res = p.res; a.b2 = p.b2; a.mask = p.mask; a.ld = p.ld;
   a.ln_g = p.ln_g; a.ln_b = p.ln_b; a.ln_eps = p.ln_eps; a.ln_out = p.ln_out; a.ln_out2 = p.ln_out2; a.ln_out2_ld = p.ln_out2_ld;
-  a.ln_pre = p.ln_pre; a.ln_post = p.ln_post; a.ln_wmask = p.ln_wmask;
+  a.ln_pre = p.ln_pre; a.ln_post = p.ln_post; a.ln_wmask = p.ln_wmask; a.ln_add = p.ln_add;
   if (p.ln_g && !p.out) { set_error("block_fused: the fused LayerNorm needs the cluster reduction"); return 1; }
   const bool cl = p.out != nullptr;
   if (cl && (p.FS != 4 || !p.res || !p.b2 || p.ld % 4 != 0)) { set_error("block_fused: the cluster reduction needs 4 hidden slices, a residual and a bias"); return 1; }

@@ -871,6 +871,7 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
   }
   const float* cur = e->dX0;
   const Ctx* curc = &e->cX0;
+  bool pinp_done = false;
   for (int l = 0; l < 2; ++l) {
     std::string a = "conan.align." + std::to_string(l) + ".";
     auto q = conv_on_ctx(e, *curc, 1, 1, e->P(a + "q.w"), e->F(a + "q.b"), H, n);
@@ -891,6 +892,10 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
         f.out = e->dT2; f.res = e->dO1; f.b2 = e->F(a + "ffn2.b"); f.mask = nullptr; f.ld = H;
         f.ln_g = e->F(a + "norm2.g"); f.ln_b = e->F(a + "norm2.b"); f.ln_eps = 1e-5f;
         f.ln_out = e->cPROS[l].new_rows(); f.ln_out2 = e->dPROS[l]; f.ln_out2_ld = H;
+        if (l == 1) {                              // + content rows (Conan.py:168): the pitch predictor's input, no separate add launch
+          f.ln_add = e->dX0; f.ln_out = e->cUV[0].new_rows(); f.ln_out2 = e->dPINP;
+          pinp_done = true;
+        }
       }
       TRY(run_block(e, f, st));
       if (cl) {
@@ -918,7 +923,7 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
     }
     cur = e->dPROS[l]; curc = &e->cPROS[l];
   }
-  TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, nullptr, seg, H, st));  // Conan.py:168
+  if (!pinp_done) TRY(launch_add_rows(e->dX0, cur, e->dPINP, e->cUV[0].new_rows(), n, nullptr, seg, H, st));  // Conan.py:168
   for (int i = 0; i < 5; ++i) {                                                                // uv_predictor convs
     std::string u = "conan.uv." + std::to_string(i) + ".";
     auto p = conv_on_ctx(e, e->cUV[i], c.predictor_kernel, 1, e->P(u + "w"), e->F(u + "b"), 128, n);

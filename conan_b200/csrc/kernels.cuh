@@ -159,6 +159,7 @@ struct BlockFusedParams {
   const float* ln_g; const float* ln_b; float ln_eps;
   RowView ln_out; float* ln_out2; int ln_out2_ld;
   const float* ln_pre; const float* ln_post; float* ln_wmask;
+  const float* ln_add;                               // optional fp32 rows (stride ld) added to y before both stores
 };
 bool block_fused_eligible(int C1, int k, int hidden, int N2, int L);
 int block_fused_split(int n_streams, int L, int hidden, long long max_partial_rows);
