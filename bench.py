@@ -495,6 +495,36 @@ def leg_config2(local, sds, K):
     return res
 
 
+def leg_config1(local, sds):
+    """BASELINE.json configs[0] on the GPU: ONE stream, 80 ms chunks, full pipeline.  Chunk latency two ways: device time of one step
+    (chunk resident in HBM) and the wall clock of the synchronous plugin call conan_step_host (pinned host chunk in, wav + mel + tokens
+    back on the host when it returns): what a single caller waits per chunk.  RTF = latency / 80 ms."""
+    import numpy as np
+    import torch
+    rig = Rig(1, local, sds)
+    for _ in range(40):
+        rig.step()
+    torch.cuda.synchronize(rig.dev)
+    per, total = rig.sustained(100, 5)
+    eng = rig.eng
+    h_chunks = [c.cpu().pin_memory().numpy() for c in rig.chunks]
+    out = (torch.empty(1, eng.hop_out).pin_memory().numpy(), torch.empty(1, SEG, MELS).pin_memory().numpy(),
+           torch.empty(1, SEG, dtype=torch.int32).pin_memory().numpy())
+    slots = np.zeros(1, np.int32)
+    wall = []
+    for i in range(540):
+        t0 = time.perf_counter()
+        eng.step_host(slots, h_chunks[i % rig.n_pool], *out)
+        wall.append((time.perf_counter() - t0) * 1e3)
+    wall = wall[40:]
+    res = {"streams": 1, "device": {"ms_per_step": total / len(per), "latency_ms": _lat(per), "rtf": (total / len(per)) / (CHUNK_S * 1e3)},
+           "host_call": {"api": "conan_step_host (synchronous; wall clock around the call)", "ms_per_chunk": sum(wall) / len(wall),
+                         "latency_ms": _lat(wall), "rtf": (sum(wall) / len(wall)) / (CHUNK_S * 1e3)},
+           "graph_replays": eng.graph_replays}
+    rig.close()
+    return res
+
+
 def leg_config3(local, sds, K):
     """BASELINE.json configs[2]: causal shuffle HiFi-GAN vocoder only, 256 concurrent streams, mel ~ N(0, 0.6^2)."""
     import torch
@@ -791,6 +821,7 @@ def run_b200(args):
         leg("session", leg_session, rig, K)
     rig.close()
     if extras:
+        leg("config1", leg_config1, local, sds)
         leg("config2", leg_config2, local, sds, K)
         leg("config3", leg_config3, local, sds, K)
         leg("fp32_grade", leg_fp32_grade, local, sds, S, K)
