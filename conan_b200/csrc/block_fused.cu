@@ -331,12 +331,37 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / BF_N2) + a.ln_eps);
           const float post = a.ln_post ? a.ln_post[row] : 1.f;
           const long long oo = (long long)stream * a.ln_out.slot_stride + (long long)(a.ln_out.row0 + t) * a.ln_out.row_stride + lane * 8;
+          float y[8];
+          const float4 g0 = *reinterpret_cast<const float4*>(a.ln_g + lane * 8), g1 = *reinterpret_cast<const float4*>(a.ln_g + lane * 8 + 4);
+          const float4 e0 = *reinterpret_cast<const float4*>(a.ln_b + lane * 8), e1 = *reinterpret_cast<const float4*>(a.ln_b + lane * 8 + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float y = ((v[u] - mean) * rstd * a.ln_g[lane * 8 + u] + a.ln_b[lane * 8 + u]) * post;
-            if (a.ln_add) y += a.ln_add[row * a.ld + lane * 8 + u];
-            store_view(a.ln_out, oo + u, y);
-            if (a.ln_out2) a.ln_out2[row * a.ln_out2_ld + lane * 8 + u] = y;
+          for (int u = 0; u < 8; ++u) y[u] = ((v[u] - mean) * rstd * gg[u] + bb[u]) * post;
+          if (a.ln_add) {
+            const float4 a0 = *reinterpret_cast<const float4*>(a.ln_add + row * a.ld + lane * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(a.ln_add + row * a.ld + lane * 8 + 4);
+            y[0] += a0.x; y[1] += a0.y; y[2] += a0.z; y[3] += a0.w; y[4] += a1.x; y[5] += a1.y; y[6] += a1.z; y[7] += a1.w;
+          }
+          if (a.ln_out.is_half == 2 && (oo & 7) == 0 && (a.ln_out.lo_off & 7) == 0) {
+            // split-fp16 operand rows: eight values = one 16-byte store per plane
+            __half2 hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const __half h0 = __float2half_rn(y[2 * u]), h1 = __float2half_rn(y[2 * u + 1]);
+              hi[u] = __halves2half2(h0, h1);
+              lo[u] = __halves2half2(__float2half_rn(y[2 * u] - __half2float(h0)), __float2half_rn(y[2 * u + 1] - __half2float(h1)));
+            }
+            __half* ob = reinterpret_cast<__half*>(a.ln_out.base) + oo;
+            *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(ob + a.ln_out.lo_off) = *reinterpret_cast<const uint4*>(lo);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) store_view(a.ln_out, oo + u, y[u]);
+          }
+          if (a.ln_out2) {
+            float* o2 = a.ln_out2 + row * a.ln_out2_ld + lane * 8;
+            *reinterpret_cast<float4*>(o2) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(o2 + 4) = make_float4(y[4], y[5], y[6], y[7]);
           }
         }
       }

@@ -327,7 +327,7 @@ logmel_kernel(const float* __restrict__ spec, int ld, int bins, const float* __r
 // ------------------------------------------------------------------ ring maintenance
 __global__ void hist_move_kernel(const HistDesc* __restrict__ descs, const int* slot_ids, int scatter) {
   HistDesc d = descs[blockIdx.x];
-  if (scatter && !d.scatter_back) return;
+  if (scatter ? !d.scatter_back : d.scatter_back == 2) return;
   int slot = slot_of(slot_ids, blockIdx.y);
   unsigned char* w = reinterpret_cast<unsigned char*>(d.work) + (long long)blockIdx.y * d.work_stride_bytes + (scatter ? d.new_bytes : 0);
   unsigned char* h = reinterpret_cast<unsigned char*>(d.hist) + (long long)slot * d.hist_bytes;

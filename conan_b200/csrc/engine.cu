@@ -93,6 +93,7 @@ struct conan_engine {
   // fused residual blocks (resblock_fused.cu): per (scale, block) packed weights / biases and the resident history block
   bool vFused[8] = {false, false, false, false, false, false, false, false};
   __half* fW[8][4] = {}; float* fB[8][4] = {}; __half* fHist[8][4] = {}; int fHistRows[8][4] = {};
+  __half* fHistOut[8][4] = {};                     // two-lane fused kernel: compact staging of the new history (scattered with the contexts)
   int vL[9], vC[9];     // rows / channels entering scale i (vL[0] = segment, vC[0] = initial channel)
   // ---- history gather/scatter tables
   HistDesc* histConan = nullptr; int nHistConan = 0;
@@ -393,10 +394,12 @@ int run_conv_group(const conan_engine* e, const conan_conv_params_t* ps, int G, 
 
 // profiling category 4: fused residual block (six convs per launch)
 // CONAN_FUSED_LANES: bit 0 -> two-lane kernel at C = 64, bit 1 -> at C = 32 (default 3: both; 0 = one stream per CTA)
-int fused_launch(const ResblockFusedParams& f, cudaStream_t st) {
+bool fused_two_lanes(int C, int k, const int* dil) {
   static const int lanes = [] { const char* v = getenv("CONAN_FUSED_LANES"); return v ? atoi(v) : 3; }();
-  const bool two = ((f.C == 64 && (lanes & 1)) || (f.C == 32 && (lanes & 2))) && resblock_fused2_smem(f.C, f.k, f.dil) != 0;
-  return two ? launch_resblock_fused2(f, st) : launch_resblock_fused(f, st);
+  return ((C == 64 && (lanes & 1)) || (C == 32 && (lanes & 2))) && resblock_fused2_smem(C, k, dil) != 0;
+}
+int fused_launch(const ResblockFusedParams& f, cudaStream_t st) {
+  return fused_two_lanes(f.C, f.k, f.dil) ? launch_resblock_fused2(f, st) : launch_resblock_fused(f, st);
 }
 
 int run_fused(const conan_engine* e, const ResblockFusedParams& f, cudaStream_t st) {
@@ -549,6 +552,7 @@ int allocate_state(conan_engine* e) {
   TRY(alloc_ctx(e, &e->vPRE, 6, seg, 0, c.voc_use_tensor_cores ? pad32(c.n_mels) : c.n_mels, hf));
   size_t maxLC = 0;
   std::vector<ZeroDesc> fused_zero;
+  std::vector<HistDesc> fused_hist;
   for (int i = 0; i < c.voc_n_ups; ++i) {
     TRY(alloc_ctx(e, &e->vUP[i], c.voc_up_kernels[i] - 1, e->vL[i], 0, e->vC[i], hf));
     int L = e->vL[i + 1], C = e->vC[i + 1];
@@ -567,6 +571,13 @@ int allocate_state(conan_engine* e) {
         e->fHistRows[i][r] = resblock_fused_hist_rows(k, c.voc_res_dilations);
         TRY(dalloc(e, &e->fHist[i][r], (size_t)S * e->fHistRows[i][r] * C));
         fused_zero.push_back(ZeroDesc{e->fHist[i][r], (long long)e->fHistRows[i][r] * C * 2, (long long)e->fHistRows[i][r] * C * 2});
+        if (fused_two_lanes(C, k, c.voc_res_dilations)) {
+          // the kernel leaves the new history in a compact staging block; the vocoder's history scatter moves it to the slot
+          // (so lanes may cut a stream between tiles: nobody overwrites history another lane has yet to read)
+          const int hb = e->fHistRows[i][r] * C * 2;
+          TRY(dalloc(e, &e->fHistOut[i][r], (size_t)S * e->fHistRows[i][r] * C));
+          fused_hist.push_back(HistDesc{e->fHistOut[i][r], (long long)hb, e->fHist[i][r], hb, 0, 2});
+        }
         const size_t wn = (size_t)C * k * C;
         TRY(dalloc(e, &e->fW[i][r], (size_t)kFusedWeightCopies * 6 * wn)); TRY(dalloc(e, &e->fB[i][r], (size_t)6 * C));
         for (int j = 0; j < 3; ++j)
@@ -642,7 +653,7 @@ int allocate_state(conan_engine* e) {
       for (int r = 0; r < c.voc_n_res; ++r)
         for (int j = 0; j < c.voc_n_dil; ++j) { if (j > 0) cs.push_back(&e->vC1[i][r][j]); cs.push_back(&e->vC2[i][r][j]); }
     }
-    TRY(build_tables(cs, {}, &e->histVoc, &e->nHistVoc, &e->zeroVoc, &e->nZeroVoc, fused_zero));
+    TRY(build_tables(cs, fused_hist, &e->histVoc, &e->nHistVoc, &e->zeroVoc, &e->nZeroVoc, fused_zero));
   }
   // ---- session scratch
   e->SB = std::min(S, 64);
@@ -1057,7 +1068,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
       f.C = C; f.L = L; f.k = c.voc_res_kernels[r]; f.n_streams = n; f.slot_ids = ids;
       for (int j = 0; j < 3; ++j) f.dil[j] = c.voc_res_dilations[j];
       f.w = e->fW[i][r]; f.bias = e->fB[i][r]; f.w_copies = fused_weight_copies();
-      f.hist = e->fHist[i][r]; f.hist_slot_stride = (long long)e->fHistRows[i][r] * C;
+      f.hist = e->fHist[i][r]; f.hist_slot_stride = (long long)e->fHistRows[i][r] * C; f.hist_out = e->fHistOut[i][r];
       f.sum_in = r > 0 ? e->vSUMh : nullptr;
       f.sum_out = r < c.voc_n_res - 1 ? e->vSUMh : nullptr;
       if (r == c.voc_n_res - 1) { f.next = next.at_row(next.H); f.next_slot_stride = next.slot_stride(); f.next_row0 = 0; }

@@ -118,6 +118,8 @@ struct ResblockFusedParams {
   const void* w; const float* bias;                 // packed [w_copies][6*C][k*C] fp16 (c1.0, c2.0, c1.1, c2.1, c1.2, c2.2) and [6*C] fp32
   int w_copies;                                     // identical copies of the packed weights (spreads the L2 load of lockstep CTAs)
   void* hist; long long hist_slot_stride;           // resident fp16 history [slot][resblock_fused_hist_rows][C] (elements)
+  void* hist_out = nullptr;                         // two-lane kernel: compact [stream][hist rows][C] staging for the NEW history (the
+                                                    // caller scatters it to the slots afterwards); lets lanes cut streams between tiles
   const void* sum_in; void* sum_out;                // running MRF sum, compact fp16 [i][L][C] (either may be null)
   void* next; long long next_slot_stride; int next_row0;    // following layer's context rows <- lrelu(out_scale * (x_out + sum_in))
   float out_scale, slope;
@@ -173,7 +175,7 @@ int launch_logmel(const float* spec, int ld, int bins, const float* basis_t, int
 // Resident history of a context buffer lives per slot in `hist` [slot, hist_bytes]; the step works on a compact
 // buffer `work` [i, hist_bytes + new_bytes].  gather: hist[slot_i] -> work[i][0 : hist);  scatter: the last
 // hist_bytes of work[i] -> hist[slot_i].  scatter_back = 0 marks read-only session state (style vector).
-struct HistDesc { void* work; long long work_stride_bytes; void* hist; int hist_bytes; int new_bytes; int scatter_back; };
+struct HistDesc { void* work; long long work_stride_bytes; void* hist; int hist_bytes; int new_bytes; int scatter_back; };   // scatter_back 2: scatter only (never gathered)
 int launch_hist_gather(const HistDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st);
 int launch_hist_scatter(const HistDesc* descs_dev, int n_descs, int n, const int* slot_ids, cudaStream_t st);
 struct ZeroDesc { void* base; long long slot_stride_bytes; long long bytes; };

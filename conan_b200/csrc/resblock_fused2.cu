@@ -40,6 +40,9 @@ struct Fused2Args {
   int wt_off, bar_off, bias_off, stages, group;
   const int* slot_ids;
   __half* hist; long long hist_slot_stride;
+  __half* hist_out;            // compact [stream][hist rows][C]: the new history (scattered to the slots after the launch); null: in place
+  int split;                   // lanes take balanced contiguous TILE ranges (a range may start inside a stream); 0: whole streams
+  int n_lanes;
   const float* bias;
   const __half* sum_in; __half* sum_out; long long sum_slot_stride;
   __half* next; long long next_slot_stride; int next_row0;
@@ -52,14 +55,31 @@ __device__ __forceinline__ uint32_t swz2(uint32_t off) {
   return off ^ (((off >> 7) & (ROWB == 128 ? 7u : 3u)) << 4);
 }
 
-// position of one lane in its sequence of (stream, tile, conv) steps; every warp role advances identical copies
+// position of one lane in its sequence of (stream, tile, conv) steps; every warp role advances identical copies.
+// A lane owns a contiguous range of the launch's tiles in (stream, tile) order.  With a.split the ranges are balanced to +-1 tile and
+// may start inside a stream: the lane then first runs the tile BEFORE its range as a warm-up (outputs suppressed).  The six window
+// halos it leaves depend on at most sum_c H[c] <= 128 input rows, all inside that tile, so the range continues with exactly the
+// state a lane that had run the stream from its first tile would hold -- same bits, no dependence on where the cut falls.
 struct LaneIter {
-  int i, t, c, stride, n, tiles;
+  int i, t, c, left, tiles;
+  bool warm;
   uint32_t steps, tiles_done;     // conv steps / tiles completed so far (barrier parities)
-  __device__ __forceinline__ bool done() const { return i >= n; }
+  __device__ __forceinline__ bool done() const { return left <= 0; }
   __device__ __forceinline__ void advance() {
     ++steps;
-    if (++c == R2_CONVS) { c = 0; ++tiles_done; if (++t == tiles) { t = 0; i += stride; } }
+    if (++c == R2_CONVS) { c = 0; ++tiles_done; --left; warm = false; if (++t == tiles) { t = 0; ++i; } }
+  }
+  __device__ __forceinline__ void init(int g, int n_lanes, int n_streams, int tiles_, int split) {
+    tiles = tiles_; c = 0; steps = 0; tiles_done = 0; warm = false;
+    if (split) {
+      const long long T = (long long)n_streams * tiles_;
+      const long long b = T * g / n_lanes, e = T * (g + 1) / n_lanes;
+      i = (int)(b / tiles_); t = (int)(b - (long long)i * tiles_); left = (int)(e - b);
+      if (left > 0 && t > 0) { --t; ++left; warm = true; }
+    } else {
+      const int b = (int)((long long)n_streams * g / n_lanes), e = (int)((long long)n_streams * (g + 1) / n_lanes);
+      i = b; t = 0; left = (e - b) * tiles_;
+    }
   }
 };
 
@@ -110,8 +130,9 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   LaneIter it[2];
 #pragma unroll
   for (int l = 0; l < 2; ++l) {
-    it[l].i = blockIdx.x + l * gridDim.x; it[l].t = 0; it[l].c = 0; it[l].stride = 2 * gridDim.x; it[l].n = a.n_streams;
-    it[l].tiles = a.tiles; it[l].steps = 0; it[l].tiles_done = 0;
+    const int g = (int)blockIdx.x + l * (int)gridDim.x;
+    if (g < a.n_lanes) it[l].init(g, a.n_lanes, a.n_streams, a.tiles, a.split);
+    else { it[l].init(0, 1, 0, a.tiles, 0); }
   }
 
   if (warp == 0) {
@@ -212,28 +233,37 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int l = 0; l < 2; ++l) {
         if (it[l].done()) continue;
         const int c = it[l].c, t = it[l].t, i = it[l].i;
-        const bool last = t == a.tiles - 1;
+        const bool last = t == a.tiles - 1, warm = it[l].warm;
         uint8_t* lbase = smem + l * a.lane_bytes;
         uint8_t* hs = lbase + a.hs_off;
         // conv 0 of a tile depends only on the TMA box, so a fast thread could get here while a slow one still reads window 4
         // (residual of conv 5 of the previous tile) from the buffer that window 1 is about to be written into: wait until every
         // epilogue thread has finished that tile (found with compute-sanitizer's timing, invisible at full speed)
         if (c == 0) mbar_wait_lane0(&tile_done[l], (it[l].tiles_done & 1) ^ 1, 0);
-        if (t == 0 && c == 0) hist_l[l] = a.hist + (long long)(a.slot_ids ? a.slot_ids[i] : i) * a.hist_slot_stride;
-        __half* hist = hist_l[l];
+        if ((t == 0 || warm) && c == 0)
+          hist_l[l] = a.hist_out ? a.hist_out + (long long)i * a.hist_slot_stride
+                                 : a.hist + (long long)(a.slot_ids ? a.slot_ids[i] : i) * a.hist_slot_stride;
+        __half* hist = hist_l[l];                     // where the stream's NEW history goes (its last tile)
+        if (warm && c == 0) {
+          // warm-up tile of a range that starts inside a stream: nothing the lane keeps depends on the halos (see LaneIter); zeros
+          const int hrows = a.hs_row[R2_CONVS - 1] + a.H[R2_CONVS - 1];
+          for (int q = etid; q < hrows * CH; q += EPI) *reinterpret_cast<uint4*>(hs + q * 16) = make_uint4(0, 0, 0, 0);
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        }
         if (t == 0 && c == 0) {
+          const __half* hin = a.hist + (long long)(a.slot_ids ? a.slot_ids[i] : i) * a.hist_slot_stride;
           // new stream on this lane: its resident history becomes the halo store (every MMA of the lane's previous stream is
           // complete: these threads have passed its last accumulator barrier)
           const int hrows = a.hs_row[R2_CONVS - 1] + a.H[R2_CONVS - 1];
           for (int q = etid; q < hrows * CH; q += EPI)
-            *reinterpret_cast<uint4*>(hs + q * 16) = *reinterpret_cast<const uint4*>(hist + (long long)q * 8);
+            *reinterpret_cast<uint4*>(hs + q * 16) = *reinterpret_cast<const uint4*>(hin + (long long)q * 8);
           asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");             // halo store complete before anyone restores from it
         }
         const int cp = c > 0 ? c - 1 : 0, cn = c < R2_CONVS - 1 ? c + 1 : 0;
         const int cm3 = c >= 3 ? c - 3 : c, cp3 = cp >= 3 ? cp - 3 : cp, cn3 = cn >= 3 ? cn - 3 : cn;
         const long long grow = (long long)t * TILE_M + r;
         uint4 sprev[2];
-        if (c == R2_CONVS - 1 && a.sum_in) {
+        if (c == R2_CONVS - 1 && a.sum_in && !warm) {
           const __half* sp = a.sum_in + (long long)i * a.sum_slot_stride + grow * C + col0;
           sprev[0] = *reinterpret_cast<const uint4*>(sp); sprev[1] = *(reinterpret_cast<const uint4*>(sp) + 1);
         }
@@ -292,7 +322,7 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             *reinterpret_cast<uint4*>(dstw + swz2<ROWB>((uint32_t)(row * ROWB + ch * 16))) =
                 *reinterpret_cast<const uint4*>(hs + ((a.hs_row[cn] + row) * CH + ch) * 16);
           }
-        } else {
+        } else if (!warm) {
           if (a.sum_in) {
 #pragma unroll
             for (int h8 = 0; h8 < 2; ++h8) {
@@ -372,9 +402,14 @@ int launch_fused2_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const 
       }))
     return 1;
   // one CTA per SM at C = 64, two at C = 32; two streams in flight per CTA
-  const int grid = std::min((a.n_streams + 1) / 2, num_sms() * (C == 32 ? 2 : 1));
-  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused2<%d,%d> k %d tiles/stream %d smem %zu grid %d\n", C, KT, a.k, a.tiles, smem, grid);
-  kern<<<grid, r2_threads(C), smem, st>>>(tmA, tmW, a);
+  // split: as many lanes as the device holds, unless that leaves under ~3 tiles per lane (every cut costs one warm-up tile)
+  const int max_lanes = 2 * num_sms() * (C == 32 ? 2 : 1);
+  Fused2Args b = a;
+  if (b.split) b.n_lanes = (int)std::max(1LL, std::min((long long)max_lanes, (long long)a.n_streams * a.tiles / 3));
+  else b.n_lanes = std::min(a.n_streams, max_lanes);
+  const int grid = (b.n_lanes + 1) / 2;
+  if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "resblock_fused2<%d,%d> k %d tiles/stream %d smem %zu grid %d lanes %d split %d\n", C, KT, a.k, a.tiles, smem, grid, b.n_lanes, b.split);
+  kern<<<grid, r2_threads(C), smem, st>>>(tmA, tmW, b);
   CONAN_CHECK_LAUNCH();
   return 0;
 }
@@ -444,6 +479,15 @@ int launch_resblock_fused2(const ResblockFusedParams& p, cudaStream_t st) {
   a.bias_off = off; off += R2_CONVS * C * 4;
   const size_t smem = (size_t)off + 1024;
   a.slot_ids = p.slot_ids; a.hist = (__half*)p.hist; a.hist_slot_stride = p.hist_slot_stride; a.bias = p.bias;
+  a.hist_out = (__half*)p.hist_out;
+  {
+    // a range may start inside a stream only if (1) the new history does not land where another lane still reads the old one and
+    // (2) one warm-up tile rebuilds every window halo: sum of the six halos <= 128 rows
+    static const int want = [] { const char* v = getenv("CONAN_FUSED_SPLIT"); return v ? atoi(v) : 1; }();
+    int hsum = 0;
+    for (int c = 0; c < R2_CONVS; ++c) hsum += a.H[c];
+    a.split = want && a.hist_out && hsum <= TILE_M && a.tiles > 1;
+  }
   a.sum_in = (const __half*)p.sum_in; a.sum_out = (__half*)p.sum_out; a.sum_slot_stride = (long long)p.L * C;
   a.next = (__half*)p.next; a.next_slot_stride = p.next_slot_stride; a.next_row0 = p.next_row0;
   a.out_scale = p.out_scale; a.slope = p.slope;
