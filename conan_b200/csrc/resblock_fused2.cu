@@ -61,24 +61,24 @@ __device__ __forceinline__ uint32_t swz2(uint32_t off) {
 // halos it leaves depend on at most sum_c H[c] <= 128 input rows, all inside that tile, so the range continues with exactly the
 // state a lane that had run the stream from its first tile would hold -- same bits, no dependence on where the cut falls.
 struct LaneIter {
-  int i, t, c, left, tiles;
+  int i, t, c, left, tiles, stride;
   bool warm;
   uint32_t steps, tiles_done;     // conv steps / tiles completed so far (barrier parities)
   __device__ __forceinline__ bool done() const { return left <= 0; }
   __device__ __forceinline__ void advance() {
     ++steps;
-    if (++c == R2_CONVS) { c = 0; ++tiles_done; --left; warm = false; if (++t == tiles) { t = 0; ++i; } }
+    if (++c == R2_CONVS) { c = 0; ++tiles_done; --left; warm = false; if (++t == tiles) { t = 0; i += stride; } }
   }
   __device__ __forceinline__ void init(int g, int n_lanes, int n_streams, int tiles_, int split) {
-    tiles = tiles_; c = 0; steps = 0; tiles_done = 0; warm = false;
+    tiles = tiles_; c = 0; steps = 0; tiles_done = 0; warm = false; stride = 1;
     if (split) {
       const long long T = (long long)n_streams * tiles_;
       const long long b = T * g / n_lanes, e = T * (g + 1) / n_lanes;
       i = (int)(b / tiles_); t = (int)(b - (long long)i * tiles_); left = (int)(e - b);
       if (left > 0 && t > 0) { --t; ++left; warm = true; }
-    } else {
-      const int b = (int)((long long)n_streams * g / n_lanes), e = (int)((long long)n_streams * (g + 1) / n_lanes);
-      i = b; t = 0; left = (e - b) * tiles_;
+    } else {                                      // whole streams, round robin: lane g takes streams g, g + n_lanes, ...
+      i = g; t = 0; stride = n_lanes;
+      left = g < n_streams ? (n_streams - g + n_lanes - 1) / n_lanes * tiles_ : 0;
     }
   }
 };
@@ -390,6 +390,12 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 inline int align1k2(int x) { return (x + 1023) & ~1023; }
 
+// CONAN_FUSED_SPLIT: 0 = lanes always take whole streams, 1 (default) = tile ranges when there are fewer streams than lanes, 2 = always
+inline int fused_split_mode() {
+  static const int v = [] { const char* e = getenv("CONAN_FUSED_SPLIT"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 template <int C, int KT>
 int launch_fused2_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const Fused2Args& a, size_t smem, cudaStream_t st) {
   auto kern = resblock_fused2_kernel<C, KT>;
@@ -402,9 +408,13 @@ int launch_fused2_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, const 
       }))
     return 1;
   // one CTA per SM at C = 64, two at C = 32; two streams in flight per CTA
-  // split: as many lanes as the device holds, unless that leaves under ~3 tiles per lane (every cut costs one warm-up tile)
+  // With at least one stream per lane the lanes take whole streams: lanes that run out leave the SM's operand bandwidth to the others,
+  // so the uneven last round costs little (measured: cutting 1024 streams into 296 equal ranges is 5 % SLOWER, every cut pays a
+  // warm-up tile).  With fewer streams than lanes the launch is cut into tile ranges so the idle lanes work: as many lanes as the
+  // device holds, unless that leaves under ~3 tiles per lane.
   const int max_lanes = 2 * num_sms() * (C == 32 ? 2 : 1);
   Fused2Args b = a;
+  b.split = a.split && (a.n_streams < max_lanes || fused_split_mode() == 2);
   if (b.split) b.n_lanes = (int)std::max(1LL, std::min((long long)max_lanes, (long long)a.n_streams * a.tiles / 3));
   else b.n_lanes = std::min(a.n_streams, max_lanes);
   const int grid = (b.n_lanes + 1) / 2;
@@ -483,7 +493,7 @@ int launch_resblock_fused2(const ResblockFusedParams& p, cudaStream_t st) {
   {
     // a range may start inside a stream only if (1) the new history does not land where another lane still reads the old one and
     // (2) one warm-up tile rebuilds every window halo: sum of the six halos <= 128 rows
-    static const int want = [] { const char* v = getenv("CONAN_FUSED_SPLIT"); return v ? atoi(v) : 1; }();
+    const int want = fused_split_mode();
     int hsum = 0;
     for (int c = 0; c < R2_CONVS; ++c) hsum += a.H[c];
     a.split = want && a.hist_out && hsum <= TILE_M && a.tiles > 1;
