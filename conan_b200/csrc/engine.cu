@@ -80,6 +80,9 @@ struct conan_engine {
   int* TOK = nullptr;
   // ---- Conan chunk path
   Ctx cC, cUV[5], cD[8][2], cP;
+  Ctx cPOSTO;                                      // tensor-core path: post-conv rows as the split operand of the mel projection
+  float* dMELP = nullptr; int MP = 0;              // mel rows padded to MP = 96 columns (the projection's padded N)
+  bool melDirect = false;                          // the mel projection also writes the vocoder's input rows (vPRE) in its epilogue
   Ctx cX0, cATT, cO1, cHF, cPROS[2], cDECH;     // GEMM operands without history (fp32 or split fp16)
   float *dX0 = nullptr, *dQ = nullptr, *dT1 = nullptr, *dO1 = nullptr, *dT2 = nullptr,
         *dPROS[2] = {nullptr, nullptr}, *dPINP = nullptr, *dUVH = nullptr, *dDECX = nullptr, *dPOST = nullptr,
@@ -209,7 +212,7 @@ void declare_weights(conan_engine* e) {
     }
   need(e, "conan.dec.last_norm.g", H); need(e, "conan.dec.last_norm.b", H);
   need_linear(e, "conan.dec.post", H, H, c.dec_post_kernel);
-  need(e, "conan.mel_out.w", (size_t)c.n_mels * H); need(e, "conan.mel_out.b", c.n_mels);
+  need_linear(e, "conan.mel_out", c.n_mels, H);
   // session-setup branch
   need(e, "conan.global_in.w", (size_t)H * c.n_mels); need(e, "conan.global_in.b", H);
   for (int b = 0; b < 5; ++b)
@@ -539,6 +542,8 @@ int allocate_state(conan_engine* e) {
   TRY(dalloc(e, &e->dPINP, (size_t)S * seg * H)); TRY(dalloc(e, &e->dUVH, (size_t)S * seg * 128));
   TRY(dalloc(e, &e->dDECX, (size_t)S * seg * H));
   TRY(dalloc(e, &e->dPOST, (size_t)S * seg * H)); TRY(dalloc(e, &e->dMEL, (size_t)S * seg * c.n_mels));
+  e->MP = pad32(c.n_mels);
+  if (e->lin_tc) { TRY(alloc_ctx(e, &e->cPOSTO, 0, seg, 0, H, lt)); TRY(dalloc(e, &e->dMELP, (size_t)S * seg * e->MP)); }
   TRY(dalloc(e, &e->dUVP, (size_t)S * seg * 4)); TRY(dalloc(e, &e->dMASK0, (size_t)S * seg));
   TRY(dalloc(e, &e->dMASKB, (size_t)S * seg));
   TRY(dalloc(e, &e->sSTYLE, (size_t)S * H)); TRY(dalloc(e, &e->sSTYLEW, (size_t)S * H));
@@ -598,6 +603,10 @@ int allocate_state(conan_engine* e) {
     maxLC = std::max(maxLC, (size_t)L * C);
   }
   TRY(alloc_ctx(e, &e->vPOST, 6, e->vL[c.voc_n_ups], 0, e->vC[c.voc_n_ups], hf));
+  {
+    const char* v = getenv("CONAN_MEL_DIRECT");
+    e->melDirect = e->lin_tc && e->vPRE.is_half != 0 && e->vPRE.C == e->MP && c.voc_group <= 0 && !(v && atoi(v) == 0);
+  }
   TRY(dalloc(e, &e->vXS, (size_t)S * maxLC)); TRY(dalloc(e, &e->vXR[0], (size_t)S * maxLC));
   TRY(dalloc(e, &e->vXR[1], (size_t)S * maxLC)); TRY(dalloc(e, &e->vSUM, (size_t)S * maxLC));
   TRY(dalloc(e, &e->vSUMh, (size_t)S * maxLC));
@@ -1018,14 +1027,34 @@ int decoder_step(conan_engine* e, int n, const int* ids, const int* tokens_ext, 
   }
   {
     auto p = conv_on_ctx(e, e->cP, c.dec_post_kernel, 1, e->P("conan.dec.post.w"), e->F("conan.dec.post.b"), H, n);
-    out_rows(p, e->dPOST, seg, H); p.rowmask = e->dMASK0; p.mask_slot_stride = seg;
-    TRY(run_conv(e, p, st, tc));
-    auto m = conv_on_rows(e, e->dPOST, seg, 0, seg, H, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), c.n_mels, n);
-    out_rows(m, e->dMEL, seg, c.n_mels);
-    TRY(run_conv(e, m, st));
+    p.rowmask = e->dMASK0; p.mask_slot_stride = seg;
+    if (tc) {
+      // mel projection on tensor cores too: N padded to 96 (zero weight rows); its epilogue also writes the vocoder's input rows
+      out2_ctx(p, e->cPOSTO, ACT_NONE, 0.f);
+      TRY(run_conv(e, p, st, tc));
+      auto m = conv_on_ctx(e, e->cPOSTO, 1, 1, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), e->MP, n);
+      out_rows(m, e->dMELP, seg, e->MP);
+      if (e->melDirect) out2_ctx(m, e->vPRE, ACT_NONE, 0.f);
+      TRY(run_conv(e, m, st, tc));
+      if (!e->melDirect)
+        CONAN_CUDA_OK(cudaMemcpy2DAsync(e->dMEL, (size_t)c.n_mels * 4, e->dMELP, (size_t)e->MP * 4, (size_t)c.n_mels * 4, (size_t)n * seg,
+                                        cudaMemcpyDeviceToDevice, st));
+    } else {
+      out_rows(p, e->dPOST, seg, H);
+      TRY(run_conv(e, p, st, tc));
+      auto m = conv_on_rows(e, e->dPOST, seg, 0, seg, H, e->P("conan.mel_out.w"), e->F("conan.mel_out.b"), c.n_mels, n);
+      out_rows(m, e->dMEL, seg, c.n_mels);
+      TRY(run_conv(e, m, st));
+    }
   }
   TRY(launch_hist_scatter(e->histConan, e->nHistConan, n, ids, st));
-  if (mel_out) CONAN_CUDA_OK(cudaMemcpyAsync(mel_out, e->dMEL, (size_t)n * seg * c.n_mels * 4, cudaMemcpyDeviceToDevice, st));
+  if (mel_out) {
+    if (tc && e->melDirect)
+      CONAN_CUDA_OK(cudaMemcpy2DAsync(mel_out, (size_t)c.n_mels * 4, e->dMELP, (size_t)e->MP * 4, (size_t)c.n_mels * 4, (size_t)n * seg,
+                                      cudaMemcpyDeviceToDevice, st));
+    else
+      CONAN_CUDA_OK(cudaMemcpyAsync(mel_out, e->dMEL, (size_t)n * seg * c.n_mels * 4, cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 
@@ -1037,7 +1066,7 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
   // from_ctx: x_j is not kept as an fp32 stream; conv c2_j reads it back from lrelu(x_j), the rows conv c1_j consumed
   const bool from_ctx = c.voc_residual_from_ctx != 0;
   TRY(launch_hist_gather(e->histVoc, e->nHistVoc, n, ids, st));
-  TRY(launch_rows_to_view(mel, e->vPRE.new_rows(), n, nullptr, c.segment, c.n_mels, st));
+  if (mel) TRY(launch_rows_to_view(mel, e->vPRE.new_rows(), n, nullptr, c.segment, c.n_mels, st));   // null: the mel projection wrote them
   {
     auto p = conv_on_ctx(e, e->vPRE, 7, 1, e->P("voc.pre.w"), e->F("voc.pre.b"), e->vC[0], n);
     out2_ctx(p, e->vUP[0], ACT_LRELU, sl);
@@ -1162,7 +1191,9 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
 
 int vocoder_step(conan_engine* e, int n, const int* ids, const float* mel_ext, float* wav_out, cudaStream_t st) {
   const conan_config_t& c = e->cfg;
+  const bool direct = !mel_ext && e->melDirect;      // decoder_step of this step already wrote vPRE's new rows
   const float* mel = mel_ext ? mel_ext : e->dMEL;
+  if (direct) return vocoder_pass(e, n, ids, nullptr, wav_out, st);
   // voc_group > 0: the compact buffers [0, G) are reused by consecutive groups of streams, so one group's
   // activations (G x ~5 MB) can stay L2-resident between producer and consumer layers
   const int G = c.voc_group > 0 ? c.voc_group : n;

@@ -178,6 +178,7 @@ def pack_engine_weights(sd_conan: Dict[str, torch.Tensor], sd_emf: Dict[str, tor
         taps = {n: 1 for n in names}
         taps["conan.content_proj"] = cfg.content_kernel
         taps["conan.dec.post"] = cfg.dec_post_kernel
+        taps["conan.mel_out"] = 1
         taps.update({f"conan.uv.{i}": cfg.predictor_kernel for i in range(5)})
         taps.update({f"conan.dec.{b_}.{s_}.conv": cfg.dec_kernel for b_ in range(cfg.dec_blocks) for s_ in range(2)})
         for n, k in taps.items():

@@ -580,6 +580,25 @@ def test_vocoder_fused_resblocks_match_per_conv_path(state_dicts):
         assert snr_db(x.numpy(), y.numpy()) > 70.0
 
 
+@pytest.mark.skipif(NO_TC, reason="CONAN_TEST_NO_TC set")
+def test_vocoder_tile_range_cuts_do_not_change_bits(state_dicts):
+    """The two-lane fused residual-block kernel cuts a launch with fewer streams than lanes into tile ranges; a range that starts
+    inside a stream re-derives the window halos from one warm-up tile (resblock_fused2.cu::LaneIter).  Where the cuts fall depends
+    on the stream count, so the same stream must give the same bits alone (3 lanes), among 7 (other cut positions) and among 300
+    (C = 64 runs whole streams there, C = 32 still cuts), over three chunks so that the staged history hand-over is exercised."""
+    g = torch.Generator().manual_seed(21)
+    one = torch.randn(1, 12, 80, generator=g) * 0.6
+    base = None
+    for n in (1, 7, 300):
+        eng = _engine(state_dicts, max_slots=n)
+        mel = torch.cat([one, torch.randn(n - 1, 12, 80, generator=g) * 0.6]) if n > 1 else one
+        wav = _run_vocoder(eng, mel, list(range(n))[::-1])         # stream 0 lives in the last slot
+        eng.close()
+        if base is None:
+            base = wav[0].clone()
+        assert torch.equal(wav[0], base), n
+
+
 def test_vocoder_group_blocking_is_exact(state_dicts):
     """voc_group (L2 blocking over streams) must not change results."""
     mel = (torch.randn(6, 8, 80, generator=torch.Generator().manual_seed(4)) * 0.6)
