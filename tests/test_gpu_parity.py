@@ -710,7 +710,8 @@ def test_step_graph_replay_is_bitwise_equal_to_eager_launches(state_dicts):
                 ch2.copy_(src[4:6, k * 4:k * 4 + 6])
                 eng.step(ids2, ch2, w2, m2, t2)
                 got.append((w2.cpu(), m2.cpu(), t2.cpu()))
-        assert (eng.graph_replays > 0) == graphs
+        env = os.environ.get("CONAN_STEP_GRAPH")                               # the switch overrides the config (A/B runs)
+        assert (eng.graph_replays > 0) == (graphs if env is None else env != "0")
         outs[graphs] = got
         eng.close()
     for a, b in zip(outs[False], outs[True]):
