@@ -86,6 +86,6 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st);
 bool conv_gemm_tc_eligible(const conan_conv_params_t& p);
 bool conv_gemm_tc_uses_window(const conan_conv_params_t& p);
 // G <= 3 independent convs of one shape as one launch of the CTA-pair kernel; -1 = the group does not qualify (nothing launched)
-int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t st);
+int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t st, bool sum = false);
 
 }  // namespace conan

@@ -322,6 +322,75 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* __res
   else epilogue_rows_k<BN, RES_F32>(e, s_bias, tmem_lane_base, nbase, valid, slot, t, acc_full_bar, parity);
 }
 
+// Epilogue of a SUMMED group (the last convs of the MRF branches of a vocoder scale, accumulated into one TMEM tile):
+//   v = acc + sum_p bias_p + sum_p inverse-LeakyReLU(res_p rows)   (s_bias holds the summed bias; res_p = the fp16 context rows
+//   branch p's conv c1 consumed, i.e. lrelu(x_p));  v *= out_scale;  y2 = lrelu(v) as fp16 rows of the next layer's context
+// (hifigan_causal.py:324-329: the MRF average).  Residual chunks are double-buffered one chunk ahead.
+struct SumRes { const __half* p[3]; float inv[3]; long long ss[3]; int rs[3]; };
+template <int BN>
+__device__ __forceinline__ void epilogue_rows_sum(const TcEpi& eo, const SumRes& sr, const float* __restrict__ s_bias, uint32_t tmem_lane_base,
+                                                  int nbase, bool valid, int slot, int t, uint64_t* acc_full_bar, uint32_t parity) {
+  constexpr int NCH = BN / 16;
+  __half* y2p = (eo.y2 && valid) ? eo.y2 + (long long)slot * eo.y2_slot_stride + (long long)(eo.y2_row0 + t) * eo.y2_row_stride + nbase : nullptr;
+  const float s2 = eo.act2 == ACT_NONE ? 1.f : eo.slope2;
+  const __half* rp[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+    rp[p] = (sr.p[p] && valid) ? sr.p[p] + (long long)slot * sr.ss[p] + (long long)t * sr.rs[p] + nbase : nullptr;
+  uint4 rb[2][3][2];
+  auto fetch = [&](uint4 (&dst)[3][2], int c0) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) dst[p][i] = rp[p] ? *(reinterpret_cast<const uint4*>(rp[p] + c0) + i) : make_uint4(0, 0, 0, 0);
+  };
+  fetch(rb[0], 0);
+  mbar_wait(acc_full_bar, parity);
+  tc_fence_after();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = ch * 16;
+    if (ch + 1 < NCH) fetch(rb[(ch + 1) & 1], c0 + 16);
+    uint32_t acc[16];
+    tc_ld_32x32b_x16(tmem_lane_base + (uint32_t)c0, acc);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nbase + c0 + 4 * i);
+      v[4 * i] = __uint_as_float(acc[4 * i]) + b4.x;
+      v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4.y;
+      v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z;
+      v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const float inv = sr.inv[p];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&rb[ch & 1][p][i]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 a = __half22float2(hp[u]);
+          v[8 * i + 2 * u] += fminf(a.x, a.x * inv);
+          v[8 * i + 2 * u + 1] += fminf(a.y, a.y * inv);
+        }
+      }
+    }
+    if (y2p) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __half2 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float x0 = v[8 * i + 2 * u] * eo.out_scale, x1 = v[8 * i + 2 * u + 1] * eo.out_scale;
+          h[u] = __floats2half2_rn(fmaxf(x0, x0 * s2), fmaxf(x1, x1 * s2));
+        }
+        *(reinterpret_cast<uint4*>(y2p + c0) + i) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+  }
+}
+
 // stage the bias (or zeros) of all `cout` output channels in shared memory, once per CTA
 __device__ __forceinline__ void stage_bias(float* s_bias, const float* bias, int cout) {
   for (int i = threadIdx.x; i < cout; i += blockDim.x) s_bias[i] = bias ? bias[i] : 0.f;
@@ -537,7 +606,9 @@ struct TcGroup {
   TcArgs a;                  // shared shape: n_streams, L, TT, cin, cout, n_tiles, m_tiles, num_tiles (per problem)
 };
 
-template <int BN, int STAGES, int ES, int OCC>
+// SUM: the problems are not independent tiles but terms of ONE output (same rows, same output channels): every tile runs the k-blocks
+// of all problems into the same accumulator and one epilogue adds the summed bias and every problem's residual.
+template <int BN, int STAGES, int ES, int OCC, bool SUM = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * ES, OCC)
 conv_gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
   const TcArgs& a = g.a;
@@ -552,8 +623,16 @@ conv_gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * SL::STAGE_BYTES + 256);
-  for (int pi = 0; pi < g.n_prob; ++pi) stage_bias(s_bias + pi * a.cout, g.prob[pi].e.bias, a.cout);
-  const int total_tiles = g.n_prob * a.num_tiles;
+  if (SUM) {
+    for (int i = threadIdx.x; i < a.cout; i += blockDim.x) {
+      float b = 0.f;
+      for (int pi = 0; pi < g.n_prob; ++pi) b += g.prob[pi].e.bias ? g.prob[pi].e.bias[i] : 0.f;
+      s_bias[i] = b;
+    }
+  } else {
+    for (int pi = 0; pi < g.n_prob; ++pi) stage_bias(s_bias + pi * a.cout, g.prob[pi].e.bias, a.cout);
+  }
+  const int total_tiles = SUM ? a.num_tiles : g.n_prob * a.num_tiles;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -583,25 +662,28 @@ conv_gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
     int s = 0;
     uint32_t ph = 0;
     for (int gt = cluster_id; gt < total_tiles; gt += n_clusters) {
-      const int pi = gt / a.num_tiles, tile = gt - pi * a.num_tiles;
-      const TcProb& pr = g.prob[pi];
+      const int p_lo = SUM ? 0 : gt / a.num_tiles, p_hi = SUM ? g.n_prob : p_lo + 1;
+      const int tile = SUM ? gt : gt - p_lo * a.num_tiles;
       const int nt = tile % a.n_tiles;
       int mt = (tile / a.n_tiles) * 2 + rank;
       if (mt >= a.m_tiles) mt = a.m_tiles - 1;             // odd tile count: the peer computes a duplicate that its epilogue drops
       const int stream0 = (mt / TPS) * NS, t0 = (mt % TPS) * a.TT;
-      int j = 0, c0 = 0;
-      for (int kb = 0; kb < pr.kblocks; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * SL::STAGE_BYTES;
-        uint8_t* sb = sa + SL::A_BYTES;
-        if (elect_one_sync()) {
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * SL::STAGE_BYTES);
-          tma_load_3d_2sm(sa, &g.tmA[pi], &full_bar[s], c0, pr.row0 + t0 + j * pr.dil, stream0);     // box {64, TT, NS}
-          tma_load_2d_2sm(sb, &g.tmW[pi], &full_bar[s], kb * BK, nt * BN + rank * (BN / 2));           // box {64, BN / 2}
+      for (int pi = p_lo; pi < p_hi; ++pi) {
+        const TcProb& pr = g.prob[pi];
+        int j = 0, c0 = 0;
+        for (int kb = 0; kb < pr.kblocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * SL::STAGE_BYTES;
+          uint8_t* sb = sa + SL::A_BYTES;
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * SL::STAGE_BYTES);
+            tma_load_3d_2sm(sa, &g.tmA[pi], &full_bar[s], c0, pr.row0 + t0 + j * pr.dil, stream0);     // box {64, TT, NS}
+            tma_load_2d_2sm(sb, &g.tmW[pi], &full_bar[s], kb * BK, nt * BN + rank * (BN / 2));           // box {64, BN / 2}
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+          c0 += BK;
+          if (c0 == a.cin) { c0 = 0; ++j; }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-        c0 += BK;
-        if (c0 == a.cin) { c0 = 0; ++j; }
       }
     }
   } else if (warp == 1) {
@@ -611,7 +693,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
       int it = 0, s = 0;
       uint32_t ph = 0;
       for (int gt = cluster_id; gt < total_tiles; gt += n_clusters, ++it) {
-        const int kblocks = g.prob[gt / a.num_tiles].kblocks;
+        int kblocks = 0;
+        if (SUM) { for (int pi = 0; pi < g.n_prob; ++pi) kblocks += g.prob[pi].kblocks; }
+        else kblocks = g.prob[gt / a.num_tiles].kblocks;
         const int ab = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[ab], aph ^ 1);                  // both CTAs' epilogues have drained this accumulator
@@ -640,12 +724,26 @@ conv_gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
     const int r = quarter * 32 + lane;
     const int q = r / a.TT, tt = r - q * a.TT;
     int it = 0;
+    SumRes sr;
+    if (SUM) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const bool on = p < g.n_prob && g.prob[p].e.res;
+        sr.p[p] = on ? reinterpret_cast<const __half*>(g.prob[p].e.res) : nullptr;
+        sr.inv[p] = on && g.prob[p].e.res_inv_slope != 0.f ? g.prob[p].e.res_inv_slope : 1.f;
+        sr.ss[p] = on ? g.prob[p].e.res_slot_stride : 0; sr.rs[p] = on ? g.prob[p].e.res_row_stride : 0;
+      }
+    }
     for (int gt = cluster_id; gt < total_tiles; gt += n_clusters, ++it) {
-      const int pi = gt / a.num_tiles, tile = gt - pi * a.num_tiles;
+      const int pi = SUM ? g.n_prob - 1 : gt / a.num_tiles, tile = SUM ? gt : gt - pi * a.num_tiles;
       const int ab = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int nt = tile % a.n_tiles, mt = (tile / a.n_tiles) * 2 + rank;
       const int stream = (mt / TPS) * NS + q, t = (mt % TPS) * a.TT + tt;
+      if (SUM)
+        epilogue_rows_sum<BNE>(g.prob[pi].e, sr, s_bias, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + cpart * BNE),
+                               nt * BN + cpart * BNE, mt < a.m_tiles && stream < a.n_streams, stream, t, &acc_full[ab], aph);
+      else
       epilogue_rows<BNE, false>(g.prob[pi].e, s_bias + pi * a.cout, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + cpart * BNE),
                                 nt * BN + cpart * BNE, mt < a.m_tiles && stream < a.n_streams, stream, t, &acc_full[ab], aph);
       tc_fence_before();
@@ -937,11 +1035,11 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW, TcArgs a, lon
   return 0;
 }
 
-template <int BN, int STAGES, int ES, int OCC = 1>
+template <int BN, int STAGES, int ES, int OCC = 1, bool SUM = false>
 int launch_pair_variant(const TcGroup& g0, long long m_tiles, cudaStream_t st) {
   using SL = Smem2Layout<BN, STAGES>;
   static_assert(OCC * 2 * BN <= 512, "TMEM columns of the co-resident CTAs");
-  auto kern = conv_gemm_tc2_kernel<BN, STAGES, ES, OCC>;
+  auto kern = conv_gemm_tc2_kernel<BN, STAGES, ES, OCC, SUM>;
   constexpr int threads = 64 + 128 * ES;
   static DeviceOnce once;
   if (device_once(once, nullptr, [&](int*) {
@@ -954,7 +1052,7 @@ int launch_pair_variant(const TcGroup& g0, long long m_tiles, cudaStream_t st) {
   TcGroup g = g0;
   g.a.m_tiles = (int)m_tiles;
   g.a.num_tiles = (int)(((m_tiles + 1) / 2) * g.a.n_tiles);              // tiles of 256 rows x BN columns, per problem
-  const int clusters = std::min(g.n_prob * g.a.num_tiles, (num_sms() / 2) * OCC);     // persistent: OCC CTA pairs per TPC
+  const int clusters = std::min((SUM ? 1 : g.n_prob) * g.a.num_tiles, (num_sms() / 2) * OCC);     // persistent: OCC CTA pairs per TPC
   if (getenv("CONAN_TC_VERBOSE")) fprintf(stderr, "pair<%d,%d,%d,%d> problems %d tiles %d clusters %d\n", BN, STAGES, ES, OCC, g.n_prob, g.a.num_tiles, clusters);
   kern<<<2 * clusters, threads, SL::TOTAL, st>>>(g);                     // cluster dims (2, 1, 1) are compiled into the kernel
   CONAN_CHECK_LAUNCH();
@@ -962,7 +1060,11 @@ int launch_pair_variant(const TcGroup& g0, long long m_tiles, cudaStream_t st) {
 }
 
 int pair_mode();
-int launch_pair_group(const TcGroup& g, int bn2, long long m_tiles, cudaStream_t st) {
+int launch_pair_group(const TcGroup& g, int bn2, long long m_tiles, cudaStream_t st, bool sum = false) {
+  if (sum) {
+    if (bn2 == 256) return launch_pair_variant<256, 5, 2, 1, true>(g, m_tiles, st);
+    return launch_pair_variant<128, 3, 2, 2, true>(g, m_tiles, st);
+  }
   if (bn2 == 256) return pair_mode() == 4 ? launch_pair_variant<256, 5, 4>(g, m_tiles, st) : launch_pair_variant<256, 5, 2>(g, m_tiles, st);
   // 128 output channels: two pairs per TPC (3 stages each), so one pair's epilogue runs under the other's MMAs
   return pair_mode() == 3 ? launch_pair_variant<128, 6, 2>(g, m_tiles, st) : launch_pair_variant<128, 3, 2, 2>(g, m_tiles, st);
@@ -1170,9 +1272,20 @@ int launch_conv_gemm_tc(const conan_conv_params_t& p, cudaStream_t st) {
 
 // Up to three independent convs of one shape as ONE launch of the CTA-pair kernel.  Returns -1 (nothing launched) when the group
 // does not qualify: the caller then launches the convs one by one.
-int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t st) {
+int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t st, bool sum) {
   if (G < 2 || G > kMaxGroup || !pair_mode()) return -1;
   const conan_conv_params_t& p0 = ps[0];
+  if (sum) {
+    // terms of one output: fp16 context residuals only, no per-term outputs; ps[G - 1] carries the output (y2, out_scale, slope2)
+    for (int i = 0; i < G; ++i) {
+      const conan_conv_params_t& p = ps[i];
+      if (p.y || p.res2 || p.rowmask || p.accumulate || p.act != ACT_NONE || p.scale != 1.f || (p.res && !p.res_is_half) ||
+          (p.acc_scale != 0.f && p.acc_scale != 1.f) || (i < G - 1 && p.y2))
+        return -1;
+    }
+    const conan_conv_params_t& pl = ps[G - 1];
+    if (!pl.y2 || !pl.y2_is_half || pl.y2_split || !(pl.act2 == ACT_NONE || (pl.act2 == ACT_LRELU && pl.slope2 > 0.f && pl.slope2 < 1.f))) return -1;
+  }
   for (int i = 0; i < G; ++i) {
     const conan_conv_params_t& p = ps[i];
     if (!conv_gemm_tc_eligible(p) || window_eligible(p) || p.x_split || p.cin % 64 != 0 || p.cout % 128 != 0) return -1;
@@ -1185,10 +1298,12 @@ int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t
   if (!bn2) return -1;
   const long long m_tiles = (long long)((p0.n_streams + NS - 1) / NS) * (p0.L / TT);
   static const long long min_tiles = [] { const char* e = getenv("CONAN_TC_2CTA_MIN"); return e ? atoll(e) : -1LL; }();
-  if (((m_tiles + 1) / 2) * (p0.cout / bn2) < (min_tiles >= 0 ? min_tiles : (long long)num_sms() / 2)) return -1;
+  // (a summed group takes this kernel at every size: the individual launches round the running sum to fp16 between the terms, so
+  // switching by stream count would make a stream's bits depend on how many others are ready)
+  if (!sum && ((m_tiles + 1) / 2) * (p0.cout / bn2) < (min_tiles >= 0 ? min_tiles : (long long)num_sms() / 2)) return -1;
   // longest K first: the short problem's tiles fill the tail of the long one's
   int order[kMaxGroup] = {0, 1, 2};
-  std::sort(order, order + G, [&](int x, int y) { return ps[x].k > ps[y].k; });
+  if (!sum) std::sort(order, order + G, [&](int x, int y) { return ps[x].k > ps[y].k; });
   TcGroup g;
   g.n_prob = G;
   for (int i = 0; i < G; ++i) {
@@ -1208,7 +1323,7 @@ int launch_conv_gemm_tc_group(const conan_conv_params_t* ps, int G, cudaStream_t
   TcArgs& a = g.a;
   a.n_streams = p0.n_streams; a.L = p0.L; a.TT = TT; a.cin = p0.cin; a.k = 0; a.dil = 0; a.cout = p0.cout; a.row0 = 0;
   a.kblocks = 0; a.n_tiles = p0.cout / bn2; a.nseg = 1; a.lo_slot_off = 0; a.e = g.prob[0].e;
-  return launch_pair_group(g, bn2, m_tiles, st);
+  return launch_pair_group(g, bn2, m_tiles, st, sum);
 }
 
 }  // namespace conan

@@ -372,7 +372,8 @@ int run_conv(const conan_engine* e, const conan_conv_params_t& p, cudaStream_t s
 }
 
 // G independent convs of one shape: one grouped launch of the CTA-pair kernel where they qualify, else one launch each
-int run_conv_group(const conan_engine* e, const conan_conv_params_t* ps, int G, cudaStream_t st) {
+// sum: the problems are terms of one output (launch_conv_gemm_tc_group's sum mode); returns -1 if the group does not qualify
+int run_conv_group(const conan_engine* e, const conan_conv_params_t* ps, int G, cudaStream_t st, bool sum = false) {
   conan_engine::ProfRec r;
   if (e->profiling) {
     r.cat = 1; r.flops = 0; r.bytes = 0;
@@ -385,9 +386,10 @@ int run_conv_group(const conan_engine* e, const conan_conv_params_t* ps, int G, 
     CONAN_CUDA_OK(cudaEventCreate(&r.a)); CONAN_CUDA_OK(cudaEventCreate(&r.b));
     CONAN_CUDA_OK(cudaEventRecord(r.a, st));
   }
-  const int rc = launch_conv_gemm_tc_group(ps, G, st);
+  const int rc = launch_conv_gemm_tc_group(ps, G, st, sum);
   if (rc < 0) {                                   // not a group for the pair kernel: launch them one by one (profiled individually)
     if (e->profiling) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (sum) return -1;
     for (int i = 0; i < G; ++i) TRY_RC(run_conv(e, ps[i], st, true));
     return 0;
   }
@@ -1157,8 +1159,29 @@ int vocoder_pass(conan_engine* e, int n, const int* ids, const float* mel, float
         for (int r = 0; r < c.voc_n_res; ++r) ps[r] = make_p1(r, j);
         TRY(run_conv_group(e, ps, c.voc_n_res, st));
         for (int r = 0; r < c.voc_n_res; ++r) ps[r] = make_p2(r, j);
-        if (j + 1 < c.voc_n_dil) TRY(run_conv_group(e, ps, c.voc_n_res, st));
-        else for (int r = 0; r < c.voc_n_res; ++r) TRY(run_conv(e, ps[r], st, true));          // the running sum orders these
+        if (j + 1 < c.voc_n_dil) { TRY(run_conv_group(e, ps, c.voc_n_res, st)); continue; }
+        // last convs of the branches: x_out = sum_r (c2_r(.) + x_r) / n_res is ONE accumulator -- every tile runs the k-blocks of all
+        // branches into it, the epilogue adds the biases and the branches' residual rows and emits lrelu(sum / n_res) into the next
+        // layer's context (no running-sum tensor, one launch instead of n_res ordered ones)
+        static const int sum_env = [] { const char* v = getenv("CONAN_VOC_SUM"); return v ? atoi(v) : 1; }();
+        int rc_sum = -1;
+        if (sum_env) {
+          conan_conv_params_t qs[4];
+          for (int r = 0; r < c.voc_n_res; ++r) {
+            const Ctx& in1 = e->vC1[i][r][j];
+            std::string q = "voc.res." + std::to_string(i) + "." + std::to_string(r) + ".";
+            qs[r] = conv_on_ctx(e, e->vC2[i][r][j], c.voc_res_kernels[r], 1, e->P(q + "c2." + std::to_string(j) + ".w"),
+                                e->F(q + "c2." + std::to_string(j) + ".b"), C, n);
+            qs[r].res = (const float*)in1.at_row(in1.H); qs[r].res_slot_stride = in1.slot_stride(); qs[r].res_row_stride = C;
+            qs[r].res_is_half = 1; qs[r].res_inv_slope = 1.0f / sl;
+          }
+          qs[c.voc_n_res - 1].out_scale = 1.0f / (float)c.voc_n_res;
+          out2_ctx(qs[c.voc_n_res - 1], next, ACT_LRELU, sl);
+          rc_sum = j > 0 ? run_conv_group(e, qs, c.voc_n_res, st, true) : -1;
+          if (rc_sum > 0) return rc_sum;
+        }
+        if (rc_sum < 0)
+          for (int r = 0; r < c.voc_n_res; ++r) TRY(run_conv(e, ps[r], st, true));          // the running sum orders these
       }
     } else if (!e->vFused[i]) {
       if (multi) {
