@@ -41,6 +41,7 @@ struct Fused2Args {
   const int* slot_ids;
   __half* hist; long long hist_slot_stride;
   __half* hist_out;            // compact [stream][hist rows][C]: the new history (scattered to the slots after the launch); null: in place
+  int share_w;                 // a conv's taps fit the weight ring: while both lanes are active they use ONE copy of the stream
   int split;                   // lanes take balanced contiguous TILE ranges (a range may start inside a stream); 0: whole streams
   int n_lanes;
   const float* bias;
@@ -154,22 +155,26 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 2) {
     // ===================================================================== weight producer: taps in the MMA warp's global order
+    // (share_w: while both lanes are active they run the same conv index back to back, so lane 1 re-uses the stages lane 0 consumed)
     int s = 0;
     uint32_t ph = 1;
     while (!it[0].done() || !it[1].done()) {
+      const bool both = a.share_w && !it[0].done() && !it[1].done();
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
         if (it[l].done()) continue;
         const int c = it[l].c;
-        for (int j0 = 0; j0 < a.k; j0 += GROUP) {
-          const int nt = min(GROUP, a.k - j0);
-          mbar_wait_lane0(&w_empty[s], ph, 32);
-          if (elect_one_sync()) {
-            mbar_expect_tx(&w_full[s], (uint32_t)(nt * TAPB));
-            uint8_t* dst = smem + a.wt_off + s * GROUP * TAPB;
-            for (int j = 0; j < nt; ++j) tma_load_2d(dst + j * TAPB, &tmW, &w_full[s], (j0 + j) * C, c * C);
+        if (!(both && l == 1)) {
+          for (int j0 = 0; j0 < a.k; j0 += GROUP) {
+            const int nt = min(GROUP, a.k - j0);
+            mbar_wait_lane0(&w_empty[s], ph, 32);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&w_full[s], (uint32_t)(nt * TAPB));
+              uint8_t* dst = smem + a.wt_off + s * GROUP * TAPB;
+              for (int j = 0; j < nt; ++j) tma_load_2d(dst + j * TAPB, &tmW, &w_full[s], (j0 + j) * C, c * C);
+            }
+            if (++s == a.stages) { s = 0; ph ^= 1; }
           }
-          if (++s == a.stages) { s = 0; ph ^= 1; }
         }
         it[l].advance();
       }
@@ -185,10 +190,15 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint32_t wph = 0;
     const int kk_taps = KT > 0 ? KT : a.k;
     while (!it[0].done() || !it[1].done()) {
+      const bool both = a.share_w && !it[0].done() && !it[1].done();
+      const int s_round = s;
+      const uint32_t wph_round = wph;
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
         if (it[l].done()) continue;
         const int c = it[l].c;
+        const bool keep = both && l == 0;          // lane 1 runs the same conv next: leave the stages full
+        if (both && l == 1) { s = s_round; wph = wph_round; }
         if (c == 0) mbar_wait_warp(&a_full[l], it[l].tiles_done & 1);
         else mbar_wait_warp(&win_ready[l * R2_CONVS + c], it[l].tiles_done & 1);
         tc_fence_after();
@@ -211,7 +221,7 @@ resblock_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               ad += tap_step; bd += (TAPB >> 4);
             }
           }
-          if (elect_one_sync()) tc_commit(&w_empty[s]);
+          if (!keep && elect_one_sync()) tc_commit(&w_empty[s]);
           if (++s == a.stages) { s = 0; wph ^= 1; }
         }
         if (elect_one_sync()) tc_commit(&acc_full[l * 2 + ab]);
@@ -490,6 +500,11 @@ int launch_resblock_fused2(const ResblockFusedParams& p, cudaStream_t st) {
   const size_t smem = (size_t)off + 1024;
   a.slot_ids = p.slot_ids; a.hist = (__half*)p.hist; a.hist_slot_stride = p.hist_slot_stride; a.bias = p.bias;
   a.hist_out = (__half*)p.hist_out;
+  {
+    // one copy of the weight stream for both lanes when a conv's tap groups fit the ring with a stage to spare for the prefetch
+    static const int share_env = [] { const char* v = getenv("CONAN_FUSED_SHARE_W"); return v ? atoi(v) : 1; }();
+    a.share_w = share_env && (p.k + a.group - 1) / a.group < a.stages;
+  }
   {
     // a range may start inside a stream only if (1) the new history does not land where another lane still reads the old one and
     // (2) one warm-up tile rebuilds every window halo: sum of the six halos <= 128 rows
